@@ -1,0 +1,93 @@
+// Shared host/device definitions for the B200 CycleGAN hot path.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdexcept>
+#include <string>
+
+namespace cgb {
+
+typedef __nv_bfloat16 bf16;
+
+// Thread-local last-error string, surfaced through the C ABI (cgb_last_error()).
+void set_last_error(const std::string& msg);
+
+struct Error : public std::runtime_error {
+  explicit Error(const std::string& m) : std::runtime_error(m) {}
+};
+
+#define CGB_CHECK(cond, msg)                                                                  \
+  do {                                                                                        \
+    if (!(cond)) {                                                                            \
+      throw ::cgb::Error(std::string(__FILE__) + ":" + std::to_string(__LINE__) + ": " + msg); \
+    }                                                                                         \
+  } while (0)
+
+#define CGB_CUDA(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      throw ::cgb::Error(std::string(__FILE__) + ":" + std::to_string(__LINE__) + ": CUDA " +   \
+                         cudaGetErrorString(_e) + " in " #expr);                               \
+    }                                                                                          \
+  } while (0)
+
+// One K-iteration of the implicit GEMM: which 5-D box of the activation tensor to fetch
+// (relative to the tile's output origin) and which K offset of the packed weights.
+struct KIter {
+  int16_t a_c;    // coordinate 0: channel (already includes the w-parity * C offset)
+  int16_t a_dx;   // added to the tile's w origin -> coordinate 1
+  int16_t a_par;  // coordinate 2: h-parity plane (0 for stride-1 views)
+  int16_t a_dy;   // added to the tile's h origin -> coordinate 3
+  int32_t b_k;    // K coordinate in the packed weight matrix [Cout_pad][Ktot]
+  int32_t pad;
+};
+static_assert(sizeof(KIter) == 16, "KIter must be 16 bytes");
+
+constexpr int kMaxClasses = 4;  // output-parity classes of a stride-2 transposed conv / dgrad
+
+// Arguments of the tcgen05 implicit-GEMM kernel (fprop, dgrad and transposed fprop are
+// all expressed through the K-iteration table).
+struct IgemmArgs {
+  const KIter* kiters;
+  int k_begin[kMaxClasses];
+  int k_count[kMaxClasses];
+  long long out_off[kMaxClasses];  // element offset of the class's first output pixel
+  int tiles_w, tiles_h;            // tiles per image (tile = TH x TW output pixels, TH*TW = 128)
+  int tw_shift;                    // TW = 1 << tw_shift
+  int Ho, Wo;                      // valid output extent in class-local coordinates
+  int Cout;                        // channels actually stored (<= n_blocks * BN)
+  long long sN, sH, sW;            // output element strides (class-local pixel steps)
+  bf16* out;
+  const float* bias;               // nullptr = none (fp32, indexed by absolute channel)
+  int bias_n;                      // number of valid bias entries
+  int act;                         // 0 none, 1 LeakyReLU(0.2), 2 tanh
+  float* stats;                    // optional [N][Cout][2] fp32 (sum, sumsq) accumulated with atomics
+};
+
+// One filter tap of the weight-gradient GEMM: offsets for both operands.
+struct WTap {
+  int16_t a_c, a_dx, a_par, a_dy;  // dY side (M = Cout)
+  int16_t b_c, b_dx, b_par, b_dy;  // X side  (N = Cin)
+  int32_t out_tap;                 // tap index in g[Cout][T][Cin]
+  int32_t pad;
+};
+static_assert(sizeof(WTap) == 24, "WTap must be 24 bytes");
+
+struct WgradArgs {
+  const WTap* taps;
+  int num_taps;
+  int T;                   // taps per filter (kh*kw) = middle dim of g
+  int Cout, Cin;           // valid extents of g
+  int tiles_w, tiles_h, N; // pixel chunks (64 pixels = THk x TWk) per image, images
+  int tw_shift;            // TWk = 1 << tw_shift, THk = 64 >> tw_shift
+  int split_k;             // number of K splits (gridDim.z)
+  float* g;                // [Cout][T][Cin] fp32, accumulated with atomics (must be zeroed)
+};
+
+enum Act { kActNone = 0, kActLeaky = 1, kActTanh = 2, kActRelu = 3 };
+
+}  // namespace cgb

@@ -1,0 +1,367 @@
+// Host-side planning of the implicit-GEMM convolutions (see conv_plan.h).
+#include "conv_plan.h"
+
+#include <algorithm>
+#include <cstring>
+
+namespace cgb {
+
+int padded_rows(int c) { return c <= 16 ? 16 : (c + 63) / 64 * 64; }
+long long packed_wf_elems(const ConvSpec& s) { return (long long)padded_rows(s.CoutS) * s.taps() * s.CinS; }
+long long packed_wt_elems(const ConvSpec& s) { return (long long)padded_rows(s.CinS) * s.taps() * s.CoutS; }
+
+int out_extent(const ConvSpec& s, int in) {
+  if (s.transposed) return in * 2;
+  return (in + 2 * s.pad - s.k) / s.stride + 1;
+}
+
+static bool chan_ok(int c) { return c == 16 || (c > 0 && c % 64 == 0); }
+bool tc_supports_fprop(const ConvSpec& s) { return chan_ok(s.CinS) && chan_ok(s.CoutS); }
+bool tc_supports_dgrad(const ConvSpec& s) { return chan_ok(s.CinS) && chan_ok(s.CoutS); }
+bool tc_supports_wgrad(const ConvSpec& s) { return s.CinS % 64 == 0 && s.CoutS % 64 == 0; }
+
+static int ilog2_ceil(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+
+// floor-division split of a tap offset q into (parity, half-resolution offset): q = 2*off + par
+static void split_parity(int q, int* par, int* off) {
+  *par = ((q % 2) + 2) % 2;
+  *off = (q - *par) / 2;
+}
+
+static CUtensorMap view_s1(const TensorDesc& t, bool padded_view, int box_c, int box_w, int box_h) {
+  const int h = padded_view ? t.halo : 0;
+  const int dims[5] = {t.C, t.W + 2 * h, 1, t.H + 2 * h, t.N};
+  const long long str[4] = {t.sW(), t.sH(), t.sH(), t.sN()};
+  return make_tmap_act5d(padded_view ? t.ptr : t.interior(), dims, str, box_c, box_w, box_h, box_c * 2);
+}
+
+static CUtensorMap view_s2(const TensorDesc& t, int box_c, int box_w, int box_h) {
+  CGB_CHECK(t.H % 2 == 0 && t.W % 2 == 0, "stride-2 parity view needs even extents");
+  const int dims[5] = {2 * t.C, t.W / 2, 2, t.H / 2, t.N};
+  const long long str[4] = {2 * t.sW(), t.sH(), 2 * t.sH(), t.sN()};
+  return make_tmap_act5d(t.interior(), dims, str, box_c, box_w, box_h, box_c * 2);
+}
+
+static int choose_bn(int rows, int bk, long long ctas_per_nblock, int sm_count) {
+  if (rows <= 16) return 16;
+  if (bk == 16) return 64;
+  const int cands[3] = {256, 128, 64};
+  for (int bn : cands) {
+    if (rows % bn != 0) continue;
+    if (ctas_per_nblock * (rows / bn) >= (long long)(sm_count * 0.85)) return bn;
+  }
+  return 64;
+}
+
+static void set_tiles(IgemmPlan& p, int N, int Ho, int Wo) {
+  const int shift = std::max(3, std::min(7, ilog2_ceil(std::min(Wo, 128))));
+  const int TW = 1 << shift, TH = 128 >> shift;
+  p.args.tw_shift = shift;
+  p.args.tiles_w = (Wo + TW - 1) / TW;
+  p.args.tiles_h = (Ho + TH - 1) / TH;
+  p.args.Ho = Ho;
+  p.args.Wo = Wo;
+  p.num_tiles = N * p.args.tiles_w * p.args.tiles_h;
+}
+
+IgemmPlan plan_fprop(const ConvSpec& s, const TensorDesc& x, const bf16* wf, const TensorDesc& y, const float* bias,
+                     int act, int sm_count) {
+  CGB_CHECK(tc_supports_fprop(s), "fprop: channel counts not supported by the tensor-core path");
+  CGB_CHECK(x.C == s.CinS && y.C == s.CoutS, "fprop: tensor channels do not match the spec");
+  IgemmPlan p;
+  std::memset(&p.args, 0, sizeof(p.args));
+  const int k = s.k, T = s.taps();
+  const int BK = (s.CinS % 64 == 0) ? 64 : 16;
+  p.BK = BK;
+  const int Ho = out_extent(s, x.H), Wo = out_extent(s, x.W);
+  CGB_CHECK(y.H == Ho && y.W == Wo && y.N == x.N, "fprop: output extent mismatch");
+  const int Kw = T * s.CinS;  // packed weight row length
+  p.args.out = y.interior();
+  p.args.sN = y.sN();
+  p.args.bias = bias;
+  p.args.bias_n = bias ? s.Cout : 0;
+  p.args.act = act;
+  p.args.Cout = s.CoutS;
+  p.args.stats = nullptr;
+
+  if (!s.transposed) {
+    set_tiles(p, x.N, Ho, Wo);
+    p.n_classes = 1;
+    p.args.sH = y.sH();
+    p.args.sW = y.sW();
+    p.args.out_off[0] = 0;
+    p.args.k_begin[0] = 0;
+    const int TW = 1 << p.args.tw_shift, TH = 128 >> p.args.tw_shift;
+    if (s.stride == 1) {
+      if (s.reflect) CGB_CHECK(x.halo == s.pad, "reflect conv input must carry a halo equal to the padding");
+      p.tmA = view_s1(x, s.reflect, BK, TW, TH);
+      for (int r = 0; r < k; ++r)
+        for (int c = 0; c < k; ++c)
+          for (int c0 = 0; c0 < s.CinS; c0 += BK) {
+            KIter it{};
+            it.a_c = (int16_t)c0;
+            it.a_dx = (int16_t)(s.reflect ? c : c - s.pad);
+            it.a_par = 0;
+            it.a_dy = (int16_t)(s.reflect ? r : r - s.pad);
+            it.b_k = (r * k + c) * s.CinS + c0;
+            p.kiters.push_back(it);
+          }
+    } else {
+      CGB_CHECK(s.stride == 2 && !s.reflect, "only zero-padded stride-2 convs are supported");
+      p.tmA = view_s2(x, BK, TW, TH);
+      for (int r = 0; r < k; ++r)
+        for (int c = 0; c < k; ++c) {
+          int hp, hy, wp, wx;
+          split_parity(r - s.pad, &hp, &hy);
+          split_parity(c - s.pad, &wp, &wx);
+          for (int c0 = 0; c0 < s.CinS; c0 += BK) {
+            KIter it{};
+            it.a_c = (int16_t)(wp * s.CinS + c0);
+            it.a_dx = (int16_t)wx;
+            it.a_par = (int16_t)hp;
+            it.a_dy = (int16_t)hy;
+            it.b_k = (r * k + c) * s.CinS + c0;
+            p.kiters.push_back(it);
+          }
+        }
+    }
+    p.args.k_count[0] = (int)p.kiters.size();
+  } else {
+    CGB_CHECK(s.k == 3 && s.stride == 2 && s.pad == 1, "transposed conv: only k=3, s=2, p=1, op=1");
+    // four output-parity classes, each a small stride-1 conv over the input
+    set_tiles(p, x.N, x.H, x.W);
+    p.n_classes = 4;
+    p.args.sH = 2 * y.sH();
+    p.args.sW = 2 * y.sW();
+    const int TW = 1 << p.args.tw_shift, TH = 128 >> p.args.tw_shift;
+    p.tmA = view_s1(x, false, BK, TW, TH);
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) {
+        const int z = a * 2 + b;
+        p.args.out_off[z] = a * y.sH() + b * y.sW();
+        p.args.k_begin[z] = (int)p.kiters.size();
+        for (int r = 0; r < k; ++r) {
+          if ((a + s.pad - r) % 2 != 0) continue;
+          for (int c = 0; c < k; ++c) {
+            if ((b + s.pad - c) % 2 != 0) continue;
+            for (int c0 = 0; c0 < s.CinS; c0 += BK) {
+              KIter it{};
+              it.a_c = (int16_t)c0;
+              it.a_dx = (int16_t)((b + s.pad - c) / 2);
+              it.a_par = 0;
+              it.a_dy = (int16_t)((a + s.pad - r) / 2);
+              it.b_k = (r * k + c) * s.CinS + c0;
+              p.kiters.push_back(it);
+            }
+          }
+        }
+        p.args.k_count[z] = (int)p.kiters.size() - p.args.k_begin[z];
+      }
+  }
+  p.BN = choose_bn(s.CoutS, BK, (long long)p.num_tiles * p.n_classes, sm_count);
+  p.n_blocks = (padded_rows(s.CoutS) + p.BN - 1) / p.BN;
+  p.tmB = make_tmap_2d(wf, padded_rows(s.CoutS), Kw, Kw, BK, p.BN, BK * 2);
+  p.flops = 2.0 * x.N * (s.transposed ? (double)x.H * x.W : (double)Ho * Wo) * s.Cout * s.Cin * T;
+  return p;
+}
+
+IgemmPlan plan_dgrad(const ConvSpec& s, const TensorDesc& dy, const bf16* wt, const TensorDesc& dx, int sm_count) {
+  CGB_CHECK(tc_supports_dgrad(s), "dgrad: channel counts not supported by the tensor-core path");
+  CGB_CHECK(dy.C == s.CoutS && dx.C == s.CinS, "dgrad: tensor channels do not match the spec");
+  IgemmPlan p;
+  std::memset(&p.args, 0, sizeof(p.args));
+  const int k = s.k, T = s.taps();
+  const int BK = (s.CoutS % 64 == 0) ? 64 : 16;
+  p.BK = BK;
+  const int Kw = T * s.CoutS;
+  p.args.out = dx.interior();
+  p.args.sN = dx.sN();
+  p.args.bias = nullptr;
+  p.args.bias_n = 0;
+  p.args.act = kActNone;
+  p.args.Cout = s.CinS;
+  p.args.stats = nullptr;
+
+  if (!s.transposed && s.stride == 1) {
+    // zero pad:   dx[h]   = sum_r dy[h + p - r] w[r]
+    // reflect:    dxp[hp] = sum_r dy[hp - r]    w[r]   on the padded domain (dx.H == H + 2p)
+    const int off = s.reflect ? 0 : s.pad;
+    set_tiles(p, dx.N, dx.H, dx.W);
+    p.n_classes = 1;
+    p.args.sH = dx.sH();
+    p.args.sW = dx.sW();
+    const int TW = 1 << p.args.tw_shift, TH = 128 >> p.args.tw_shift;
+    p.tmA = view_s1(dy, false, BK, TW, TH);
+    for (int r = 0; r < k; ++r)
+      for (int c = 0; c < k; ++c)
+        for (int c0 = 0; c0 < s.CoutS; c0 += BK) {
+          KIter it{};
+          it.a_c = (int16_t)c0;
+          it.a_dx = (int16_t)(off - c);
+          it.a_par = 0;
+          it.a_dy = (int16_t)(off - r);
+          it.b_k = (r * k + c) * s.CoutS + c0;
+          p.kiters.push_back(it);
+        }
+    p.args.k_begin[0] = 0;
+    p.args.k_count[0] = (int)p.kiters.size();
+  } else if (!s.transposed) {
+    // stride 2: ih = 2*oh + r - p.  Four input-parity classes (a, b); oh = i + (a + p - r)/2.
+    CGB_CHECK(s.stride == 2 && !s.reflect, "dgrad: only zero-padded stride-2 convs are supported");
+    CGB_CHECK(dx.H % 2 == 0 && dx.W % 2 == 0, "dgrad stride 2: input extents must be even");
+    set_tiles(p, dx.N, dx.H / 2, dx.W / 2);
+    p.n_classes = 4;
+    p.args.sH = 2 * dx.sH();
+    p.args.sW = 2 * dx.sW();
+    const int TW = 1 << p.args.tw_shift, TH = 128 >> p.args.tw_shift;
+    p.tmA = view_s1(dy, false, BK, TW, TH);
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) {
+        const int z = a * 2 + b;
+        p.args.out_off[z] = a * dx.sH() + b * dx.sW();
+        p.args.k_begin[z] = (int)p.kiters.size();
+        for (int r = 0; r < k; ++r) {
+          if (((a + s.pad - r) % 2 + 2) % 2 != 0) continue;
+          for (int c = 0; c < k; ++c) {
+            if (((b + s.pad - c) % 2 + 2) % 2 != 0) continue;
+            int py, oy, px, ox;
+            split_parity(a + s.pad - r, &py, &oy);
+            split_parity(b + s.pad - c, &px, &ox);
+            for (int c0 = 0; c0 < s.CoutS; c0 += BK) {
+              KIter it{};
+              it.a_c = (int16_t)c0;
+              it.a_dx = (int16_t)ox;
+              it.a_par = 0;
+              it.a_dy = (int16_t)oy;
+              it.b_k = (r * k + c) * s.CoutS + c0;
+              p.kiters.push_back(it);
+            }
+          }
+        }
+        p.args.k_count[z] = (int)p.kiters.size() - p.args.k_begin[z];
+      }
+  } else {
+    // transposed conv: dx[i] = sum_r dy[2i - p + r] w[r]  == a stride-2 conv over dy
+    set_tiles(p, dx.N, dx.H, dx.W);
+    p.n_classes = 1;
+    p.args.sH = dx.sH();
+    p.args.sW = dx.sW();
+    const int TW = 1 << p.args.tw_shift, TH = 128 >> p.args.tw_shift;
+    p.tmA = view_s2(dy, BK, TW, TH);
+    for (int r = 0; r < k; ++r)
+      for (int c = 0; c < k; ++c) {
+        int hp, hy, wp, wx;
+        split_parity(r - s.pad, &hp, &hy);
+        split_parity(c - s.pad, &wp, &wx);
+        for (int c0 = 0; c0 < s.CoutS; c0 += BK) {
+          KIter it{};
+          it.a_c = (int16_t)(wp * s.CoutS + c0);
+          it.a_dx = (int16_t)wx;
+          it.a_par = (int16_t)hp;
+          it.a_dy = (int16_t)hy;
+          it.b_k = (r * k + c) * s.CoutS + c0;
+          p.kiters.push_back(it);
+        }
+      }
+    p.args.k_begin[0] = 0;
+    p.args.k_count[0] = (int)p.kiters.size();
+  }
+  p.BN = choose_bn(s.CinS, BK, (long long)p.num_tiles * p.n_classes, sm_count);
+  p.n_blocks = (padded_rows(s.CinS) + p.BN - 1) / p.BN;
+  p.tmB = make_tmap_2d(wt, padded_rows(s.CinS), Kw, Kw, BK, p.BN, BK * 2);
+  const double out_px = s.transposed ? (double)dx.H * dx.W : (double)dy.H * dy.W;
+  p.flops = 2.0 * dy.N * out_px * s.Cout * s.Cin * T;
+  return p;
+}
+
+WgradPlan plan_wgrad(const ConvSpec& s, const TensorDesc& x, const TensorDesc& dy, float* g, int sm_count) {
+  CGB_CHECK(tc_supports_wgrad(s), "wgrad: channel counts not supported by the tensor-core path");
+  CGB_CHECK(x.C == s.CinS && dy.C == s.CoutS, "wgrad: tensor channels do not match the spec");
+  WgradPlan p;
+  std::memset(&p.args, 0, sizeof(p.args));
+  const int k = s.k, T = s.taps();
+  // pixel domain of the reduction: conv -> output pixels; transposed conv -> input pixels
+  const int PH = s.transposed ? x.H : dy.H;
+  const int PW = s.transposed ? x.W : dy.W;
+  const int shift = std::max(3, std::min(6, ilog2_ceil(std::min(PW, 64))));
+  const int TWk = 1 << shift, THk = 64 >> shift;
+  p.args.tw_shift = shift;
+  p.args.tiles_w = (PW + TWk - 1) / TWk;
+  p.args.tiles_h = (PH + THk - 1) / THk;
+  p.args.N = x.N;
+  p.args.T = T;
+  p.args.Cout = s.Cout;
+  p.args.Cin = s.Cin;
+  p.args.g = g;
+  p.BNW = std::min(256, s.CinS);
+  CGB_CHECK(p.BNW == 64 || p.BNW == 128 || p.BNW == 256, "wgrad: unsupported Cin tile");
+  p.m_blocks = (s.CoutS + 127) / 128;
+
+  if (!s.transposed) {
+    p.tmDY = view_s1(dy, false, 64, TWk, THk);
+    if (s.stride == 1) {
+      if (s.reflect) CGB_CHECK(x.halo == s.pad, "reflect conv input must carry a halo equal to the padding");
+      p.tmX = view_s1(x, s.reflect, 64, TWk, THk);
+    } else {
+      p.tmX = view_s2(x, 64, TWk, THk);
+    }
+    for (int r = 0; r < k; ++r)
+      for (int c = 0; c < k; ++c) {
+        WTap t{};
+        if (s.stride == 1) {
+          t.b_dx = (int16_t)(s.reflect ? c : c - s.pad);
+          t.b_dy = (int16_t)(s.reflect ? r : r - s.pad);
+        } else {
+          int hp, hy, wp, wx;
+          split_parity(r - s.pad, &hp, &hy);
+          split_parity(c - s.pad, &wp, &wx);
+          t.b_c = (int16_t)(wp * s.CinS);
+          t.b_dx = (int16_t)wx;
+          t.b_par = (int16_t)hp;
+          t.b_dy = (int16_t)hy;
+        }
+        t.out_tap = r * k + c;
+        p.taps.push_back(t);
+      }
+  } else {
+    p.tmDY = view_s2(dy, 64, TWk, THk);
+    p.tmX = view_s1(x, false, 64, TWk, THk);
+    for (int r = 0; r < k; ++r)
+      for (int c = 0; c < k; ++c) {
+        WTap t{};
+        int hp, hy, wp, wx;
+        split_parity(r - s.pad, &hp, &hy);
+        split_parity(c - s.pad, &wp, &wx);
+        t.a_c = (int16_t)(wp * s.CoutS);
+        t.a_dx = (int16_t)wx;
+        t.a_par = (int16_t)hp;
+        t.a_dy = (int16_t)hy;
+        t.out_tap = r * k + c;
+        p.taps.push_back(t);
+      }
+  }
+  p.args.num_taps = (int)p.taps.size();
+  const long long total_chunks = (long long)p.args.N * p.args.tiles_w * p.args.tiles_h;
+  const long long base_ctas = (long long)p.m_blocks * ((s.CinS + p.BNW - 1) / p.BNW) * T;
+  long long split = (2LL * sm_count + base_ctas - 1) / base_ctas;  // aim at ~2 waves
+  split = std::max(1LL, std::min(split, std::max(1LL, total_chunks / 4)));
+  p.args.split_k = (int)split;
+  p.flops = 2.0 * x.N * (double)PH * PW * s.Cout * s.Cin * T;
+  return p;
+}
+
+void run(const IgemmPlan& p, cudaStream_t stream) {
+  CGB_CHECK(p.args.kiters != nullptr, "igemm plan has no device K-iteration table");
+  launch_igemm(p.BN, p.BK, p.tmA, p.tmB, p.args, p.num_tiles, p.n_blocks, p.n_classes, stream);
+}
+
+void run(const WgradPlan& p, cudaStream_t stream) {
+  CGB_CHECK(p.args.taps != nullptr, "wgrad plan has no device tap table");
+  launch_wgrad(p.BNW, p.tmDY, p.tmX, p.args, p.m_blocks, stream);
+}
+
+}  // namespace cgb

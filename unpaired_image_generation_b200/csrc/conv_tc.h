@@ -1,0 +1,24 @@
+// Host-side entry points of the tcgen05 convolution kernels (conv_tc.cu) and the TMA
+// tensor-map builder (tmap.cc).
+#pragma once
+#include "common.h"
+
+namespace cgb {
+
+// 5-D activation view: dims (d0 channels, d1 width, d2 parity plane, d3 height, d4 image),
+// strides in ELEMENTS for d1..d4 (d0 is contiguous), box = (box_c, box_w, 1, box_h, 1).
+// swizzle_bytes must equal box_c * 2 (32, 64 or 128).
+CUtensorMap make_tmap_act5d(const bf16* base, const int dims[5], const long long strides_elems[4], int box_c,
+                            int box_w, int box_h, int swizzle_bytes);
+
+// 2-D K-major matrix [rows][cols] bf16 with row pitch `pitch_elems`; box = (box_cols, box_rows).
+CUtensorMap make_tmap_2d(const bf16* base, long long rows, long long cols, long long pitch_elems, int box_cols,
+                         int box_rows, int swizzle_bytes);
+
+void launch_igemm(int BN, int BK, const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmArgs& args,
+                  int num_tiles, int n_blocks, int n_classes, cudaStream_t stream);
+
+void launch_wgrad(int BNW, const CUtensorMap& tmDY, const CUtensorMap& tmX, const WgradArgs& args, int m_blocks,
+                  cudaStream_t stream);
+
+}  // namespace cgb

@@ -1,0 +1,77 @@
+// HBM-bound kernels of the CycleGAN step: layout conversion, InstanceNorm statistics / apply /
+// backward (with reflection-halo writing and halo-gradient folding), activation backward,
+// LSGAN / L1 losses with their seed gradients, bias gradients, weight packing and Adam.
+// Stand-in counterparts (oracle/cyclegan_standin.py): _inorm, F.pad(mode="reflect"), F.relu,
+// F.leaky_relu, torch.tanh, F.l1_loss, CycleGANTrainer._mse_to, torch.optim.Adam.
+#pragma once
+#include "common.h"
+#include "conv_plan.h"
+
+namespace cgb {
+
+// ---- layout ------------------------------------------------------------------------------
+// fp32 NCHW [N][C][H][W] -> bf16 NHWC (dst.C stored channels, zero padded) interior + reflect halo
+void nchw_to_nhwc(const float* src, int C, const TensorDesc& dst, cudaStream_t st);
+// bf16 NHWC interior -> fp32 NCHW (first C channels)
+void nhwc_to_nchw(const TensorDesc& src, int C, float* dst, cudaStream_t st);
+// mirror the interior into the halo (reflection padding) in place
+void fill_reflect_halo(const TensorDesc& t, cudaStream_t st);
+
+// ---- InstanceNorm --------------------------------------------------------------------------
+// stats[n][c] = (sum, sumsq) over H*W of the bf16 values; buffer must be zero on entry.
+void in_stats(const TensorDesc& y, float2* stats, cudaStream_t st);
+// out(interior + reflect halo) = act(norm(y)) [+ residual.interior]
+void in_apply(const TensorDesc& y, const float2* stats, int act, const TensorDesc* residual, const TensorDesc& out,
+              cudaStream_t st);
+
+// Gradient w.r.t. a layer's post-activation output, assembled on the fly from up to two sources:
+//   g1: plain tensor (interior view), g2: gradient on the reflect-padded domain (H+2p, W+2p) whose
+//   mirrored border is folded back onto the interior.
+struct GradSrc {
+  const TensorDesc* g1 = nullptr;
+  const TensorDesc* g2 = nullptr;  // dims (H + 2*fold, W + 2*fold), halo 0
+  int fold = 0;
+};
+// bstats[n][c] += (sum dz, sum dz*xhat); optionally stores the assembled (bf16-rounded) gradient.
+void in_bwd_reduce(const TensorDesc& y, const float2* stats, const GradSrc& g, int act, const TensorDesc* da_out,
+                   float2* bstats, cudaStream_t st);
+// dy = rstd * (dz - mean(dz) - xhat * mean(dz * xhat))
+void in_bwd_apply(const TensorDesc& y, const float2* stats, const float2* bstats, const GradSrc& g, int act,
+                  const TensorDesc& dy, cudaStream_t st);
+
+// ---- pointwise activation backward ----------------------------------------------------------
+// generator head: dpre = (l1_scale * sign(out - target) + g1 + fold(g2)) * (1 - out^2); also
+// accumulates loss_slot += l1_scale * sum|out - target| (only the first `C` channels count).
+void tanh_bwd(const TensorDesc& out, const TensorDesc* target, float l1_scale, const GradSrc& g, int C,
+              const TensorDesc& dpre, float* loss_slot, cudaStream_t st);
+// L1 loss value only (forward-only paths): loss_slot += scale * sum|a - b| over first C channels
+void l1_loss(const TensorDesc& a, const TensorDesc& b, int C, float scale, float* loss_slot, cudaStream_t st);
+// discriminator conv0: dpre = g * (a > 0 ? 1 : 0.2)
+void leaky_bwd(const TensorDesc& a, const TensorDesc& g, const TensorDesc& dpre, cudaStream_t st);
+// LSGAN: loss_slot += w * mean((p - target)^2); dlogits(ch 0) = 2 w (p - target) / numel (may be null)
+void mse_loss(const TensorDesc& logits, float target, float w, float* loss_slot, const TensorDesc* dlogits,
+              cudaStream_t st);
+// gbias[c] += sum over pixels of dy[..][c], c < C
+void bias_grad(const TensorDesc& dy, int C, float* gbias, cudaStream_t st);
+
+// ---- weights ---------------------------------------------------------------------------------
+struct PackEntry {
+  long long src_off;  // offset (elements) of the fp32 master weight [Cout][T][Cin] in the flat buffer
+  long long wf_off;   // offset (elements) into the bf16 pack arena of Wf [CoutP][T][CinS]
+  long long wt_off;   // offset of Wt [CinP][T][CoutS]
+  int Cout, Cin, T, CinS, CoutS;
+  int pad;
+};
+// one launch re-packs every layer of a parameter group (after Adam)
+void pack_weights(const float* master, const PackEntry* entries_dev, int n_entries, int max_elems, bf16* arena,
+                  cudaStream_t st);
+
+// torch.optim.Adam semantics (no weight decay, no amsgrad); g is multiplied by grad_scale first.
+void adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+               float eps, int step, float grad_scale, cudaStream_t st);
+
+// ---- CUDA-core convolution passes for the 3-channel / 1-channel layers ------------------------
+// g[Cout][T][Cin] += sum_pixels dy * x   (x may carry a reflect halo == pad; zero padding otherwise)
+void wgrad_direct(const ConvSpec& s, const TensorDesc& x, const TensorDesc& dy, float* g, cudaStream_t st);
+
+}  // namespace cgb
