@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""Benchmark of the CycleGAN 256x256 training step (BASELINE.json metric: train images/sec).
+
+    python bench.py --gpus N --steps K --warmup W            # B200 path (one rank per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W    # the stand-in on the host CPU cores
+
+One "step" = one full CycleGAN optimisation step (6 generator forwards, G backward + Adam, D forward/
+backward + Adam) on one batch of synthetic image pairs; one "image" = one (A, B) pair.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "cyclegan_256_train_images_per_sec"
+UNIT = "images/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(source="measured (MEASURED_PEAKS.json)", hbm_gbs=p["hbm_gbs"], tf_burst=p["bf16_tflops"],
+                    tf_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]))
+    return dict(source="fallback (B200_PROFILING.md)", hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0)
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(prefix="clocks_", suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            with open(self.path) as f:
+                for line in f:
+                    parts = [p.strip() for p in line.split(",")]
+                    if len(parts) < 9:
+                        continue
+                    try:
+                        sm.append(float(parts[1]))
+                        mx.append(float(parts[2]))
+                    except ValueError:
+                        continue
+                    for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                         parts[5:9]):
+                        if val.lower().startswith("active"):
+                            reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the stand-in oracle on the host cores
+# ----------------------------------------------------------------------------------------------
+def time_standin(batch: int, size: int, steps: int, warmup: int):
+    import torch
+    from oracle import cyclegan_standin as ref
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    G_AB, G_BA, D_A, D_B = ref.build_models(seed=0)
+    tr = ref.CycleGANTrainer(G_AB, G_BA, D_A, D_B)
+    real_A, real_B = ref.synthetic_pair(batch, size, seed=1234)
+    for _ in range(warmup):
+        tr.train_step(real_A, real_B)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        tr.train_step(real_A, real_B)
+        times.append(time.perf_counter() - t0)
+    return times, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # rank 0 alone runs the CPU arm
+    steps = min(args.steps, 8)      # bounded sample: ~5 s per step on 8 cores
+    warmup = min(max(args.warmup, 1), 2)
+    times, cores = time_standin(args.batch, args.size, steps, warmup)
+    sec = sum(times) / len(times)
+    value = args.batch / sec
+    sample = (f"{steps} timed + {warmup} warm-up full train steps of oracle/cyclegan_standin.py (fp32, torch CPU, "
+              f"{cores} threads), batch {args.batch}, {args.size}x{args.size}")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"CycleGAN {args.size}x{args.size} ResNet-9blk + 70x70 PatchGAN, batch {args.batch}, "
+                               "one full train step (stand-in, CPU)", "batch_per_gpu": args.batch, "size": args.size},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import unpaired_image_generation_b200 as cgb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (B200 arm) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    peaks = load_peaks()
+    batch, size = args.batch, args.size
+
+    G_AB, G_BA = cgb.Generator(seed=1), cgb.Generator(seed=2)
+    D_A, D_B = cgb.Discriminator(seed=3), cgb.Discriminator(seed=4)
+    tr = cgb.CycleGANTrainer(G_AB, G_BA, D_A, D_B)
+    g = torch.Generator().manual_seed(1234 + rank)
+    host_A = (torch.rand(batch, 3, size, size, generator=g) * 2 - 1).pin_memory()
+    host_B = (torch.rand(batch, 3, size, size, generator=g) * 2 - 1).pin_memory()
+    dev_A, dev_B = host_A.cuda(), host_B.cuda()
+    eng = tr._ensure_engine(dev_A)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_step():
+        # inputs already resident in HBM; no host round trip inside the step
+        if world == 1:
+            with torch.cuda.stream(tr.stream):
+                eng.set_inputs(dev_A, dev_B)
+                eng.train_step()
+        else:
+            tr._train_step_dp_nosync(eng, dev_A, dev_B)
+
+    # ---- value: whole-job throughput, device-resident inputs
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(tr.stream)
+    for _ in range(args.steps):
+        device_step()
+    ev1.record(tr.stream)
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = world * batch / (ms_step * 1e-3)
+
+    # ---- e2e: public API, pinned HOST inputs, losses read back every step
+    for _ in range(2):
+        tr.train_step(host_A, host_B)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = args.steps
+    for _ in range(e2e_steps):
+        losses = tr.train_step(host_A, host_B)
+    barrier()
+    e2e_sec = (time.perf_counter() - t0) / e2e_steps
+    te = torch.tensor([e2e_sec], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * batch / float(te.item())
+    h2d = 2 * batch * 3 * size * size * 4
+    d2h = len(cgb.LOSS_KEYS) * 4
+
+    line = None
+    if rank == 0:
+        # ---- roofline of the dominant kernel class (tcgen05 implicit-GEMM fprop/dgrad), timed live with CUDA events
+        with torch.cuda.stream(tr.stream):
+            ms_ig, n_ig, fl_ig = eng.profile_kind(1, reps=5)
+            ms_wg, n_wg, fl_wg = eng.profile_kind(2, reps=5)
+            ms_wd, n_wd, fl_wd = eng.profile_kind(3, reps=3)
+            ms_pw, n_pw, _ = eng.profile_kind(4, reps=5)
+        achieved = fl_ig / (ms_ig * 1e-3) / 1e12
+        roofline = {
+            "bound": "tensor", "kernel": "igemm_conv_kernel (tcgen05 implicit-GEMM conv fprop/dgrad, all layer shapes)",
+            "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"],
+            "traffic": None, "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
+            "launches_per_step": n_ig, "ms_per_step": ms_ig, "flops_per_step": fl_ig,
+            "other_kernels": {
+                "wgrad_kernel(tcgen05)": {"ms_per_step": ms_wg, "launches": n_wg,
+                                          "tflops": fl_wg / (ms_wg * 1e-3) / 1e12 if ms_wg > 0 else None},
+                "wgrad_direct(3-channel layers)": {"ms_per_step": ms_wd, "launches": n_wd,
+                                                   "tflops": fl_wd / (ms_wd * 1e-3) / 1e12 if ms_wd > 0 else None},
+                "instnorm_pointwise": {"ms_per_step": ms_pw, "launches": n_pw},
+            },
+            "step_conv_tflops": eng.conv_flops_per_step / (ms_step * 1e-3) / 1e12,
+            "step_conv_frac_of_peak": eng.conv_flops_per_step / (ms_step * 1e-3) / 1e12 / peaks["tf_sustained"],
+        }
+        # ---- cpu_baseline: the stand-in on this box's host cores, bounded sample
+        cpu = None
+        if not args.no_cpu_baseline:
+            times, cores = time_standin(1, size, 2, 1)
+            sec = min(times)
+            cpu = {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"best of 2 full train steps after 1 warm-up of oracle/cyclegan_standin.py (fp32 torch CPU, "
+                             f"{cores} threads), batch 1, {size}x{size}"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"CycleGAN {size}x{size} ResNet-9blk + 70x70 PatchGAN, batch {batch} per GPU, bf16 "
+                                   "storage / fp32 accumulate, full train step (BASELINE.json configs[1])",
+                       "batch_per_gpu": batch, "global_batch": batch * world, "size": size,
+                       "parallelism": f"dp{world}",
+                       "l2": f"per-step working set {eng.workspace_bytes / 2**20:.0f} MiB >> 126 MB L2 (no explicit flush)"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": eng.launches_per_step * args.steps,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "losses_last_step": losses,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=1, help="image pairs per GPU per step (configs[1]: 1)")
+    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

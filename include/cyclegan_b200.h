@@ -1,0 +1,133 @@
+/* C ABI of the B200-native CycleGAN training-step library (libcyclegan_b200.so).
+ *
+ * The nominal reference (EleutherAI/Unpaired-Image-Generation) has no FFI and no code
+ * (/root/reference/README.md:1 is the whole repository); the interface replaced here is the
+ * public surface of the committed stand-in, oracle/cyclegan_standin.py:
+ *   Generator.forward            (oracle/cyclegan_standin.py:131)  -> cgb_generator_forward
+ *   Discriminator.forward        (oracle/cyclegan_standin.py:176)  -> cgb_discriminator_forward
+ *   CycleGANTrainer.forward_only (oracle/cyclegan_standin.py:228)  -> cgb_forward_cycle + cgb_get_image
+ *   CycleGANTrainer.train_step   (oracle/cyclegan_standin.py:298)  -> cgb_phase_generators, cgb_adam,
+ *                                                                     cgb_phase_discriminators, cgb_get_losses
+ *   CycleGANTrainer.backward_only(oracle/cyclegan_standin.py:274)  -> the two phase calls without cgb_adam
+ *   module.state_dict()/load_state_dict()                          -> cgb_param_info + caller-owned flat buffers
+ *
+ * Conventions: every function returns 0 on success and a non-zero code on failure, in which case
+ * cgb_last_error() returns a thread-local message.  All pointers are plain device pointers unless the
+ * name says `host`.  No function synchronises the device except the *_host variants and
+ * cgb_get_losses_host.  Streams are passed as void* (cudaStream_t).  The library owns only small
+ * lookup tables (tap tables, pack tables); every large buffer is supplied by the caller.
+ */
+#ifndef CYCLEGAN_B200_H_
+#define CYCLEGAN_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cgb_engine cgb_engine_t;
+
+typedef struct cgb_config {
+  int batch;        /* images per domain per step on this GPU */
+  int size;         /* square image edge, multiple of 8 (canonical: 256) */
+  int n_blocks;     /* residual blocks in each generator (canonical: 9) */
+  float lambda_A;   /* cycle loss weight A (10) */
+  float lambda_B;   /* cycle loss weight B (10) */
+  float lambda_idt; /* identity loss weight (0.5) */
+  float lr;         /* Adam learning rate (2e-4) */
+  float beta1;      /* 0.5 */
+  float beta2;      /* 0.999 */
+  float eps;        /* 1e-8 */
+} cgb_config_t;
+
+enum { CGB_NET_G_AB = 0, CGB_NET_G_BA = 1, CGB_NET_D_A = 2, CGB_NET_D_B = 3 };
+enum { CGB_GROUP_G = 0, CGB_GROUP_D = 1 };
+enum { CGB_IMG_FAKE_B = 0, CGB_IMG_REC_A = 1, CGB_IMG_FAKE_A = 2, CGB_IMG_REC_B = 3, CGB_IMG_IDT_A = 4,
+       CGB_IMG_IDT_B = 5, CGB_IMG_REAL_A = 6, CGB_IMG_REAL_B = 7 };
+/* loss slots, same order as CycleGANTrainer.LOSS_KEYS in the stand-in */
+enum { CGB_LOSS_G = 0, CGB_LOSS_G_A, CGB_LOSS_G_B, CGB_LOSS_CYCLE_A, CGB_LOSS_CYCLE_B, CGB_LOSS_IDT_A,
+       CGB_LOSS_IDT_B, CGB_LOSS_D_A, CGB_LOSS_D_B, CGB_NUM_LOSSES };
+
+typedef struct cgb_param_info {
+  char name[64];        /* stand-in state_dict key, e.g. "res.3.conv1.weight" */
+  int is_bias;
+  int transposed;       /* 1: ConvTranspose2d (torch layout [Cin][Cout][k][k]) */
+  int cout, cin, k;     /* bias: cout entries */
+  long long offset;     /* element offset in the group's flat fp32 buffers */
+  long long numel;
+  /* weights are stored internally as [cout][k*k][cin] (fp32); a torch view of the flat buffer is
+   * flat[offset:offset+numel].view(cout,k,k,cin).permute(0,3,1,2)  (conv)  or .permute(3,0,1,2) (transposed) */
+} cgb_param_info_t;
+
+const char* cgb_last_error(void);
+int cgb_version(void);
+
+/* ---- construction (host only; works without a GPU) -------------------------------------------------- */
+int cgb_engine_create(const cgb_config_t* cfg, cgb_engine_t** out);
+void cgb_engine_destroy(cgb_engine_t* e);
+int cgb_num_params(const cgb_engine_t* e, int net);                       /* tensors in a network */
+int cgb_param_info(const cgb_engine_t* e, int net, int index, cgb_param_info_t* out);
+long long cgb_group_numel(const cgb_engine_t* e, int group);              /* floats in the flat buffers */
+long long cgb_workspace_bytes(const cgb_engine_t* e);
+
+/* ---- binding (needs the GPU) ------------------------------------------------------------------------- */
+/* params/grads/m/v: fp32 flat buffers of cgb_group_numel(group) elements; workspace: cgb_workspace_bytes. */
+int cgb_engine_bind(cgb_engine_t* e, float* params_G, float* grads_G, float* m_G, float* v_G, float* params_D,
+                    float* grads_D, float* m_D, float* v_D, void* workspace, long long workspace_bytes);
+/* re-derive the bf16 packed weights from the fp32 masters (after load_state_dict / Adam) */
+int cgb_refresh_weights(cgb_engine_t* e, int group, void* stream);
+int cgb_set_grad_scale(cgb_engine_t* e, float scale); /* 1/world_size for data parallel */
+int cgb_set_step_count(cgb_engine_t* e, int group, int step);
+
+/* ---- modules -------------------------------------------------------------------------------------------- */
+/* x, y: fp32 NCHW [batch][3][size][size] device tensors */
+int cgb_generator_forward(cgb_engine_t* e, int net, const float* x, float* y, void* stream);
+/* logits: fp32 [batch][1][size/8-2][size/8-2] */
+int cgb_discriminator_forward(cgb_engine_t* e, int net, const float* x, float* logits, void* stream);
+
+/* ---- training step ----------------------------------------------------------------------------------------- */
+int cgb_set_inputs(cgb_engine_t* e, const float* real_A, const float* real_B, void* stream);
+int cgb_forward_cycle(cgb_engine_t* e, void* stream);              /* the six generator passes */
+int cgb_get_image(cgb_engine_t* e, int which, float* out, void* stream);
+/* forward + G-phase backward: grads_G = d loss_G / d(G_AB, G_BA); zeroes grads_G first */
+int cgb_phase_generators(cgb_engine_t* e, void* stream);
+/* D-phase forward/backward on real images and the pre-update fakes: grads_D; zeroes grads_D first */
+int cgb_phase_discriminators(cgb_engine_t* e, void* stream);
+/* Adam on a group (grads multiplied by grad_scale), then refreshes that group's bf16 weights */
+int cgb_adam(cgb_engine_t* e, int group, void* stream);
+/* whole step on one stream, replayed from a CUDA graph after the first call */
+int cgb_train_step(cgb_engine_t* e, void* stream);
+/* copies the CGB_NUM_LOSSES loss values to host memory (synchronises the stream) */
+int cgb_get_losses_host(cgb_engine_t* e, float* losses_host, void* stream);
+/* end-to-end convenience: pinned/pageable HOST inputs in, losses out (H2D + step + D2H, synchronous) */
+int cgb_train_step_host(cgb_engine_t* e, const float* real_A_host, const float* real_B_host, float* losses_host,
+                        void* stream);
+
+/* ---- accounting -------------------------------------------------------------------------------------------- */
+long long cgb_launches_per_step(const cgb_engine_t* e);  /* kernels launched by one cgb_train_step */
+double cgb_conv_flops_per_step(const cgb_engine_t* e);    /* algorithmic 2*MACs of all conv passes */
+
+/* Replays, `reps` times between two CUDA events on `stream`, every launch of one kind of the recorded step
+ * (kind: 1 = tcgen05 implicit-GEMM fprop/dgrad, 2 = tcgen05 wgrad, 3 = CUDA-core wgrad of the 3-channel
+ * layers, 4 = InstanceNorm / pointwise).  Data dependencies are ignored (profiling only: gradients and
+ * activations are garbage afterwards).  Returns milliseconds per step-equivalent, launches and algorithmic
+ * FLOPs per step-equivalent.  Synchronises the stream. */
+int cgb_profile_kind(cgb_engine_t* e, int kind, int reps, void* stream, float* ms_per_step, long long* launches,
+                     double* flops);
+
+/* ---- single-layer harness used by the parity tests (allocates its own scratch with cudaMalloc) -------------- */
+/* Runs fprop (+bias, +act), and when dy != NULL also dgrad and wgrad, of one layer through the same plans the
+ * engine uses.  x:[n][cin][h][w], w: torch layout, y/dy:[n][cout][ho][wo], dx like x, dw like w, db:[cout].
+ * act: 0 none, 1 LeakyReLU(0.2), 2 tanh.  Any output pointer may be NULL. */
+int cgb_conv_layer_test(int n, int h, int w, int cin, int cout, int k, int stride, int pad, int reflect,
+                        int transposed, int act, const float* x, const float* weight, const float* bias,
+                        const float* dy, float* y, float* dx, float* dw, float* db);
+/* InstanceNorm(+act, +residual) forward and backward on NCHW fp32 tensors through the bf16 NHWC kernels.
+ * act: 0 none, 3 ReLU, 1 LeakyReLU.  out_halo > 0 also checks the reflect-halo writer (out is still NCHW
+ * interior).  da: gradient w.r.t. out; dy_out: gradient w.r.t. y. */
+int cgb_instnorm_test(int n, int c, int h, int w, int act, const float* y, const float* residual, const float* da,
+                      float* out, float* dy_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CYCLEGAN_B200_H_ */

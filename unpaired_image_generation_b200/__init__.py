@@ -1,0 +1,9 @@
+"""B200-native CycleGAN training step (sm_100a CUDA behind a C ABI) with the module / train-step API
+of the committed stand-in (oracle/cyclegan_standin.py).  No CPU fallback: importing the compute entry
+points without the built libcyclegan_b200.so raises."""
+from .engine import LOSS_KEYS, StepEngine, describe
+from .modules import Discriminator, Generator
+from .parallel import GradSync
+from .trainer import CycleGANTrainer
+
+__all__ = ["Generator", "Discriminator", "CycleGANTrainer", "StepEngine", "GradSync", "LOSS_KEYS", "describe"]

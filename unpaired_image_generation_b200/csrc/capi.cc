@@ -1,0 +1,482 @@
+// extern "C" surface of libcyclegan_b200.so (declared in include/cyclegan_b200.h).
+#include <cstring>
+#include <vector>
+
+#include "engine.h"
+
+using namespace cgb;
+
+namespace cgb {
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+}  // namespace cgb
+
+#define CGB_API_BEGIN try {
+#define CGB_API_END                       \
+  }                                       \
+  catch (const std::exception& ex) {      \
+    cgb::set_last_error(ex.what());       \
+    return 1;                             \
+  }                                       \
+  catch (...) {                           \
+    cgb::set_last_error("unknown error"); \
+    return 2;                             \
+  }                                       \
+  return 0;
+
+static cudaStream_t S(void* stream) { return static_cast<cudaStream_t>(stream); }
+
+extern "C" {
+
+const char* cgb_last_error(void) { return cgb::g_last_error.c_str(); }
+int cgb_version(void) { return 100; }
+
+int cgb_engine_create(const cgb_config_t* cfg, cgb_engine_t** out) {
+  CGB_API_BEGIN
+  CGB_CHECK(cfg && out, "null argument");
+  CGB_CHECK(cfg->batch >= 1, "batch must be >= 1");
+  CGB_CHECK(cfg->size >= 32 && cfg->size % 8 == 0, "size must be a multiple of 8 and >= 32");
+  CGB_CHECK(cfg->n_blocks >= 1 && cfg->n_blocks <= 32, "n_blocks must be in [1, 32]");
+  cgb_engine* e = new cgb_engine();
+  e->cfg = *cfg;
+  e->build_inventory();
+  Arena A;
+  e->layout(A);
+  e->workspace_bytes = A.off;
+  *out = e;
+  CGB_API_END
+}
+
+void cgb_engine_destroy(cgb_engine_t* e) { delete e; }
+
+int cgb_num_params(const cgb_engine_t* e, int net) {
+  if (!e || net < 0 || net > 3) return -1;
+  return (int)e->layers[net].size() * 2;
+}
+
+int cgb_param_info(const cgb_engine_t* e, int net, int index, cgb_param_info_t* out) {
+  CGB_API_BEGIN
+  CGB_CHECK(e && out && net >= 0 && net < 4, "bad argument");
+  CGB_CHECK(index >= 0 && index < (int)e->layers[net].size() * 2, "parameter index out of range");
+  const LayerParam& p = e->layers[net][index / 2];
+  std::memset(out, 0, sizeof(*out));
+  const bool is_bias = index % 2 == 1;
+  const std::string nm = p.name + (is_bias ? ".bias" : ".weight");
+  std::strncpy(out->name, nm.c_str(), sizeof(out->name) - 1);
+  out->is_bias = is_bias;
+  out->transposed = p.spec.transposed;
+  out->cout = p.spec.Cout;
+  out->cin = p.spec.Cin;
+  out->k = p.spec.k;
+  out->offset = is_bias ? p.b_off : p.w_off;
+  out->numel = is_bias ? p.spec.Cout : (long long)p.spec.Cout * p.spec.taps() * p.spec.Cin;
+  CGB_API_END
+}
+
+long long cgb_group_numel(const cgb_engine_t* e, int group) { return (e && group >= 0 && group < 2) ? e->group_numel[group] : -1; }
+long long cgb_workspace_bytes(const cgb_engine_t* e) { return e ? (long long)e->workspace_bytes : -1; }
+
+int cgb_engine_bind(cgb_engine_t* e, float* pG, float* gG, float* mG, float* vG, float* pD, float* gD, float* mD,
+                    float* vD, void* workspace, long long workspace_bytes) {
+  CGB_API_BEGIN
+  CGB_CHECK(e, "null engine");
+  CGB_CHECK(!e->bound, "engine is already bound");
+  CGB_CHECK(pG && gG && mG && vG && pD && gD && mD && vD && workspace, "null buffer");
+  CGB_CHECK(workspace_bytes >= (long long)e->workspace_bytes, "workspace too small");
+  CGB_CHECK((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "workspace must be 1024-byte aligned");
+  int dev = 0;
+  CGB_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CGB_CUDA(cudaGetDeviceProperties(&prop, dev));
+  CGB_CHECK(prop.major == 10, "this library is built for sm_100a (B200) only; found compute capability " +
+                                  std::to_string(prop.major) + "." + std::to_string(prop.minor));
+  e->sm_count = prop.multiProcessorCount;
+  e->P[0] = pG; e->G[0] = gG; e->M[0] = mG; e->V[0] = vG;
+  e->P[1] = pD; e->G[1] = gD; e->M[1] = mD; e->V[1] = vD;
+  Arena A;
+  A.base = static_cast<uint8_t*>(workspace);
+  e->layout(A);
+  CGB_CUDA(cudaMemset(workspace, 0, e->workspace_bytes));
+  e->meta_cap = 16u << 20;
+  CGB_CUDA(cudaMalloc(&e->meta, e->meta_cap));
+  e->record_programs();
+  e->bound = true;
+  e->prog_refresh[0].run(0);
+  e->prog_refresh[1].run(0);
+  CGB_CUDA(cudaDeviceSynchronize());
+  CGB_API_END
+}
+
+int cgb_refresh_weights(cgb_engine_t* e, int group, void* stream) {
+  CGB_API_BEGIN
+  CGB_CHECK(e && e->bound && group >= 0 && group < 2, "bad argument / engine not bound");
+  e->prog_refresh[group].run(S(stream));
+  CGB_API_END
+}
+
+int cgb_set_grad_scale(cgb_engine_t* e, float scale) {
+  if (!e) return 1;
+  e->grad_scale = scale;
+  if (e->graph) {  // the scale is a baked kernel argument: re-capture
+    cudaGraphExecDestroy(e->graph);
+    e->graph = nullptr;
+  }
+  return 0;
+}
+
+int cgb_set_step_count(cgb_engine_t* e, int group, int step) {
+  CGB_API_BEGIN
+  CGB_CHECK(e && e->bound && group >= 0 && group < 2, "bad argument / engine not bound");
+  CGB_CUDA(cudaMemcpy(e->adam_step[group], &step, sizeof(int), cudaMemcpyHostToDevice));
+  CGB_API_END
+}
+
+int cgb_generator_forward(cgb_engine_t* e, int net, const float* x, float* y, void* stream) {
+  CGB_API_BEGIN
+  CGB_CHECK(e && e->bound && (net == 0 || net == 1) && x && y, "bad argument / engine not bound");
+  nchw_to_nhwc(x, 3, e->mod_in, S(stream));
+  e->prog_mod_gen[net].run(S(stream));
+  nhwc_to_nchw(e->mod_out, 3, y, S(stream));
+  CGB_API_END
+}
+
+int cgb_discriminator_forward(cgb_engine_t* e, int net, const float* x, float* logits, void* stream) {
+  CGB_API_BEGIN
+  CGB_CHECK(e && e->bound && (net == 2 || net == 3) && x && logits, "bad argument / engine not bound");
+  nchw_to_nhwc(x, 3, e->mod_in, S(stream));
+  e->prog_mod_dis[net - 2].run(S(stream));
+  nhwc_to_nchw(e->dis[4].logits, 1, logits, S(stream));
+  CGB_API_END
+}
+
+int cgb_set_inputs(cgb_engine_t* e, const float* real_A, const float* real_B, void* stream) {
+  CGB_API_BEGIN
+  CGB_CHECK(e && e->bound && real_A && real_B, "bad argument / engine not bound");
+  const size_t bytes = (size_t)e->cfg.batch * 3 * e->cfg.size * e->cfg.size * sizeof(float);
+  CGB_CUDA(cudaMemcpyAsync(e->staging[0], real_A, bytes, cudaMemcpyDefault, S(stream)));
+  CGB_CUDA(cudaMemcpyAsync(e->staging[1], real_B, bytes, cudaMemcpyDefault, S(stream)));
+  e->prog_set_inputs.run(S(stream));
+  CGB_API_END
+}
+
+int cgb_forward_cycle(cgb_engine_t* e, void* stream) {
+  CGB_API_BEGIN
+  CGB_CHECK(e && e->bound, "engine not bound");
+  e->prog_cycle.run(S(stream));
+  CGB_API_END
+}
+
+int cgb_get_image(cgb_engine_t* e, int which, float* out, void* stream) {
+  CGB_API_BEGIN
+  CGB_CHECK(e && e->bound && which >= 0 && which < 8 && out, "bad argument / engine not bound");
+  nhwc_to_nchw(e->img[which], 3, out, S(stream));
+  CGB_API_END
+}
+
+int cgb_phase_generators(cgb_engine_t* e, void* stream) {
+  CGB_API_BEGIN
+  CGB_CHECK(e && e->bound, "engine not bound");
+  e->prog_cycle.run(S(stream));
+  e->prog_G.run(S(stream));
+  CGB_API_END
+}
+
+int cgb_phase_discriminators(cgb_engine_t* e, void* stream) {
+  CGB_API_BEGIN
+  CGB_CHECK(e && e->bound, "engine not bound");
+  e->prog_D.run(S(stream));
+  CGB_API_END
+}
+
+int cgb_adam(cgb_engine_t* e, int group, void* stream) {
+  CGB_API_BEGIN
+  CGB_CHECK(e && e->bound && group >= 0 && group < 2, "bad argument / engine not bound");
+  e->prog_adam[group].run(S(stream));
+  CGB_API_END
+}
+
+static void run_step_eager(cgb_engine* e, cudaStream_t st) {
+  e->prog_set_inputs.run(st);
+  e->prog_cycle.run(st);
+  e->prog_G.run(st);
+  e->prog_adam[0].run(st);
+  e->prog_D.run(st);
+  e->prog_adam[1].run(st);
+}
+
+int cgb_train_step(cgb_engine_t* e, void* stream) {
+  CGB_API_BEGIN
+  CGB_CHECK(e && e->bound, "engine not bound");
+  cudaStream_t st = S(stream);
+  static const bool no_graph = std::getenv("CGB_NO_GRAPH") != nullptr;
+  // first call runs eagerly (configures kernel attributes, validates); the second call captures the
+  // step into a CUDA graph that later calls replay.  The legacy default stream cannot be captured.
+  const bool can_graph = !no_graph && st != nullptr && !e->graph_failed;
+  if (can_graph && e->graph == nullptr && e->step_calls >= 1) {
+    cudaGraph_t g = nullptr;
+    cudaError_t err = cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed);
+    if (err == cudaSuccess) {
+      try {
+        run_step_eager(e, st);
+      } catch (...) {
+        cudaStreamEndCapture(st, &g);
+        if (g) cudaGraphDestroy(g);
+        e->graph_failed = true;
+        throw;
+      }
+      err = cudaStreamEndCapture(st, &g);
+      if (err == cudaSuccess) err = cudaGraphInstantiate(&e->graph, g, 0);
+      if (g) cudaGraphDestroy(g);
+    }
+    if (err != cudaSuccess) {
+      e->graph = nullptr;
+      e->graph_failed = true;
+      cudaGetLastError();
+    }
+  }
+  ++e->step_calls;
+  if (e->graph) {
+    CGB_CUDA(cudaGraphLaunch(e->graph, st));
+  } else {
+    run_step_eager(e, st);
+  }
+  CGB_API_END
+}
+
+int cgb_get_losses_host(cgb_engine_t* e, float* losses_host, void* stream) {
+  CGB_API_BEGIN
+  CGB_CHECK(e && e->bound && losses_host, "bad argument / engine not bound");
+  CGB_CUDA(cudaMemcpyAsync(losses_host, e->losses, CGB_NUM_LOSSES * sizeof(float), cudaMemcpyDeviceToHost, S(stream)));
+  CGB_CUDA(cudaStreamSynchronize(S(stream)));
+  losses_host[CGB_LOSS_G] = 0.f;
+  for (int i = CGB_LOSS_G_A; i <= CGB_LOSS_IDT_B; ++i) losses_host[CGB_LOSS_G] += losses_host[i];
+  CGB_API_END
+}
+
+int cgb_train_step_host(cgb_engine_t* e, const float* real_A_host, const float* real_B_host, float* losses_host,
+                        void* stream) {
+  CGB_API_BEGIN
+  CGB_CHECK(e && e->bound && real_A_host && real_B_host && losses_host, "bad argument / engine not bound");
+  const size_t bytes = (size_t)e->cfg.batch * 3 * e->cfg.size * e->cfg.size * sizeof(float);
+  CGB_CUDA(cudaMemcpyAsync(e->staging[0], real_A_host, bytes, cudaMemcpyHostToDevice, S(stream)));
+  CGB_CUDA(cudaMemcpyAsync(e->staging[1], real_B_host, bytes, cudaMemcpyHostToDevice, S(stream)));
+  int rc = cgb_train_step(e, stream);
+  if (rc != 0) return rc;
+  rc = cgb_get_losses_host(e, losses_host, stream);
+  if (rc != 0) return rc;
+  CGB_API_END
+}
+
+long long cgb_launches_per_step(const cgb_engine_t* e) {
+  if (!e || !e->bound) return -1;
+  return e->prog_set_inputs.launches + e->prog_cycle.launches + e->prog_G.launches + e->prog_D.launches +
+         e->prog_adam[0].launches + e->prog_adam[1].launches;
+}
+
+int cgb_profile_kind(cgb_engine_t* e, int kind, int reps, void* stream, float* ms_per_step, long long* launches,
+                     double* flops) {
+  CGB_API_BEGIN
+  CGB_CHECK(e && e->bound && kind > 0 && kind < kNumOpKinds && reps > 0, "bad argument / engine not bound");
+  cudaStream_t st = S(stream);
+  const Program* progs[3] = {&e->prog_cycle, &e->prog_G, &e->prog_D};
+  long long count = 0;
+  double fl = 0;
+  for (const Program* p : progs) p->run_kind(kind, st, &count, &fl);  // warm-up + accounting
+  cudaEvent_t e0, e1;
+  CGB_CUDA(cudaEventCreate(&e0));
+  CGB_CUDA(cudaEventCreate(&e1));
+  CGB_CUDA(cudaEventRecord(e0, st));
+  for (int r = 0; r < reps; ++r)
+    for (const Program* p : progs) p->run_kind(kind, st, nullptr, nullptr);
+  CGB_CUDA(cudaEventRecord(e1, st));
+  CGB_CUDA(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  CGB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (ms_per_step) *ms_per_step = ms / reps;
+  if (launches) *launches = count;
+  if (flops) *flops = fl;
+  CGB_API_END
+}
+
+double cgb_conv_flops_per_step(const cgb_engine_t* e) { return (e && e->bound) ? e->conv_flops : -1.0; }
+
+// ------------------------------------------------------------------------------------------------
+// Single-layer harnesses for the parity tests
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct Scratch {
+  std::vector<void*> ptrs;
+  ~Scratch() {
+    for (void* p : ptrs) cudaFree(p);
+  }
+  void* alloc(size_t bytes) {
+    void* p = nullptr;
+    CGB_CUDA(cudaMalloc(&p, bytes));
+    CGB_CUDA(cudaMemset(p, 0, bytes));
+    ptrs.push_back(p);
+    return p;
+  }
+  TensorDesc tensor(int N, int H, int W, int C, int halo) {
+    TensorDesc t;
+    t.N = N; t.H = H; t.W = W; t.C = C; t.halo = halo;
+    t.ptr = static_cast<bf16*>(alloc((size_t)t.elems() * sizeof(bf16)));
+    return t;
+  }
+};
+
+// torch layout -> master [Cout][T][Cin]   (conv: [Cout][Cin][k][k]; transposed: [Cin][Cout][k][k])
+std::vector<float> to_master(const std::vector<float>& w, int cout, int cin, int k, bool transposed) {
+  const int T = k * k;
+  std::vector<float> m((size_t)cout * T * cin);
+  for (int co = 0; co < cout; ++co)
+    for (int t = 0; t < T; ++t)
+      for (int ci = 0; ci < cin; ++ci) {
+        const size_t src = transposed ? ((size_t)ci * cout + co) * T + t : ((size_t)co * cin + ci) * T + t;
+        m[((size_t)co * T + t) * cin + ci] = w[src];
+      }
+  return m;
+}
+}  // namespace
+
+int cgb_conv_layer_test(int n, int h, int w, int cin, int cout, int k, int stride, int pad, int reflect,
+                        int transposed, int act, const float* x, const float* weight, const float* bias,
+                        const float* dy, float* y, float* dx, float* dw, float* db) {
+  CGB_API_BEGIN
+  CGB_CHECK(x && weight, "x and weight are required");
+  int sm = 148;
+  cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, 0);
+  ConvSpec s;
+  s.Cin = cin; s.Cout = cout;
+  s.CinS = cin % 64 == 0 ? cin : 16;
+  s.CoutS = cout % 64 == 0 ? cout : 16;
+  s.k = k; s.stride = stride; s.pad = pad; s.reflect = reflect != 0; s.transposed = transposed != 0;
+  CGB_CHECK(cin % 64 == 0 || cin <= 16, "cin must be a multiple of 64 or <= 16");
+  CGB_CHECK(cout % 64 == 0 || cout <= 16, "cout must be a multiple of 64 or <= 16");
+  const int T = k * k, ho = out_extent(s, h), wo = out_extent(s, w);
+  Scratch sc;
+  const int halo = s.reflect ? pad : 0;
+  TensorDesc X = sc.tensor(n, h, w, s.CinS, halo);
+  TensorDesc Y = sc.tensor(n, ho, wo, s.CoutS, 0);
+  nchw_to_nhwc(x, cin, X, 0);
+  // weights: torch layout (device) -> master -> packs via the product pack kernel
+  const size_t wn = (size_t)cout * T * cin;
+  std::vector<float> wh(wn);
+  CGB_CUDA(cudaMemcpy(wh.data(), weight, wn * sizeof(float), cudaMemcpyDeviceToHost));
+  std::vector<float> wm = to_master(wh, cout, cin, k, s.transposed);
+  float* d_master = static_cast<float*>(sc.alloc(wn * sizeof(float)));
+  CGB_CUDA(cudaMemcpy(d_master, wm.data(), wn * sizeof(float), cudaMemcpyHostToDevice));
+  const long long wf_elems = packed_wf_elems(s), wt_elems = packed_wt_elems(s);
+  bf16* arena = static_cast<bf16*>(sc.alloc((size_t)(wf_elems + wt_elems + 1024) * sizeof(bf16)));
+  PackEntry pe{};
+  pe.src_off = 0; pe.wf_off = 0; pe.wt_off = (wf_elems + 511) / 512 * 512;
+  pe.Cout = cout; pe.Cin = cin; pe.T = T; pe.CinS = s.CinS; pe.CoutS = s.CoutS;
+  PackEntry* d_pe = static_cast<PackEntry*>(sc.alloc(sizeof(PackEntry)));
+  CGB_CUDA(cudaMemcpy(d_pe, &pe, sizeof(pe), cudaMemcpyHostToDevice));
+  pack_weights(d_master, d_pe, 1, (int)wn, arena, 0);
+
+  IgemmPlan pf = plan_fprop(s, X, arena + pe.wf_off, Y, bias, act, sm);
+  KIter* kt = static_cast<KIter*>(sc.alloc(pf.kiters.size() * sizeof(KIter)));
+  CGB_CUDA(cudaMemcpy(kt, pf.kiters.data(), pf.kiters.size() * sizeof(KIter), cudaMemcpyHostToDevice));
+  pf.args.kiters = kt;
+  run(pf, 0);
+  if (y) nhwc_to_nchw(Y, cout, y, 0);
+
+  if (dy) {
+    TensorDesc DY = sc.tensor(n, ho, wo, s.CoutS, 0);
+    nchw_to_nhwc(dy, cout, DY, 0);
+    if (dx) {
+      TensorDesc DX = sc.tensor(n, h + 2 * halo, w + 2 * halo, s.CinS, 0);
+      IgemmPlan pd = plan_dgrad(s, DY, arena + pe.wt_off, DX, sm);
+      KIter* kd = static_cast<KIter*>(sc.alloc(pd.kiters.size() * sizeof(KIter)));
+      CGB_CUDA(cudaMemcpy(kd, pd.kiters.data(), pd.kiters.size() * sizeof(KIter), cudaMemcpyHostToDevice));
+      pd.args.kiters = kd;
+      run(pd, 0);
+      if (halo == 0) {
+        nhwc_to_nchw(DX, cin, dx, 0);
+      } else {
+        // fold the padded-domain gradient back onto the interior with the product fold path:
+        // tanh_bwd-free route: use in_bwd machinery's loader through a plain fold (act none, no norm)
+        // -> implemented by a zero-initialised interior tensor + GradSrc fold via l1-free tanh? Keep it
+        // simple: copy the padded-domain tensor out and fold on the host.
+        std::vector<bf16> hb((size_t)DX.elems());
+        CGB_CUDA(cudaMemcpy(hb.data(), DX.ptr, hb.size() * sizeof(bf16), cudaMemcpyDeviceToHost));
+        std::vector<float> out((size_t)n * cin * h * w, 0.f);
+        const int HP = h + 2 * halo, WP = w + 2 * halo;
+        auto refl = [](int i, int nn) { if (i < 0) i = -i; if (i >= nn) i = 2 * (nn - 1) - i; return i; };
+        for (int b = 0; b < n; ++b)
+          for (int hp = 0; hp < HP; ++hp)
+            for (int wp = 0; wp < WP; ++wp) {
+              const int hs = refl(hp - halo, h), ws = refl(wp - halo, w);
+              for (int c = 0; c < cin; ++c)
+                out[(((size_t)b * cin + c) * h + hs) * w + ws] +=
+                    __bfloat162float(hb[(((size_t)b * HP + hp) * WP + wp) * s.CinS + c]);
+            }
+        CGB_CUDA(cudaMemcpy(dx, out.data(), out.size() * sizeof(float), cudaMemcpyHostToDevice));
+      }
+    }
+    if (dw) {
+      float* g = static_cast<float*>(sc.alloc(wn * sizeof(float)));
+      if (tc_supports_wgrad(s)) {
+        WgradPlan pw = plan_wgrad(s, X, DY, g, sm);
+        WTap* tp = static_cast<WTap*>(sc.alloc(pw.taps.size() * sizeof(WTap)));
+        CGB_CUDA(cudaMemcpy(tp, pw.taps.data(), pw.taps.size() * sizeof(WTap), cudaMemcpyHostToDevice));
+        pw.args.taps = tp;
+        run(pw, 0);
+      } else {
+        wgrad_direct(s, X, DY, g, 0);
+      }
+      std::vector<float> gm(wn), gt(wn);
+      CGB_CUDA(cudaMemcpy(gm.data(), g, wn * sizeof(float), cudaMemcpyDeviceToHost));
+      for (int co = 0; co < cout; ++co)
+        for (int t = 0; t < T; ++t)
+          for (int ci = 0; ci < cin; ++ci) {
+            const size_t dst = s.transposed ? ((size_t)ci * cout + co) * T + t : ((size_t)co * cin + ci) * T + t;
+            gt[dst] = gm[((size_t)co * T + t) * cin + ci];
+          }
+      CGB_CUDA(cudaMemcpy(dw, gt.data(), wn * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    if (db) {
+      CGB_CUDA(cudaMemset(db, 0, cout * sizeof(float)));
+      bias_grad(DY, cout, db, 0);
+    }
+  }
+  CGB_CUDA(cudaDeviceSynchronize());
+  CGB_API_END
+}
+
+int cgb_instnorm_test(int n, int c, int h, int w, int act, const float* y, const float* residual, const float* da,
+                      float* out, float* dy_out) {
+  CGB_API_BEGIN
+  CGB_CHECK(y && out, "y and out are required");
+  CGB_CHECK(c % 8 == 0, "channels must be a multiple of 8");
+  Scratch sc;
+  TensorDesc Y = sc.tensor(n, h, w, c, 0);
+  TensorDesc O = sc.tensor(n, h, w, c, 1);  // exercises the reflect-halo writer
+  float2* stats = static_cast<float2*>(sc.alloc((size_t)n * c * sizeof(float2)));
+  float2* bstats = static_cast<float2*>(sc.alloc((size_t)n * c * sizeof(float2)));
+  nchw_to_nhwc(y, c, Y, 0);
+  in_stats(Y, stats, 0);
+  TensorDesc R;
+  if (residual) {
+    R = sc.tensor(n, h, w, c, 1);
+    nchw_to_nhwc(residual, c, R, 0);
+  }
+  in_apply(Y, stats, act, residual ? &R : nullptr, O, 0);
+  nhwc_to_nchw(O, c, out, 0);
+  if (da && dy_out) {
+    TensorDesc DA = sc.tensor(n, h, w, c, 0);
+    TensorDesc DY = sc.tensor(n, h, w, c, 0);
+    nchw_to_nhwc(da, c, DA, 0);
+    GradSrc g;
+    g.g1 = &DA;
+    in_bwd_reduce(Y, stats, g, act, nullptr, bstats, 0);
+    in_bwd_apply(Y, stats, bstats, g, act, DY, 0);
+    nhwc_to_nchw(DY, c, dy_out, 0);
+  }
+  CGB_CUDA(cudaDeviceSynchronize());
+  CGB_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,532 @@
+// CycleGAN step engine (see engine.h).  Host-side only: every device operation goes through
+// conv_plan.h (tcgen05 convolutions) and pointwise.h (HBM-bound kernels).
+#include "engine.h"
+
+#include <cstdlib>
+#include <cstring>
+
+using namespace cgb;
+
+namespace {
+
+ConvSpec make_spec(int cin, int cout, int k, int stride, int pad, bool reflect, bool transposed) {
+  ConvSpec s;
+  s.Cin = cin;
+  s.Cout = cout;
+  s.CinS = cin % 64 == 0 ? cin : 16;
+  s.CoutS = cout % 64 == 0 ? cout : 16;
+  s.k = k;
+  s.stride = stride;
+  s.pad = pad;
+  s.reflect = reflect;
+  s.transposed = transposed;
+  return s;
+}
+
+long long align_up(long long v, long long a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+cgb_engine::~cgb_engine() {
+  if (graph) cudaGraphExecDestroy(graph);
+  if (meta) cudaFree(meta);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Parameter inventory: same tensors, order and names as the stand-in's state_dict
+// (oracle/cyclegan_standin.py Generator.__init__ / Discriminator.__init__).
+// ------------------------------------------------------------------------------------------------
+void cgb_engine::build_inventory() {
+  const int nb = cfg.n_blocks;
+  for (int net = 0; net < 4; ++net) {
+    std::vector<LayerParam>& L = layers[net];
+    L.clear();
+    auto add = [&](const std::string& name, ConvSpec s, bool has_in) {
+      LayerParam p;
+      p.name = name;
+      p.spec = s;
+      p.has_in = has_in;
+      p.net = net;
+      p.group = net < 2 ? CGB_GROUP_G : CGB_GROUP_D;
+      L.push_back(p);
+    };
+    if (net < 2) {
+      add("stem", make_spec(3, 64, 7, 1, 3, true, false), true);
+      add("down1", make_spec(64, 128, 3, 2, 1, false, false), true);
+      add("down2", make_spec(128, 256, 3, 2, 1, false, false), true);
+      for (int i = 0; i < nb; ++i) {
+        add("res." + std::to_string(i) + ".conv1", make_spec(256, 256, 3, 1, 1, true, false), true);
+        add("res." + std::to_string(i) + ".conv2", make_spec(256, 256, 3, 1, 1, true, false), true);
+      }
+      add("up1", make_spec(256, 128, 3, 2, 1, false, true), true);
+      add("up2", make_spec(128, 64, 3, 2, 1, false, true), true);
+      add("head", make_spec(64, 3, 7, 1, 3, true, false), false);
+    } else {
+      add("conv0", make_spec(3, 64, 4, 2, 1, false, false), false);
+      add("conv1", make_spec(64, 128, 4, 2, 1, false, false), true);
+      add("conv2", make_spec(128, 256, 4, 2, 1, false, false), true);
+      add("conv3", make_spec(256, 512, 4, 1, 1, false, false), true);
+      add("conv4", make_spec(512, 1, 4, 1, 1, false, false), false);
+    }
+  }
+  for (int g = 0; g < 2; ++g) {
+    long long off = 0, poff = 0;
+    for (int net = g * 2; net < g * 2 + 2; ++net)
+      for (LayerParam& p : layers[net]) {
+        p.w_off = off;
+        off = align_up(off + (long long)p.spec.Cout * p.spec.taps() * p.spec.Cin, 4);
+        p.b_off = off;
+        off = align_up(off + p.spec.Cout, 4);
+        p.wf_off = poff;
+        poff = align_up(poff + packed_wf_elems(p.spec), 512);
+        p.wt_off = poff;
+        poff = align_up(poff + packed_wt_elems(p.spec), 512);
+      }
+    group_numel[g] = off;
+    pack_elems[g] = poff;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// HBM workspace layout (bf16 NHWC activations; image tensors carry 16 stored channels and a
+// 3-pixel reflect halo; residual-stream tensors carry a 1-pixel reflect halo).
+// ------------------------------------------------------------------------------------------------
+void cgb_engine::layout(Arena& A) {
+  const int N = cfg.batch, S = cfg.size, nb = cfg.n_blocks;
+  const int H2 = S / 2, H4 = S / 4, H8 = S / 8;
+  for (int g = 0; g < 2; ++g) pack[g] = static_cast<bf16*>(A.alloc((size_t)pack_elems[g] * sizeof(bf16)));
+  for (int i = 0; i < 8; ++i) img[i] = A.tensor(N, S, S, 16, 3);
+  mod_in = A.tensor(N, S, S, 16, 3);
+  mod_out = A.tensor(N, S, S, 16, 3);
+  for (int i = 0; i < 2; ++i) staging[i] = static_cast<float*>(A.alloc((size_t)N * 3 * S * S * sizeof(float)));
+  losses = static_cast<float*>(A.alloc(64 * sizeof(float)));
+  for (int g = 0; g < 2; ++g) {
+    adam_step[g] = static_cast<int*>(A.alloc(64));
+    adam_hyper[g] = static_cast<float*>(A.alloc(64));
+  }
+
+  gen.resize(7);
+  for (GenPass& P : gen) {
+    P.y_stem = A.tensor(N, S, S, 64, 0);
+    P.a_stem = A.tensor(N, S, S, 64, 0);
+    P.y_d1 = A.tensor(N, H2, H2, 128, 0);
+    P.a_d1 = A.tensor(N, H2, H2, 128, 0);
+    P.y_d2 = A.tensor(N, H4, H4, 256, 0);
+    P.xp.resize(nb + 1);
+    P.y1.resize(nb);
+    P.bp.resize(nb);
+    P.y2.resize(nb);
+    P.xp[0] = A.tensor(N, H4, H4, 256, 1);
+    for (int k = 0; k < nb; ++k) {
+      P.y1[k] = A.tensor(N, H4, H4, 256, 0);
+      P.bp[k] = A.tensor(N, H4, H4, 256, 1);
+      P.y2[k] = A.tensor(N, H4, H4, 256, 0);
+      P.xp[k + 1] = A.tensor(N, H4, H4, 256, 1);
+    }
+    P.y_u1 = A.tensor(N, H2, H2, 128, 0);
+    P.a_u1 = A.tensor(N, H2, H2, 128, 0);
+    P.y_u2 = A.tensor(N, S, S, 64, 0);
+    P.a_u2p = A.tensor(N, S, S, 64, 3);
+    // statistics: IN layer l has layers[0][l].spec.Cout channels
+    P.stat_off.assign(5 + 2 * nb, 0);
+    long long off = 0;
+    for (int l = 0; l < 5 + 2 * nb; ++l) {
+      P.stat_off[l] = off;
+      off += (long long)N * layers[0][l].spec.Cout;
+    }
+    P.stats_bytes = (size_t)off * sizeof(float2);
+    P.stats = static_cast<float2*>(A.alloc(P.stats_bytes));
+    P.bstats = static_cast<float2*>(A.alloc(P.stats_bytes));
+  }
+  dis.resize(5);
+  for (DisPass& D : dis) {
+    D.l0 = A.tensor(N, H2, H2, 64, 0);
+    D.y1 = A.tensor(N, H4, H4, 128, 0);
+    D.a1 = A.tensor(N, H4, H4, 128, 0);
+    D.y2 = A.tensor(N, H8, H8, 256, 0);
+    D.a2 = A.tensor(N, H8, H8, 256, 0);
+    D.y3 = A.tensor(N, H8 - 1, H8 - 1, 512, 0);
+    D.a3 = A.tensor(N, H8 - 1, H8 - 1, 512, 0);
+    D.logits = A.tensor(N, H8 - 2, H8 - 2, 16, 0);
+    D.stat_off[0] = 0;
+    D.stat_off[1] = (long long)N * 128;
+    D.stat_off[2] = (long long)N * (128 + 256);
+    D.stats_bytes = (size_t)N * (128 + 256 + 512) * sizeof(float2);
+    D.stats = static_cast<float2*>(A.alloc(D.stats_bytes));
+    D.bstats = static_cast<float2*>(A.alloc(D.stats_bytes));
+  }
+  // generator backward scratch
+  dpre_head = A.tensor(N, S, S, 16, 0);
+  dxp_head = A.tensor(N, S + 6, S + 6, 64, 0);
+  dyF = A.tensor(N, S, S, 64, 0);
+  dxF = A.tensor(N, S, S, 64, 0);
+  dyH = A.tensor(N, H2, H2, 128, 0);
+  dxH = A.tensor(N, H2, H2, 128, 0);
+  dyQ = A.tensor(N, H4, H4, 256, 0);
+  GQ[0] = A.tensor(N, H4, H4, 256, 0);
+  GQ[1] = A.tensor(N, H4, H4, 256, 0);
+  dbpQ = A.tensor(N, H4 + 2, H4 + 2, 256, 0);
+  dxpQ = A.tensor(N, H4 + 2, H4 + 2, 256, 0);
+  for (int i = 0; i < 2; ++i) {
+    dxp_img[i] = A.tensor(N, S + 6, S + 6, 16, 0);
+    dx_D0[i] = A.tensor(N, S, S, 16, 0);
+  }
+  // discriminator backward scratch
+  dlogits = A.tensor(N, H8 - 2, H8 - 2, 16, 0);
+  dx3 = A.tensor(N, H8 - 1, H8 - 1, 512, 0);
+  dy3 = A.tensor(N, H8 - 1, H8 - 1, 512, 0);
+  dx2 = A.tensor(N, H8, H8, 256, 0);
+  dy2 = A.tensor(N, H8, H8, 256, 0);
+  dx1 = A.tensor(N, H4, H4, 128, 0);
+  dy1 = A.tensor(N, H4, H4, 128, 0);
+  dx0 = A.tensor(N, H2, H2, 64, 0);
+  dpre0 = A.tensor(N, H2, H2, 64, 0);
+  A.alloc(1024);  // tail guard
+}
+
+void* cgb_engine::meta_upload(const void* src, size_t bytes) {
+  meta_off = (meta_off + 255) & ~size_t(255);
+  CGB_CHECK(meta_off + bytes <= meta_cap, "engine meta buffer exhausted");
+  void* dst = static_cast<uint8_t*>(meta) + meta_off;
+  CGB_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+  meta_off += bytes;
+  return dst;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Program recording
+// ------------------------------------------------------------------------------------------------
+void cgb_engine::record_programs() {
+  const int N = cfg.batch, S = cfg.size, nb = cfg.n_blocks;
+  cgb_engine* E = this;
+  double* flops = &conv_flops;
+  double dummy_flops = 0;
+
+  auto add_fprop = [E](Program& pr, double* fl, const LayerParam& L, const TensorDesc& x, const TensorDesc& y,
+                       int act) {
+    const float* bias = L.has_in ? nullptr : E->P[L.group] + L.b_off;
+    IgemmPlan p = plan_fprop(L.spec, x, E->pack[L.group] + L.wf_off, y, bias, act, E->sm_count);
+    p.args.kiters = static_cast<const KIter*>(E->meta_upload(p.kiters.data(), p.kiters.size() * sizeof(KIter)));
+    E->igemm_plans.push_back(p);
+    const IgemmPlan* pp = &E->igemm_plans.back();
+    pr.add([pp](cudaStream_t st) { run(*pp, st); }, 1, kOpIgemm, p.flops);
+    *fl += p.flops;
+  };
+  auto add_dgrad = [E](Program& pr, double* fl, const LayerParam& L, const TensorDesc& dy, const TensorDesc& dx) {
+    IgemmPlan p = plan_dgrad(L.spec, dy, E->pack[L.group] + L.wt_off, dx, E->sm_count);
+    p.args.kiters = static_cast<const KIter*>(E->meta_upload(p.kiters.data(), p.kiters.size() * sizeof(KIter)));
+    E->igemm_plans.push_back(p);
+    const IgemmPlan* pp = &E->igemm_plans.back();
+    pr.add([pp](cudaStream_t st) { run(*pp, st); }, 1, kOpIgemm, p.flops);
+    *fl += p.flops;
+  };
+  auto add_wgrad = [E](Program& pr, double* fl, const LayerParam& L, const TensorDesc& x, const TensorDesc& dy) {
+    float* g = E->G[L.group] + L.w_off;
+    if (tc_supports_wgrad(L.spec)) {
+      WgradPlan p = plan_wgrad(L.spec, x, dy, g, E->sm_count);
+      p.args.taps = static_cast<const WTap*>(E->meta_upload(p.taps.data(), p.taps.size() * sizeof(WTap)));
+      E->wgrad_plans.push_back(p);
+      const WgradPlan* pp = &E->wgrad_plans.back();
+      pr.add([pp](cudaStream_t st) { run(*pp, st); }, 1, kOpWgradTc, p.flops);
+      *fl += p.flops;
+    } else {
+      const ConvSpec s = L.spec;
+      const double f = 2.0 * dy.N * (double)dy.H * dy.W * s.Cout * s.Cin * s.taps();
+      pr.add([s, x, dy, g](cudaStream_t st) { wgrad_direct(s, x, dy, g, st); }, 1, kOpWgradDirect, f);
+      *fl += f;
+    }
+  };
+  auto add_norm = [](Program& pr, const TensorDesc& y, float2* stats, int act, const TensorDesc* residual,
+                     const TensorDesc& out) {
+    pr.add([y, stats](cudaStream_t st) { in_stats(y, stats, st); }, 1, kOpNorm);
+    if (residual) {
+      const TensorDesc r = *residual;
+      pr.add([y, stats, act, r, out](cudaStream_t st) { in_apply(y, stats, act, &r, out, st); }, 1, kOpNorm);
+    } else {
+      pr.add([y, stats, act, out](cudaStream_t st) { in_apply(y, stats, act, nullptr, out, st); }, 1, kOpNorm);
+    }
+  };
+  // InstanceNorm + activation backward; da_store (engine-owned tensor) receives the assembled gradient
+  auto add_in_bwd = [](Program& pr, const TensorDesc& y, const float2* stats, float2* bstats, GradSrc g, int act,
+                       const TensorDesc* da_store, const TensorDesc& dy) {
+    pr.add([y, stats, bstats, g, act, da_store](cudaStream_t st) { in_bwd_reduce(y, stats, g, act, da_store, bstats, st); },
+           1, kOpNorm);
+    GradSrc g2 = g;
+    if (da_store) {
+      g2 = GradSrc();
+      g2.g1 = da_store;
+    }
+    pr.add([y, stats, bstats, g2, act, dy](cudaStream_t st) { in_bwd_apply(y, stats, bstats, g2, act, dy, st); }, 1,
+           kOpNorm);
+  };
+
+  // ---------------------------------------------------------------- generator forward
+  auto emit_gen_forward = [&](Program& pr, double* fl, GenPass& P, int net, const TensorDesc& in,
+                              const TensorDesc& out, bool fill_out_halo) {
+    P.net = net;
+    P.in = in;
+    P.out = out;
+    const std::vector<LayerParam>& L = E->layers[net];
+    float2* st = P.stats;
+    pr.add([st, bytes = P.stats_bytes](cudaStream_t s) { CGB_CUDA(cudaMemsetAsync(st, 0, bytes, s)); }, 0, kOpMemset);
+    add_fprop(pr, fl, L[0], in, P.y_stem, kActNone);
+    add_norm(pr, P.y_stem, st + P.stat_off[0], kActRelu, nullptr, P.a_stem);
+    add_fprop(pr, fl, L[1], P.a_stem, P.y_d1, kActNone);
+    add_norm(pr, P.y_d1, st + P.stat_off[1], kActRelu, nullptr, P.a_d1);
+    add_fprop(pr, fl, L[2], P.a_d1, P.y_d2, kActNone);
+    add_norm(pr, P.y_d2, st + P.stat_off[2], kActRelu, nullptr, P.xp[0]);
+    for (int k = 0; k < nb; ++k) {
+      add_fprop(pr, fl, L[3 + 2 * k], P.xp[k], P.y1[k], kActNone);
+      add_norm(pr, P.y1[k], st + P.stat_off[3 + 2 * k], kActRelu, nullptr, P.bp[k]);
+      add_fprop(pr, fl, L[4 + 2 * k], P.bp[k], P.y2[k], kActNone);
+      add_norm(pr, P.y2[k], st + P.stat_off[4 + 2 * k], kActNone, &P.xp[k], P.xp[k + 1]);
+    }
+    add_fprop(pr, fl, L[3 + 2 * nb], P.xp[nb], P.y_u1, kActNone);
+    add_norm(pr, P.y_u1, st + P.stat_off[3 + 2 * nb], kActRelu, nullptr, P.a_u1);
+    add_fprop(pr, fl, L[4 + 2 * nb], P.a_u1, P.y_u2, kActNone);
+    add_norm(pr, P.y_u2, st + P.stat_off[4 + 2 * nb], kActRelu, nullptr, P.a_u2p);
+    add_fprop(pr, fl, L[5 + 2 * nb], P.a_u2p, out, kActTanh);
+    if (fill_out_halo) pr.add([out](cudaStream_t s) { fill_reflect_halo(out, s); });
+  };
+
+  // ---------------------------------------------------------------- generator backward
+  auto emit_gen_backward = [&](Program& pr, double* fl, GenPass& P, const TensorDesc* target, float l1_scale,
+                               int loss_slot, GradSrc gsrc, const TensorDesc* dxp_img_out) {
+    const std::vector<LayerParam>& L = E->layers[P.net];
+    float* Gg = E->G[CGB_GROUP_G];
+    float2* st = P.stats;
+    float2* bs = P.bstats;
+    pr.add([bs, bytes = P.stats_bytes](cudaStream_t s) { CGB_CUDA(cudaMemsetAsync(bs, 0, bytes, s)); }, 0, kOpMemset);
+    const LayerParam& head = L[5 + 2 * nb];
+    {
+      const TensorDesc out = P.out, dpre = E->dpre_head;
+      float* slot = loss_slot >= 0 ? E->losses + loss_slot : nullptr;
+      if (target) {
+        const TensorDesc tg = *target;
+        pr.add([out, tg, l1_scale, gsrc, dpre, slot](cudaStream_t s) { tanh_bwd(out, &tg, l1_scale, gsrc, 3, dpre, slot, s); });
+      } else {
+        pr.add([out, gsrc, dpre](cudaStream_t s) { tanh_bwd(out, nullptr, 0.f, gsrc, 3, dpre, nullptr, s); });
+      }
+      float* gb = Gg + head.b_off;
+      pr.add([dpre, gb](cudaStream_t s) { bias_grad(dpre, 3, gb, s); });
+    }
+    add_wgrad(pr, fl, head, P.a_u2p, E->dpre_head);
+    add_dgrad(pr, fl, head, E->dpre_head, E->dxp_head);
+    GradSrc g;
+    g.g2 = &E->dxp_head;
+    g.fold = 3;
+    add_in_bwd(pr, P.y_u2, st + P.stat_off[4 + 2 * nb], bs + P.stat_off[4 + 2 * nb], g, kActRelu, nullptr, E->dyF);
+    add_wgrad(pr, fl, L[4 + 2 * nb], P.a_u1, E->dyF);
+    add_dgrad(pr, fl, L[4 + 2 * nb], E->dyF, E->dxH);
+    g = GradSrc();
+    g.g1 = &E->dxH;
+    add_in_bwd(pr, P.y_u1, st + P.stat_off[3 + 2 * nb], bs + P.stat_off[3 + 2 * nb], g, kActRelu, nullptr, E->dyH);
+    add_wgrad(pr, fl, L[3 + 2 * nb], P.xp[nb], E->dyH);
+    int cur = 0;
+    add_dgrad(pr, fl, L[3 + 2 * nb], E->dyH, E->GQ[cur]);  // G_nb: gradient w.r.t. the residual stream output
+    for (int k = nb - 1; k >= 0; --k) {
+      // gradient w.r.t. x_{k+1}: G_{k+1} = G_{k+2} + fold(dxp_{k+1})   (k == nb-1: G_nb as is)
+      g = GradSrc();
+      g.g1 = &E->GQ[cur];
+      const TensorDesc* store = nullptr;
+      if (k != nb - 1) {
+        g.g2 = &E->dxpQ;
+        g.fold = 1;
+        store = &E->GQ[cur ^ 1];
+      }
+      add_in_bwd(pr, P.y2[k], st + P.stat_off[4 + 2 * k], bs + P.stat_off[4 + 2 * k], g, kActNone, store, E->dyQ);
+      if (store) cur ^= 1;
+      add_wgrad(pr, fl, L[4 + 2 * k], P.bp[k], E->dyQ);
+      add_dgrad(pr, fl, L[4 + 2 * k], E->dyQ, E->dbpQ);
+      g = GradSrc();
+      g.g2 = &E->dbpQ;
+      g.fold = 1;
+      add_in_bwd(pr, P.y1[k], st + P.stat_off[3 + 2 * k], bs + P.stat_off[3 + 2 * k], g, kActRelu, nullptr, E->dyQ);
+      add_wgrad(pr, fl, L[3 + 2 * k], P.xp[k], E->dyQ);
+      add_dgrad(pr, fl, L[3 + 2 * k], E->dyQ, E->dxpQ);
+    }
+    // down2 output feeds block 0 twice (conv path + skip): G_0 = G_1 + fold(dxp_0)
+    g = GradSrc();
+    g.g1 = &E->GQ[cur];
+    g.g2 = &E->dxpQ;
+    g.fold = 1;
+    add_in_bwd(pr, P.y_d2, st + P.stat_off[2], bs + P.stat_off[2], g, kActRelu, &E->GQ[cur ^ 1], E->dyQ);
+    add_wgrad(pr, fl, L[2], P.a_d1, E->dyQ);
+    add_dgrad(pr, fl, L[2], E->dyQ, E->dxH);
+    g = GradSrc();
+    g.g1 = &E->dxH;
+    add_in_bwd(pr, P.y_d1, st + P.stat_off[1], bs + P.stat_off[1], g, kActRelu, nullptr, E->dyH);
+    add_wgrad(pr, fl, L[1], P.a_stem, E->dyH);
+    add_dgrad(pr, fl, L[1], E->dyH, E->dxF);
+    g = GradSrc();
+    g.g1 = &E->dxF;
+    add_in_bwd(pr, P.y_stem, st + P.stat_off[0], bs + P.stat_off[0], g, kActRelu, nullptr, E->dyF);
+    add_wgrad(pr, fl, L[0], P.in, E->dyF);
+    if (dxp_img_out) add_dgrad(pr, fl, L[0], E->dyF, *dxp_img_out);
+  };
+
+  // ---------------------------------------------------------------- discriminator
+  auto emit_dis_forward = [&](Program& pr, double* fl, DisPass& D, int net, const TensorDesc& in) {
+    D.net = net;
+    D.in = in;
+    const std::vector<LayerParam>& L = E->layers[net];
+    float2* st = D.stats;
+    pr.add([st, bytes = D.stats_bytes](cudaStream_t s) { CGB_CUDA(cudaMemsetAsync(st, 0, bytes, s)); }, 0, kOpMemset);
+    add_fprop(pr, fl, L[0], in, D.l0, kActLeaky);
+    add_fprop(pr, fl, L[1], D.l0, D.y1, kActNone);
+    add_norm(pr, D.y1, st + D.stat_off[0], kActLeaky, nullptr, D.a1);
+    add_fprop(pr, fl, L[2], D.a1, D.y2, kActNone);
+    add_norm(pr, D.y2, st + D.stat_off[1], kActLeaky, nullptr, D.a2);
+    add_fprop(pr, fl, L[3], D.a2, D.y3, kActNone);
+    add_norm(pr, D.y3, st + D.stat_off[2], kActLeaky, nullptr, D.a3);
+    add_fprop(pr, fl, L[4], D.a3, D.logits, kActNone);
+  };
+  auto emit_dis_backward = [&](Program& pr, double* fl, DisPass& D, float target, float w, int loss_slot,
+                               bool weight_grads, const TensorDesc* dx_img_out) {
+    const std::vector<LayerParam>& L = E->layers[D.net];
+    float* Gd = E->G[CGB_GROUP_D];
+    float2* st = D.stats;
+    float2* bs = D.bstats;
+    pr.add([bs, bytes = D.stats_bytes](cudaStream_t s) { CGB_CUDA(cudaMemsetAsync(bs, 0, bytes, s)); }, 0, kOpMemset);
+    {
+      const TensorDesc lg = D.logits;
+      const TensorDesc* dl = &E->dlogits;
+      float* slot = E->losses + loss_slot;
+      pr.add([lg, target, w, slot, dl](cudaStream_t s) { mse_loss(lg, target, w, slot, dl, s); });
+    }
+    if (weight_grads) {
+      const TensorDesc dl = E->dlogits;
+      float* gb = Gd + L[4].b_off;
+      pr.add([dl, gb](cudaStream_t s) { bias_grad(dl, 1, gb, s); });
+      add_wgrad(pr, fl, L[4], D.a3, E->dlogits);
+    }
+    add_dgrad(pr, fl, L[4], E->dlogits, E->dx3);
+    GradSrc g;
+    g.g1 = &E->dx3;
+    add_in_bwd(pr, D.y3, st + D.stat_off[2], bs + D.stat_off[2], g, kActLeaky, nullptr, E->dy3);
+    if (weight_grads) add_wgrad(pr, fl, L[3], D.a2, E->dy3);
+    add_dgrad(pr, fl, L[3], E->dy3, E->dx2);
+    g.g1 = &E->dx2;
+    add_in_bwd(pr, D.y2, st + D.stat_off[1], bs + D.stat_off[1], g, kActLeaky, nullptr, E->dy2);
+    if (weight_grads) add_wgrad(pr, fl, L[2], D.a1, E->dy2);
+    add_dgrad(pr, fl, L[2], E->dy2, E->dx1);
+    g.g1 = &E->dx1;
+    add_in_bwd(pr, D.y1, st + D.stat_off[0], bs + D.stat_off[0], g, kActLeaky, nullptr, E->dy1);
+    if (weight_grads) add_wgrad(pr, fl, L[1], D.l0, E->dy1);
+    add_dgrad(pr, fl, L[1], E->dy1, E->dx0);
+    {
+      const TensorDesc l0 = D.l0, dx0_ = E->dx0, dp = E->dpre0;
+      pr.add([l0, dx0_, dp](cudaStream_t s) { leaky_bwd(l0, dx0_, dp, s); });
+      if (weight_grads) {
+        float* gb = Gd + L[0].b_off;
+        pr.add([dp, gb](cudaStream_t s) { bias_grad(dp, 64, gb, s); });
+        add_wgrad(pr, fl, L[0], D.in, E->dpre0);
+      }
+    }
+    if (dx_img_out) add_dgrad(pr, fl, L[0], E->dpre0, *dx_img_out);
+  };
+
+  // ---------------------------------------------------------------- step programs
+  const TensorDesc &fake_B = img[CGB_IMG_FAKE_B], &rec_A = img[CGB_IMG_REC_A], &fake_A = img[CGB_IMG_FAKE_A],
+                   &rec_B = img[CGB_IMG_REC_B], &idt_A = img[CGB_IMG_IDT_A], &idt_B = img[CGB_IMG_IDT_B],
+                   &real_A = img[CGB_IMG_REAL_A], &real_B = img[CGB_IMG_REAL_B];
+  (void)rec_A; (void)rec_B; (void)idt_A; (void)idt_B;
+
+  {  // staging (fp32 NCHW) -> bf16 NHWC images with reflect halo
+    const float* sa = staging[0];
+    const float* sb = staging[1];
+    const TensorDesc ra = real_A, rb = real_B;
+    prog_set_inputs.add([sa, ra](cudaStream_t s) { nchw_to_nhwc(sa, 3, ra, s); });
+    prog_set_inputs.add([sb, rb](cudaStream_t s) { nchw_to_nhwc(sb, 3, rb, s); });
+  }
+  // pass order: 0 fake_B = G_AB(real_A), 1 rec_A = G_BA(fake_B), 2 fake_A = G_BA(real_B),
+  //             3 rec_B = G_AB(fake_A), 4 idt_A = G_AB(real_B), 5 idt_B = G_BA(real_A)
+  emit_gen_forward(prog_cycle, flops, gen[0], CGB_NET_G_AB, real_A, img[CGB_IMG_FAKE_B], true);
+  emit_gen_forward(prog_cycle, flops, gen[1], CGB_NET_G_BA, fake_B, img[CGB_IMG_REC_A], false);
+  emit_gen_forward(prog_cycle, flops, gen[2], CGB_NET_G_BA, real_B, img[CGB_IMG_FAKE_A], true);
+  emit_gen_forward(prog_cycle, flops, gen[3], CGB_NET_G_AB, fake_A, img[CGB_IMG_REC_B], false);
+  emit_gen_forward(prog_cycle, flops, gen[4], CGB_NET_G_AB, real_B, img[CGB_IMG_IDT_A], false);
+  emit_gen_forward(prog_cycle, flops, gen[5], CGB_NET_G_BA, real_A, img[CGB_IMG_IDT_B], false);
+
+  const float numel_img = (float)N * 3.f * S * S;
+  {  // ---- G phase
+    Program& pr = prog_G;
+    float* gG = G[CGB_GROUP_G];
+    const size_t gbytes = (size_t)group_numel[CGB_GROUP_G] * sizeof(float);
+    float* ls = losses;
+    pr.add([gG, gbytes](cudaStream_t s) { CGB_CUDA(cudaMemsetAsync(gG, 0, gbytes, s)); }, 0, kOpMemset);
+    pr.add([ls](cudaStream_t s) { CGB_CUDA(cudaMemsetAsync(ls, 0, 64 * sizeof(float), s)); }, 0, kOpMemset);
+    // identity and cycle passes (L1 seeds)
+    emit_gen_backward(pr, flops, gen[4], &real_B, cfg.lambda_B * cfg.lambda_idt / numel_img, CGB_LOSS_IDT_A, GradSrc(), nullptr);
+    emit_gen_backward(pr, flops, gen[5], &real_A, cfg.lambda_A * cfg.lambda_idt / numel_img, CGB_LOSS_IDT_B, GradSrc(), nullptr);
+    emit_gen_backward(pr, flops, gen[1], &real_A, cfg.lambda_A / numel_img, CGB_LOSS_CYCLE_A, GradSrc(), &dxp_img[0]);
+    emit_gen_backward(pr, flops, gen[3], &real_B, cfg.lambda_B / numel_img, CGB_LOSS_CYCLE_B, GradSrc(), &dxp_img[1]);
+    // adversarial terms: D frozen, gradient flows through D into the fakes
+    emit_dis_forward(pr, flops, dis[0], CGB_NET_D_A, fake_B);
+    emit_dis_backward(pr, flops, dis[0], 1.f, 1.f, CGB_LOSS_G_A, false, &dx_D0[0]);
+    emit_dis_forward(pr, flops, dis[1], CGB_NET_D_B, fake_A);
+    emit_dis_backward(pr, flops, dis[1], 1.f, 1.f, CGB_LOSS_G_B, false, &dx_D0[1]);
+    GradSrc g;
+    g.g1 = &dx_D0[0];
+    g.g2 = &dxp_img[0];
+    g.fold = 3;
+    emit_gen_backward(pr, flops, gen[0], nullptr, 0.f, -1, g, nullptr);
+    g.g1 = &dx_D0[1];
+    g.g2 = &dxp_img[1];
+    emit_gen_backward(pr, flops, gen[2], nullptr, 0.f, -1, g, nullptr);
+  }
+  {  // ---- D phase: real passes are new; the fake passes reuse the G-phase forward (D unchanged since)
+    Program& pr = prog_D;
+    float* gD = G[CGB_GROUP_D];
+    const size_t gbytes = (size_t)group_numel[CGB_GROUP_D] * sizeof(float);
+    pr.add([gD, gbytes](cudaStream_t s) { CGB_CUDA(cudaMemsetAsync(gD, 0, gbytes, s)); }, 0, kOpMemset);
+    emit_dis_forward(pr, flops, dis[2], CGB_NET_D_A, real_B);
+    emit_dis_backward(pr, flops, dis[2], 1.f, 0.5f, CGB_LOSS_D_A, true, nullptr);
+    emit_dis_backward(pr, flops, dis[0], 0.f, 0.5f, CGB_LOSS_D_A, true, nullptr);
+    emit_dis_forward(pr, flops, dis[3], CGB_NET_D_B, real_A);
+    emit_dis_backward(pr, flops, dis[3], 1.f, 0.5f, CGB_LOSS_D_B, true, nullptr);
+    emit_dis_backward(pr, flops, dis[1], 0.f, 0.5f, CGB_LOSS_D_B, true, nullptr);
+  }
+  // ---- optimiser + bf16 weight refresh
+  for (int g = 0; g < 2; ++g) {
+    std::vector<PackEntry> table;
+    int max_elems = 0;
+    for (int net = g * 2; net < g * 2 + 2; ++net)
+      for (const LayerParam& p : layers[net]) {
+        PackEntry e{};
+        e.src_off = p.w_off;
+        e.wf_off = p.wf_off;
+        e.wt_off = p.wt_off;
+        e.Cout = p.spec.Cout;
+        e.Cin = p.spec.Cin;
+        e.T = p.spec.taps();
+        e.CinS = p.spec.CinS;
+        e.CoutS = p.spec.CoutS;
+        table.push_back(e);
+        max_elems = std::max(max_elems, e.Cout * e.Cin * e.T);
+      }
+    pack_table[g] = static_cast<PackEntry*>(meta_upload(table.data(), table.size() * sizeof(PackEntry)));
+    pack_count[g] = (int)table.size();
+    pack_max[g] = max_elems;
+    const PackEntry* tb = pack_table[g];
+    const int cnt = pack_count[g], mx = pack_max[g];
+    float* p = P[g];
+    bf16* arena = pack[g];
+    prog_refresh[g].add([p, tb, cnt, mx, arena](cudaStream_t s) { pack_weights(p, tb, cnt, mx, arena, s); });
+    float *gg = G[g], *mm = M[g], *vv = V[g];
+    const long long n = group_numel[g];
+    int* stp = adam_step[g];
+    float* hyp = adam_hyper[g];
+    prog_adam[g].add(
+        [E, p, gg, mm, vv, n, stp, hyp](cudaStream_t s) {
+          cgb::adam_step(p, gg, mm, vv, n, E->cfg.lr, E->cfg.beta1, E->cfg.beta2, E->cfg.eps, stp, hyp, E->grad_scale, s);
+        },
+        2);
+    prog_adam[g].add([p, tb, cnt, mx, arena](cudaStream_t s) { pack_weights(p, tb, cnt, mx, arena, s); });
+  }
+  // ---- module-level forward programs (Generator.forward / Discriminator.forward)
+  for (int net = 0; net < 2; ++net) {
+    emit_gen_forward(prog_mod_gen[net], &dummy_flops, gen[6], net, mod_in, mod_out, false);
+    emit_dis_forward(prog_mod_dis[net], &dummy_flops, dis[4], 2 + net, mod_in);
+  }
+}

@@ -1,0 +1,696 @@
+// HBM-bound kernels of the CycleGAN step (see pointwise.h).  All activations are bf16 NHWC with
+// the channel count a multiple of 8, so every thread moves 16-byte vectors.
+#include "pointwise.h"
+
+namespace cgb {
+
+namespace {
+
+struct DevTensor {
+  bf16* p;  // interior origin
+  long long sN, sH, sW;
+  int N, H, W, C, halo;
+};
+
+DevTensor dev(const TensorDesc& t) {
+  DevTensor d;
+  d.p = t.interior();
+  d.sN = t.sN();
+  d.sH = t.sH();
+  d.sW = t.sW();
+  d.N = t.N;
+  d.H = t.H;
+  d.W = t.W;
+  d.C = t.C;
+  d.halo = t.halo;
+  return d;
+}
+DevTensor dev_null() {
+  DevTensor d;
+  d.p = nullptr;
+  d.sN = d.sH = d.sW = 0;
+  d.N = d.H = d.W = d.C = d.halo = 0;
+  return d;
+}
+
+struct DevGrad {
+  DevTensor g1, g2;
+  int fold;
+};
+DevGrad dev(const GradSrc& g) {
+  DevGrad d;
+  d.g1 = g.g1 ? dev(*g.g1) : dev_null();
+  d.g2 = g.g2 ? dev(*g.g2) : dev_null();
+  d.fold = g.fold;
+  return d;
+}
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+
+__device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ float round_bf16(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+// gradient w.r.t. the activation at interior pixel (n, h, w), channels [c0, c0+8)
+__device__ __forceinline__ void load_grad8(const DevGrad& g, int n, int h, int w, int c0, int H, int W,
+                                           float (&out)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) out[i] = 0.f;
+  if (g.g1.p != nullptr) {
+    float v[8];
+    load8(g.g1.p + n * g.g1.sN + h * g.g1.sH + w * g.g1.sW + c0, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[i] += v[i];
+  }
+  if (g.g2.p != nullptr) {
+    const int p = g.fold;
+    int hs[2], ws[2], nh = 1, nw = 1;
+    hs[0] = h + p;
+    ws[0] = w + p;
+    if (h >= 1 && h <= p) hs[nh++] = p - h;
+    else if (h >= H - 1 - p && h <= H - 2) hs[nh++] = 2 * (H - 1) - h + p;
+    if (w >= 1 && w <= p) ws[nw++] = p - w;
+    else if (w >= W - 1 - p && w <= W - 2) ws[nw++] = 2 * (W - 1) - w + p;
+    for (int a = 0; a < nh; ++a)
+      for (int b = 0; b < nw; ++b) {
+        float v[8];
+        load8(g.g2.p + n * g.g2.sN + hs[a] * g.g2.sH + ws[b] * g.g2.sW + c0, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) out[i] += v[i];
+      }
+  }
+}
+
+__device__ __forceinline__ float act_fwd(float x, int act) {
+  if (act == kActRelu) return fmaxf(x, 0.f);
+  if (act == kActLeaky) return x > 0.f ? x : 0.2f * x;
+  return x;
+}
+__device__ __forceinline__ float act_grad(float x, int act) {
+  if (act == kActRelu) return x > 0.f ? 1.f : 0.f;
+  if (act == kActLeaky) return x > 0.f ? 1.f : 0.2f;
+  return 1.f;
+}
+
+inline unsigned blocks_for(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+// ------------------------------------------------------------------------------------------ layout
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, int C, DevTensor dst) {
+  const int HP = dst.H + 2 * dst.halo, WP = dst.W + 2 * dst.halo;
+  const long long total = (long long)dst.N * HP * WP;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int wp = idx % WP;
+  const int hp = (idx / WP) % HP;
+  const int n = idx / ((long long)WP * HP);
+  const int h = reflect_idx(hp - dst.halo, dst.H), w = reflect_idx(wp - dst.halo, dst.W);
+  bf16* o = dst.p + n * dst.sN + (hp - dst.halo) * dst.sH + (wp - dst.halo) * dst.sW;
+  for (int c0 = 0; c0 < dst.C; c0 += 8) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = c0 + i;
+      v[i] = c < C ? src[(((long long)n * C + c) * dst.H + h) * dst.W + w] : 0.f;
+    }
+    store8(o + c0, v);
+  }
+}
+
+__global__ void nhwc_to_nchw_kernel(DevTensor src, int C, float* __restrict__ dst) {
+  const long long total = (long long)src.N * src.H * src.W;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int w = idx % src.W;
+  const int h = (idx / src.W) % src.H;
+  const int n = idx / ((long long)src.W * src.H);
+  const bf16* p = src.p + n * src.sN + h * src.sH + w * src.sW;
+  for (int c = 0; c < C; ++c) dst[(((long long)n * C + c) * src.H + h) * src.W + w] = __bfloat162float(p[c]);
+}
+
+__global__ void fill_halo_kernel(DevTensor t) {
+  const int HP = t.H + 2 * t.halo, WP = t.W + 2 * t.halo, C8 = t.C / 8;
+  const long long total = (long long)t.N * HP * WP * C8;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c0 = (idx % C8) * 8;
+  long long r = idx / C8;
+  const int wp = r % WP;
+  r /= WP;
+  const int hp = r % HP;
+  const int n = r / HP;
+  const int h = hp - t.halo, w = wp - t.halo;
+  if (h >= 0 && h < t.H && w >= 0 && w < t.W) return;
+  const int hs = reflect_idx(h, t.H), ws = reflect_idx(w, t.W);
+  const uint4 v = *reinterpret_cast<const uint4*>(t.p + n * t.sN + hs * t.sH + ws * t.sW + c0);
+  *reinterpret_cast<uint4*>(t.p + n * t.sN + h * t.sH + w * t.sW + c0) = v;
+}
+
+// ------------------------------------------------------------------------------------------ column sums
+// Block = 256 threads = (C/8 channel lanes) x (rows of pixels).  MODE 0: (sum, sumsq) -> float2 stats;
+// MODE 1: sum only of the first Cvalid channels -> float* (bias gradients).
+template <int MODE>
+__global__ void colsum_kernel(DevTensor y, float* __restrict__ out, int pix_per_block, int Cvalid) {
+  const int C8 = y.C / 8;
+  const int lanes = C8 < 256 ? C8 : 256;
+  const int rows = 256 / lanes;
+  const int cl = threadIdx.x % lanes, pr = threadIdx.x / lanes;
+  const int n = blockIdx.y;
+  const int HW = y.H * y.W;
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(HW, p0 + pix_per_block);
+  __shared__ float red[256 * 16];
+  for (int cb = cl; cb < C8; cb += lanes) {
+    float s[8], ss[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = ss[i] = 0.f;
+    if (pr < rows) {
+      for (int p = p0 + pr; p < p1; p += rows) {
+        const int h = p / y.W, w = p % y.W;
+        float v[8];
+        load8(y.p + n * y.sN + h * y.sH + w * y.sW + cb * 8, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s[i] += v[i];
+          if (MODE == 0) ss[i] += v[i] * v[i];
+        }
+      }
+    }
+    // reduce across pixel rows through shared memory
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      red[threadIdx.x * 16 + i] = s[i];
+      red[threadIdx.x * 16 + 8 + i] = ss[i];
+    }
+    __syncthreads();
+    if (pr == 0) {
+      for (int r = 1; r < rows; ++r) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s[i] += red[(r * lanes + cl) * 16 + i];
+          ss[i] += red[(r * lanes + cl) * 16 + 8 + i];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = cb * 8 + i;
+        if (MODE == 0) {
+          atomicAdd(out + ((long long)n * y.C + c) * 2, s[i]);
+          atomicAdd(out + ((long long)n * y.C + c) * 2 + 1, ss[i]);
+        } else if (c < Cvalid) {
+          atomicAdd(out + c, s[i]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+int pick_pix_per_block(int HW) {
+  int ppb = (HW + 127) / 128;
+  ppb = (ppb + 31) / 32 * 32;
+  return ppb < 64 ? 64 : ppb;
+}
+
+// ------------------------------------------------------------------------------------------ IN apply
+__global__ void in_apply_kernel(DevTensor y, const float2* __restrict__ stats, int act, DevTensor res, DevTensor out) {
+  const int HP = out.H + 2 * out.halo, WP = out.W + 2 * out.halo, C8 = out.C / 8;
+  const long long total = (long long)out.N * HP * WP * C8;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c0 = (idx % C8) * 8;
+  long long r = idx / C8;
+  const int wp = r % WP;
+  r /= WP;
+  const int hp = r % HP;
+  const int n = r / HP;
+  const int h = reflect_idx(hp - out.halo, out.H), w = reflect_idx(wp - out.halo, out.W);
+  float v[8];
+  load8(y.p + n * y.sN + h * y.sH + w * y.sW + c0, v);
+  const float inv = 1.f / (float)(y.H * y.W);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float2 st = __ldg(stats + (long long)n * y.C + c0 + i);
+    const float mean = st.x * inv;
+    const float var = fmaxf(st.y * inv - mean * mean, 0.f);
+    v[i] = act_fwd((v[i] - mean) * rsqrtf(var + 1e-5f), act);
+  }
+  if (res.p != nullptr) {
+    float rv[8];
+    load8(res.p + n * res.sN + h * res.sH + w * res.sW + c0, rv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += rv[i];
+  }
+  store8(out.p + n * out.sN + (hp - out.halo) * out.sH + (wp - out.halo) * out.sW + c0, v);
+}
+
+// ------------------------------------------------------------------------------------------ IN backward
+__global__ void in_bwd_reduce_kernel(DevTensor y, const float2* __restrict__ stats, DevGrad g, int act, DevTensor da,
+                                     float* __restrict__ bstats, int pix_per_block) {
+  const int C8 = y.C / 8;
+  const int lanes = C8 < 256 ? C8 : 256;
+  const int rows = 256 / lanes;
+  const int cl = threadIdx.x % lanes, pr = threadIdx.x / lanes;
+  const int n = blockIdx.y;
+  const int HW = y.H * y.W;
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(HW, p0 + pix_per_block);
+  const float inv = 1.f / (float)HW;
+  __shared__ float red[256 * 16];
+  for (int cb = cl; cb < C8; cb += lanes) {
+    float mean[8], rstd[8], s1[8], s2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 st = __ldg(stats + (long long)n * y.C + cb * 8 + i);
+      mean[i] = st.x * inv;
+      rstd[i] = rsqrtf(fmaxf(st.y * inv - mean[i] * mean[i], 0.f) + 1e-5f);
+      s1[i] = s2[i] = 0.f;
+    }
+    if (pr < rows) {
+      for (int p = p0 + pr; p < p1; p += rows) {
+        const int h = p / y.W, w = p % y.W;
+        float v[8], gr[8];
+        load8(y.p + n * y.sN + h * y.sH + w * y.sW + cb * 8, v);
+        load_grad8(g, n, h, w, cb * 8, y.H, y.W, gr);
+        if (da.p != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) gr[i] = round_bf16(gr[i]);
+          store8(da.p + n * da.sN + h * da.sH + w * da.sW + cb * 8, gr);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xh = (v[i] - mean[i]) * rstd[i];
+          const float dz = gr[i] * act_grad(xh, act);
+          s1[i] += dz;
+          s2[i] += dz * xh;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      red[threadIdx.x * 16 + i] = s1[i];
+      red[threadIdx.x * 16 + 8 + i] = s2[i];
+    }
+    __syncthreads();
+    if (pr == 0) {
+      for (int r = 1; r < rows; ++r) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s1[i] += red[(r * lanes + cl) * 16 + i];
+          s2[i] += red[(r * lanes + cl) * 16 + 8 + i];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = cb * 8 + i;
+        atomicAdd(bstats + ((long long)n * y.C + c) * 2, s1[i]);
+        atomicAdd(bstats + ((long long)n * y.C + c) * 2 + 1, s2[i]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void in_bwd_apply_kernel(DevTensor y, const float2* __restrict__ stats, const float2* __restrict__ bstats,
+                                    DevGrad g, int act, DevTensor dy) {
+  const int C8 = y.C / 8;
+  const long long total = (long long)y.N * y.H * y.W * C8;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c0 = (idx % C8) * 8;
+  long long r = idx / C8;
+  const int w = r % y.W;
+  r /= y.W;
+  const int h = r % y.H;
+  const int n = r / y.H;
+  const float inv = 1.f / (float)(y.H * y.W);
+  float v[8], gr[8];
+  load8(y.p + n * y.sN + h * y.sH + w * y.sW + c0, v);
+  load_grad8(g, n, h, w, c0, y.H, y.W, gr);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float2 st = __ldg(stats + (long long)n * y.C + c0 + i);
+    const float2 bs = __ldg(bstats + (long long)n * y.C + c0 + i);
+    const float mean = st.x * inv;
+    const float rstd = rsqrtf(fmaxf(st.y * inv - mean * mean, 0.f) + 1e-5f);
+    const float xh = (v[i] - mean) * rstd;
+    const float dz = gr[i] * act_grad(xh, act);
+    v[i] = rstd * (dz - bs.x * inv - xh * bs.y * inv);
+  }
+  store8(dy.p + n * dy.sN + h * dy.sH + w * dy.sW + c0, v);
+}
+
+// ------------------------------------------------------------------------------------------ head / losses
+__device__ __forceinline__ float block_sum(float v) {
+  __shared__ float sh[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  if (threadIdx.x < 32) {
+    t = threadIdx.x < (blockDim.x + 31) / 32 ? sh[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  }
+  return t;  // valid in thread 0
+}
+
+// one thread per pixel; tensors have 16 stored channels, the first C (<= 8) are real
+__global__ void tanh_bwd_kernel(DevTensor out, DevTensor target, float l1_scale, DevGrad g, int C, DevTensor dpre,
+                                float* __restrict__ loss_slot) {
+  const long long total = (long long)out.N * out.H * out.W;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  float lsum = 0.f;
+  if (idx < total) {
+    const int w = idx % out.W;
+    const int h = (idx / out.W) % out.H;
+    const int n = idx / ((long long)out.W * out.H);
+    float o[8], gr[8], d[8];
+    load8(out.p + n * out.sN + h * out.sH + w * out.sW, o);
+    load_grad8(g, n, h, w, 0, out.H, out.W, gr);
+    if (target.p != nullptr) {
+      float t[8];
+      load8(target.p + n * target.sN + h * target.sH + w * target.sW, t);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (i < C) {
+          const float diff = o[i] - t[i];
+          lsum += fabsf(diff);
+          gr[i] += l1_scale * (float)((diff > 0.f) - (diff < 0.f));
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = i < C ? gr[i] * (1.f - o[i] * o[i]) : 0.f;
+    bf16* dp = dpre.p + n * dpre.sN + h * dpre.sH + w * dpre.sW;
+    store8(dp, d);
+    *reinterpret_cast<uint4*>(dp + 8) = make_uint4(0, 0, 0, 0);
+  }
+  if (loss_slot != nullptr && target.p != nullptr) {
+    const float t = block_sum(lsum);
+    if (threadIdx.x == 0) atomicAdd(loss_slot, t * l1_scale);
+  }
+}
+
+__global__ void l1_loss_kernel(DevTensor a, DevTensor b, int C, float scale, float* __restrict__ loss_slot) {
+  const long long total = (long long)a.N * a.H * a.W;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  float lsum = 0.f;
+  if (idx < total) {
+    const int w = idx % a.W;
+    const int h = (idx / a.W) % a.H;
+    const int n = idx / ((long long)a.W * a.H);
+    float x[8], y[8];
+    load8(a.p + n * a.sN + h * a.sH + w * a.sW, x);
+    load8(b.p + n * b.sN + h * b.sH + w * b.sW, y);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < C) lsum += fabsf(x[i] - y[i]);
+  }
+  const float t = block_sum(lsum);
+  if (threadIdx.x == 0) atomicAdd(loss_slot, t * scale);
+}
+
+__global__ void leaky_bwd_kernel(DevTensor a, DevTensor g, DevTensor dpre) {
+  const int C8 = a.C / 8;
+  const long long total = (long long)a.N * a.H * a.W * C8;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c0 = (idx % C8) * 8;
+  long long r = idx / C8;
+  const int w = r % a.W;
+  r /= a.W;
+  const int h = r % a.H;
+  const int n = r / a.H;
+  float av[8], gv[8];
+  load8(a.p + n * a.sN + h * a.sH + w * a.sW + c0, av);
+  load8(g.p + n * g.sN + h * g.sH + w * g.sW + c0, gv);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) gv[i] *= av[i] > 0.f ? 1.f : 0.2f;
+  store8(dpre.p + n * dpre.sN + h * dpre.sH + w * dpre.sW + c0, gv);
+}
+
+__global__ void mse_loss_kernel(DevTensor logits, float target, float wgt, float* __restrict__ loss_slot,
+                                DevTensor dl) {
+  const long long total = (long long)logits.N * logits.H * logits.W;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  float lsum = 0.f;
+  const float inv = 1.f / (float)total;
+  if (idx < total) {
+    const int w = idx % logits.W;
+    const int h = (idx / logits.W) % logits.H;
+    const int n = idx / ((long long)logits.W * logits.H);
+    const float p = __bfloat162float(logits.p[n * logits.sN + h * logits.sH + w * logits.sW]);
+    const float d = p - target;
+    lsum = d * d;
+    if (dl.p != nullptr) {
+      float v[8] = {2.f * wgt * d * inv, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      bf16* o = dl.p + n * dl.sN + h * dl.sH + w * dl.sW;
+      store8(o, v);
+      *reinterpret_cast<uint4*>(o + 8) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  const float t = block_sum(lsum);
+  if (threadIdx.x == 0 && loss_slot != nullptr) atomicAdd(loss_slot, t * wgt * inv);
+}
+
+// ------------------------------------------------------------------------------------------ weights
+__global__ void pack_weights_kernel(const float* __restrict__ master, const PackEntry* __restrict__ entries,
+                                    bf16* __restrict__ arena) {
+  const PackEntry e = entries[blockIdx.y];
+  const long long total = (long long)e.Cout * e.T * e.Cin;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ci = i % e.Cin;
+    const int t = (i / e.Cin) % e.T;
+    const int co = i / ((long long)e.Cin * e.T);
+    const bf16 v = __float2bfloat16_rn(master[e.src_off + i]);
+    arena[e.wf_off + ((long long)co * e.T + t) * e.CinS + ci] = v;
+    arena[e.wt_off + ((long long)ci * e.T + t) * e.CoutS + co] = v;
+  }
+}
+
+__global__ void adam_prep_kernel(int* step, float* hyper, float lr, float beta1, float beta2) {
+  const int t = *step + 1;
+  *step = t;
+  hyper[0] = (float)((double)lr / (1.0 - pow((double)beta1, (double)t)));
+  hyper[1] = (float)(1.0 / sqrt(1.0 - pow((double)beta2, (double)t)));
+}
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, float beta1, float beta2, float eps,
+                            const float* __restrict__ hyper, float grad_scale) {
+  const float step_size = hyper[0], inv_sqrt_bc2 = hyper[1];
+  const long long i4 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4;
+  if (i4 + 4 <= n) {
+    float4 pp = *reinterpret_cast<float4*>(p + i4);
+    const float4 gg = *reinterpret_cast<const float4*>(g + i4);
+    float4 mm = *reinterpret_cast<float4*>(m + i4);
+    float4 vv = *reinterpret_cast<float4*>(v + i4);
+    float* pa = &pp.x;
+    const float* ga = &gg.x;
+    float* ma = &mm.x;
+    float* va = &vv.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gr = ga[k] * grad_scale;
+      ma[k] = beta1 * ma[k] + (1.f - beta1) * gr;
+      va[k] = beta2 * va[k] + (1.f - beta2) * gr * gr;
+      pa[k] -= step_size * ma[k] / (sqrtf(va[k]) * inv_sqrt_bc2 + eps);
+    }
+    *reinterpret_cast<float4*>(p + i4) = pp;
+    *reinterpret_cast<float4*>(m + i4) = mm;
+    *reinterpret_cast<float4*>(v + i4) = vv;
+  } else {
+    for (long long i = i4; i < n; ++i) {
+      const float gr = g[i] * grad_scale;
+      m[i] = beta1 * m[i] + (1.f - beta1) * gr;
+      v[i] = beta2 * v[i] + (1.f - beta2) * gr * gr;
+      p[i] -= step_size * m[i] / (sqrtf(v[i]) * inv_sqrt_bc2 + eps);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ direct wgrad
+// grid (pixel blocks, taps); thread <-> (cout, cin) pair(s); fp32 atomics into g[Cout][T][Cin].
+__global__ void wgrad_direct_kernel(DevTensor x, DevTensor dy, int Cin, int Cout, int k, int stride, int pad,
+                                    int reflect, int pix_per_block, float* __restrict__ g) {
+  const int T = k * k;
+  const int t = blockIdx.y;
+  const int r = t / k, c = t % k;
+  const long long total = (long long)dy.N * dy.H * dy.W;
+  const long long p0 = (long long)blockIdx.x * pix_per_block;
+  const long long p1 = min(total, p0 + pix_per_block);
+  const int pairs = Cin * Cout;
+  for (int pair = threadIdx.x; pair < pairs; pair += blockDim.x) {
+    const int co = pair / Cin, ci = pair % Cin;
+    float acc = 0.f;
+    for (long long p = p0; p < p1; ++p) {
+      const int ow = p % dy.W;
+      const int oh = (p / dy.W) % dy.H;
+      const int n = p / ((long long)dy.W * dy.H);
+      int ih = oh * stride + r - pad, iw = ow * stride + c - pad;
+      if (!reflect && (ih < 0 || ih >= x.H || iw < 0 || iw >= x.W)) continue;
+      // reflect: the halo of x already holds the mirrored pixels (ih in [-pad, H+pad))
+      const float d = __bfloat162float(dy.p[n * dy.sN + oh * dy.sH + ow * dy.sW + co]);
+      const float xv = __bfloat162float(x.p[n * x.sN + ih * x.sH + iw * x.sW + ci]);
+      acc += d * xv;
+    }
+    atomicAdd(g + ((long long)co * T + t) * Cin + ci, acc);
+  }
+}
+
+}  // namespace
+
+// ================================================================================================ host API
+void nchw_to_nhwc(const float* src, int C, const TensorDesc& dst, cudaStream_t st) {
+  CGB_CHECK(dst.C % 8 == 0 && C <= dst.C, "nchw_to_nhwc: bad channel counts");
+  const long long total = (long long)dst.N * (dst.H + 2 * dst.halo) * (dst.W + 2 * dst.halo);
+  nchw_to_nhwc_kernel<<<blocks_for(total, 256), 256, 0, st>>>(src, C, dev(dst));
+  CGB_CUDA(cudaGetLastError());
+}
+
+void nhwc_to_nchw(const TensorDesc& src, int C, float* dst, cudaStream_t st) {
+  const long long total = (long long)src.N * src.H * src.W;
+  nhwc_to_nchw_kernel<<<blocks_for(total, 256), 256, 0, st>>>(dev(src), C, dst);
+  CGB_CUDA(cudaGetLastError());
+}
+
+void fill_reflect_halo(const TensorDesc& t, cudaStream_t st) {
+  if (t.halo == 0) return;
+  const long long total = (long long)t.N * (t.H + 2 * t.halo) * (t.W + 2 * t.halo) * (t.C / 8);
+  fill_halo_kernel<<<blocks_for(total, 256), 256, 0, st>>>(dev(t));
+  CGB_CUDA(cudaGetLastError());
+}
+
+void in_stats(const TensorDesc& y, float2* stats, cudaStream_t st) {
+  CGB_CHECK(y.C % 8 == 0, "in_stats: channels must be a multiple of 8");
+  const int HW = y.H * y.W;
+  const int ppb = pick_pix_per_block(HW);
+  dim3 grid((HW + ppb - 1) / ppb, y.N);
+  colsum_kernel<0><<<grid, 256, 0, st>>>(dev(y), reinterpret_cast<float*>(stats), ppb, y.C);
+  CGB_CUDA(cudaGetLastError());
+}
+
+void bias_grad(const TensorDesc& dy, int C, float* gbias, cudaStream_t st) {
+  const int HW = dy.H * dy.W;
+  const int ppb = pick_pix_per_block(HW);
+  dim3 grid((HW + ppb - 1) / ppb, dy.N);
+  colsum_kernel<1><<<grid, 256, 0, st>>>(dev(dy), gbias, ppb, C);
+  CGB_CUDA(cudaGetLastError());
+}
+
+void in_apply(const TensorDesc& y, const float2* stats, int act, const TensorDesc* residual, const TensorDesc& out,
+              cudaStream_t st) {
+  CGB_CHECK(y.C == out.C && y.H == out.H && y.W == out.W && y.N == out.N, "in_apply: shape mismatch");
+  const long long total = (long long)out.N * (out.H + 2 * out.halo) * (out.W + 2 * out.halo) * (out.C / 8);
+  in_apply_kernel<<<blocks_for(total, 256), 256, 0, st>>>(dev(y), stats, act, residual ? dev(*residual) : dev_null(),
+                                                          dev(out));
+  CGB_CUDA(cudaGetLastError());
+}
+
+static void check_grad(const TensorDesc& y, const GradSrc& g) {
+  CGB_CHECK(g.g1 || g.g2, "gradient source is empty");
+  if (g.g1) CGB_CHECK(g.g1->H == y.H && g.g1->W == y.W && g.g1->C == y.C, "g1 shape mismatch");
+  if (g.g2)
+    CGB_CHECK(g.g2->H == y.H + 2 * g.fold && g.g2->W == y.W + 2 * g.fold && g.g2->C == y.C && g.g2->halo == 0,
+              "g2 (padded-domain gradient) shape mismatch");
+}
+
+void in_bwd_reduce(const TensorDesc& y, const float2* stats, const GradSrc& g, int act, const TensorDesc* da_out,
+                   float2* bstats, cudaStream_t st) {
+  check_grad(y, g);
+  const int HW = y.H * y.W;
+  const int ppb = pick_pix_per_block(HW);
+  dim3 grid((HW + ppb - 1) / ppb, y.N);
+  in_bwd_reduce_kernel<<<grid, 256, 0, st>>>(dev(y), stats, dev(g), act, da_out ? dev(*da_out) : dev_null(),
+                                             reinterpret_cast<float*>(bstats), ppb);
+  CGB_CUDA(cudaGetLastError());
+}
+
+void in_bwd_apply(const TensorDesc& y, const float2* stats, const float2* bstats, const GradSrc& g, int act,
+                  const TensorDesc& dy, cudaStream_t st) {
+  check_grad(y, g);
+  const long long total = (long long)y.N * y.H * y.W * (y.C / 8);
+  in_bwd_apply_kernel<<<blocks_for(total, 256), 256, 0, st>>>(dev(y), stats, bstats, dev(g), act, dev(dy));
+  CGB_CUDA(cudaGetLastError());
+}
+
+void tanh_bwd(const TensorDesc& out, const TensorDesc* target, float l1_scale, const GradSrc& g, int C,
+              const TensorDesc& dpre, float* loss_slot, cudaStream_t st) {
+  CGB_CHECK(out.C == 16 && dpre.C == 16 && C <= 8, "tanh_bwd expects 16-channel image tensors");
+  if (g.g1 || g.g2) check_grad(out, g);
+  const long long total = (long long)out.N * out.H * out.W;
+  tanh_bwd_kernel<<<blocks_for(total, 256), 256, 0, st>>>(dev(out), target ? dev(*target) : dev_null(), l1_scale,
+                                                          dev(g), C, dev(dpre), loss_slot);
+  CGB_CUDA(cudaGetLastError());
+}
+
+void l1_loss(const TensorDesc& a, const TensorDesc& b, int C, float scale, float* loss_slot, cudaStream_t st) {
+  const long long total = (long long)a.N * a.H * a.W;
+  l1_loss_kernel<<<blocks_for(total, 256), 256, 0, st>>>(dev(a), dev(b), C, scale, loss_slot);
+  CGB_CUDA(cudaGetLastError());
+}
+
+void leaky_bwd(const TensorDesc& a, const TensorDesc& g, const TensorDesc& dpre, cudaStream_t st) {
+  const long long total = (long long)a.N * a.H * a.W * (a.C / 8);
+  leaky_bwd_kernel<<<blocks_for(total, 256), 256, 0, st>>>(dev(a), dev(g), dev(dpre));
+  CGB_CUDA(cudaGetLastError());
+}
+
+void mse_loss(const TensorDesc& logits, float target, float w, float* loss_slot, const TensorDesc* dlogits,
+              cudaStream_t st) {
+  const long long total = (long long)logits.N * logits.H * logits.W;
+  mse_loss_kernel<<<blocks_for(total, 256), 256, 0, st>>>(dev(logits), target, w, loss_slot,
+                                                          dlogits ? dev(*dlogits) : dev_null());
+  CGB_CUDA(cudaGetLastError());
+}
+
+void pack_weights(const float* master, const PackEntry* entries_dev, int n_entries, int max_elems, bf16* arena,
+                  cudaStream_t st) {
+  if (n_entries == 0) return;
+  const int bx = std::max(1, std::min(64, (max_elems + 255) / 256));
+  dim3 grid(bx, n_entries);
+  pack_weights_kernel<<<grid, 256, 0, st>>>(master, entries_dev, arena);
+  CGB_CUDA(cudaGetLastError());
+}
+
+void adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+               float eps, int* step_dev, float* hyper_dev, float grad_scale, cudaStream_t st) {
+  adam_prep_kernel<<<1, 1, 0, st>>>(step_dev, hyper_dev, lr, beta1, beta2);
+  CGB_CUDA(cudaGetLastError());
+  adam_kernel<<<blocks_for((n + 3) / 4, 256), 256, 0, st>>>(p, g, m, v, n, beta1, beta2, eps, hyper_dev, grad_scale);
+  CGB_CUDA(cudaGetLastError());
+}
+
+void wgrad_direct(const ConvSpec& s, const TensorDesc& x, const TensorDesc& dy, float* g, cudaStream_t st) {
+  CGB_CHECK(!s.transposed, "wgrad_direct: transposed convs use the tensor-core path");
+  if (s.reflect) CGB_CHECK(x.halo == s.pad, "wgrad_direct: reflect conv input must carry a halo");
+  const long long total = (long long)dy.N * dy.H * dy.W;
+  const int ppb = total >= 65536 ? 1024 : (total >= 8192 ? 256 : 64);
+  dim3 grid((unsigned)((total + ppb - 1) / ppb), s.taps());
+  wgrad_direct_kernel<<<grid, 256, 0, st>>>(dev(x), dev(dy), s.Cin, s.Cout, s.k, s.stride, s.pad, s.reflect ? 1 : 0,
+                                            ppb, g);
+  CGB_CUDA(cudaGetLastError());
+}
+
+}  // namespace cgb

@@ -67,8 +67,10 @@ void pack_weights(const float* master, const PackEntry* entries_dev, int n_entri
                   cudaStream_t st);
 
 // torch.optim.Adam semantics (no weight decay, no amsgrad); g is multiplied by grad_scale first.
+// The step counter and the bias-correction scalars live in device memory (state: int step;
+// hyper: {lr / (1 - beta1^t), 1 / sqrt(1 - beta2^t)}) so the launch is CUDA-graph replayable.
 void adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
-               float eps, int step, float grad_scale, cudaStream_t st);
+               float eps, int* step_dev, float* hyper_dev, float grad_scale, cudaStream_t st);
 
 // ---- CUDA-core convolution passes for the 3-channel / 1-channel layers ------------------------
 // g[Cout][T][Cin] += sum_pixels dy * x   (x may carry a reflect halo == pad; zero padding otherwise)

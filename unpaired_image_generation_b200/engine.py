@@ -1,0 +1,211 @@
+"""Python handle on the C++ step engine: owns the torch-allocated flat parameter / gradient / Adam
+buffers and the HBM workspace, and forwards every call to the C ABI with raw device pointers.
+PyTorch is used for device memory and streams only."""
+from __future__ import annotations
+
+import ctypes
+from collections import OrderedDict
+from typing import Dict, List
+
+import torch
+
+from . import _lib
+
+NET_G_AB, NET_G_BA, NET_D_A, NET_D_B = 0, 1, 2, 3
+GROUP_G, GROUP_D = 0, 1
+IMAGE_IDS = OrderedDict(fake_B=0, rec_A=1, fake_A=2, rec_B=3, idt_A=4, idt_B=5, real_A=6, real_B=7)
+LOSS_KEYS = ("loss_G", "loss_G_A", "loss_G_B", "loss_cycle_A", "loss_cycle_B", "loss_idt_A", "loss_idt_B",
+             "loss_D_A", "loss_D_B")
+
+
+def _ptr(t: torch.Tensor) -> ctypes.c_void_p:
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class ParamInfo:
+    def __init__(self, raw: "_lib.CgbParamInfo"):
+        self.name = raw.name.decode()
+        self.is_bias = bool(raw.is_bias)
+        self.transposed = bool(raw.transposed)
+        self.cout, self.cin, self.k = raw.cout, raw.cin, raw.k
+        self.offset, self.numel = raw.offset, raw.numel
+
+    @property
+    def torch_shape(self):
+        if self.is_bias:
+            return (self.cout,)
+        return (self.cin, self.cout, self.k, self.k) if self.transposed else (self.cout, self.cin, self.k, self.k)
+
+    def view(self, flat: torch.Tensor) -> torch.Tensor:
+        """torch-layout view (no copy) of this tensor inside a flat group buffer."""
+        seg = flat[self.offset:self.offset + self.numel]
+        if self.is_bias:
+            return seg
+        v = seg.view(self.cout, self.k, self.k, self.cin)
+        return v.permute(3, 0, 1, 2) if self.transposed else v.permute(0, 3, 1, 2)
+
+
+def describe(batch: int, size: int, n_blocks: int = 9) -> Dict[int, List[ParamInfo]]:
+    """Parameter inventory without touching the GPU (engine creation is host-only)."""
+    lib = _lib.load()
+    cfg = _lib.CgbConfig(batch, size, n_blocks, 10.0, 10.0, 0.5, 2e-4, 0.5, 0.999, 1e-8)
+    h = ctypes.c_void_p()
+    _lib.check(lib.cgb_engine_create(ctypes.byref(cfg), ctypes.byref(h)))
+    try:
+        out = {}
+        for net in range(4):
+            infos = []
+            for i in range(lib.cgb_num_params(h, net)):
+                raw = _lib.CgbParamInfo()
+                _lib.check(lib.cgb_param_info(h, net, i, ctypes.byref(raw)))
+                infos.append(ParamInfo(raw))
+            out[net] = infos
+        out["group_numel"] = (lib.cgb_group_numel(h, 0), lib.cgb_group_numel(h, 1))
+        out["workspace_bytes"] = lib.cgb_workspace_bytes(h)
+        return out
+    finally:
+        lib.cgb_engine_destroy(h)
+
+
+class StepEngine:
+    def __init__(self, batch: int, size: int, n_blocks: int = 9, lambda_A: float = 10.0, lambda_B: float = 10.0,
+                 lambda_idt: float = 0.5, lr: float = 2e-4, betas=(0.5, 0.999), eps: float = 1e-8, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("unpaired_image_generation_b200 needs a CUDA device (B200, sm_100a); "
+                               "there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.batch, self.size, self.n_blocks = batch, size, n_blocks
+        cfg = _lib.CgbConfig(batch, size, n_blocks, lambda_A, lambda_B, lambda_idt, lr, betas[0], betas[1], eps)
+        self._h = ctypes.c_void_p()
+        _lib.check(self.lib.cgb_engine_create(ctypes.byref(cfg), ctypes.byref(self._h)))
+        self.infos: Dict[int, List[ParamInfo]] = {}
+        for net in range(4):
+            lst = []
+            for i in range(self.lib.cgb_num_params(self._h, net)):
+                raw = _lib.CgbParamInfo()
+                _lib.check(self.lib.cgb_param_info(self._h, net, i, ctypes.byref(raw)))
+                lst.append(ParamInfo(raw))
+            self.infos[net] = lst
+        with torch.cuda.device(self.device):
+            numel = [self.lib.cgb_group_numel(self._h, g) for g in range(2)]
+            mk = lambda n: torch.zeros(n, dtype=torch.float32, device=self.device)
+            self.params = [mk(numel[0]), mk(numel[1])]
+            self.grads = [mk(numel[0]), mk(numel[1])]
+            self.exp_avg = [mk(numel[0]), mk(numel[1])]
+            self.exp_avg_sq = [mk(numel[0]), mk(numel[1])]
+            ws_bytes = self.lib.cgb_workspace_bytes(self._h)
+            self._ws_raw = torch.empty(ws_bytes + 1024, dtype=torch.uint8, device=self.device)
+            off = (-self._ws_raw.data_ptr()) % 1024
+            self.workspace = self._ws_raw[off:off + ws_bytes]
+            torch.cuda.synchronize(self.device)
+            _lib.check(self.lib.cgb_engine_bind(
+                self._h, _ptr(self.params[0]), _ptr(self.grads[0]), _ptr(self.exp_avg[0]), _ptr(self.exp_avg_sq[0]),
+                _ptr(self.params[1]), _ptr(self.grads[1]), _ptr(self.exp_avg[1]), _ptr(self.exp_avg_sq[1]),
+                _ptr(self.workspace), ws_bytes))
+        self.workspace_bytes = ws_bytes
+        self._losses_host = (ctypes.c_float * 16)()
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                torch.cuda.synchronize(self.device)
+            except Exception:
+                pass
+            self.lib.cgb_engine_destroy(h)
+            self._h = None
+
+    # ---- parameters -----------------------------------------------------------------------------
+    def _views(self, net: int, bufs) -> "OrderedDict[str, torch.Tensor]":
+        flat = bufs[0 if net < 2 else 1]
+        return OrderedDict((i.name, i.view(flat)) for i in self.infos[net])
+
+    def param_views(self, net: int):
+        return self._views(net, self.params)
+
+    def grad_views(self, net: int):
+        return self._views(net, self.grads)
+
+    def refresh_weights(self, group: int):
+        _lib.check(self.lib.cgb_refresh_weights(self._h, group, _stream()))
+
+    def set_grad_scale(self, scale: float):
+        _lib.check(self.lib.cgb_set_grad_scale(self._h, scale))
+
+    # ---- modules --------------------------------------------------------------------------------
+    def _check_img(self, x: torch.Tensor) -> torch.Tensor:
+        if tuple(x.shape) != (self.batch, 3, self.size, self.size):
+            raise ValueError(f"expected input of shape {(self.batch, 3, self.size, self.size)}, got {tuple(x.shape)}")
+        return x.to(device=self.device, dtype=torch.float32).contiguous()
+
+    def generator_forward(self, net: int, x: torch.Tensor) -> torch.Tensor:
+        x = self._check_img(x)
+        y = torch.empty_like(x)
+        _lib.check(self.lib.cgb_generator_forward(self._h, net, _ptr(x), _ptr(y), _stream()))
+        return y
+
+    def discriminator_forward(self, net: int, x: torch.Tensor) -> torch.Tensor:
+        x = self._check_img(x)
+        p = self.size // 8 - 2
+        y = torch.empty(self.batch, 1, p, p, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.cgb_discriminator_forward(self._h, net, _ptr(x), _ptr(y), _stream()))
+        return y
+
+    # ---- step -----------------------------------------------------------------------------------
+    def set_inputs(self, real_A: torch.Tensor, real_B: torch.Tensor):
+        a, b = self._check_img(real_A), self._check_img(real_B)
+        _lib.check(self.lib.cgb_set_inputs(self._h, _ptr(a), _ptr(b), _stream()))
+        self._keep = (a, b)  # keep alive until the async copies ran
+
+    def forward_cycle(self):
+        _lib.check(self.lib.cgb_forward_cycle(self._h, _stream()))
+
+    def get_image(self, name: str) -> torch.Tensor:
+        out = torch.empty(self.batch, 3, self.size, self.size, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.cgb_get_image(self._h, IMAGE_IDS[name], _ptr(out), _stream()))
+        return out
+
+    def phase_generators(self):
+        _lib.check(self.lib.cgb_phase_generators(self._h, _stream()))
+
+    def phase_discriminators(self):
+        _lib.check(self.lib.cgb_phase_discriminators(self._h, _stream()))
+
+    def adam(self, group: int):
+        _lib.check(self.lib.cgb_adam(self._h, group, _stream()))
+
+    def train_step(self):
+        """whole step on the current stream from the staged inputs (CUDA graph after the first call)"""
+        _lib.check(self.lib.cgb_train_step(self._h, _stream()))
+
+    def losses(self) -> Dict[str, float]:
+        _lib.check(self.lib.cgb_get_losses_host(self._h, self._losses_host, _stream()))
+        return {k: float(self._losses_host[i]) for i, k in enumerate(LOSS_KEYS)}
+
+    def train_step_host(self, real_A_host: torch.Tensor, real_B_host: torch.Tensor) -> Dict[str, float]:
+        """end to end from HOST tensors (pinned for async copies): H2D + step + D2H of the losses"""
+        assert real_A_host.device.type == "cpu" and real_A_host.dtype == torch.float32 and real_A_host.is_contiguous()
+        assert real_B_host.device.type == "cpu" and real_B_host.dtype == torch.float32 and real_B_host.is_contiguous()
+        _lib.check(self.lib.cgb_train_step_host(self._h, _ptr(real_A_host), _ptr(real_B_host), self._losses_host,
+                                                _stream()))
+        return {k: float(self._losses_host[i]) for i, k in enumerate(LOSS_KEYS)}
+
+    def profile_kind(self, kind: int, reps: int = 5):
+        """(ms per step-equivalent, launches, algorithmic FLOPs) of one kernel class, CUDA-event timed"""
+        ms, n, fl = ctypes.c_float(), ctypes.c_longlong(), ctypes.c_double()
+        _lib.check(self.lib.cgb_profile_kind(self._h, kind, reps, _stream(), ctypes.byref(ms), ctypes.byref(n),
+                                             ctypes.byref(fl)))
+        return ms.value, n.value, fl.value
+
+    @property
+    def launches_per_step(self) -> int:
+        return int(self.lib.cgb_launches_per_step(self._h))
+
+    @property
+    def conv_flops_per_step(self) -> float:
+        return float(self.lib.cgb_conv_flops_per_step(self._h))

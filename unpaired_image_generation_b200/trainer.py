@@ -1,0 +1,131 @@
+"""CycleGANTrainer with the stand-in's API (oracle/cyclegan_standin.py:195): same constructor
+arguments, `train_step(real_A, real_B) -> dict`, `forward_only`, `backward_only`.  One process per
+GPU; with torch.distributed initialised the two flat gradient buffers are all-reduced on a side
+stream, overlapped with the discriminator phase."""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Dict, Optional
+
+import torch
+
+from . import engine as _engine
+from .modules import Discriminator, Generator
+from .parallel import GradSync
+
+
+class CycleGANTrainer:
+    LOSS_KEYS = _engine.LOSS_KEYS
+
+    def __init__(self, G_AB: Generator, G_BA: Generator, D_A: Discriminator, D_B: Discriminator,
+                 lambda_A: float = 10.0, lambda_B: float = 10.0, lambda_idt: float = 0.5, lr: float = 2e-4,
+                 betas=(0.5, 0.999), eps: float = 1e-8, process_group=None):
+        self.G_AB, self.G_BA, self.D_A, self.D_B = G_AB, G_BA, D_A, D_B
+        if G_AB.n_blocks != G_BA.n_blocks:
+            raise ValueError("both generators must have the same number of residual blocks")
+        self._hyper = dict(lambda_A=lambda_A, lambda_B=lambda_B, lambda_idt=lambda_idt, lr=lr, betas=betas, eps=eps)
+        self.sync = GradSync(process_group)
+        self.engine: Optional[_engine.StepEngine] = None
+        self.stream: Optional[torch.cuda.Stream] = None
+        self.comm_stream: Optional[torch.cuda.Stream] = None
+
+    # ---- engine --------------------------------------------------------------------------------------
+    def _ensure_engine(self, real_A: torch.Tensor) -> _engine.StepEngine:
+        batch, _, h, w = real_A.shape
+        if h != w:
+            raise ValueError("only square images are supported")
+        if self.engine is not None:
+            if (self.engine.batch, self.engine.size) != (batch, h):
+                raise ValueError("the trainer is bound to input shape "
+                                 f"{(self.engine.batch, 3, self.engine.size, self.engine.size)}")
+            return self.engine
+        eng = _engine.StepEngine(batch, h, self.G_AB.n_blocks, **self._hyper)
+        for net, mod in enumerate((self.G_AB, self.G_BA, self.D_A, self.D_B)):
+            mod._attach(eng, net)
+        eng.refresh_weights(0)
+        eng.refresh_weights(1)
+        eng.set_grad_scale(self.sync.grad_scale)
+        self.engine = eng
+        self.stream = torch.cuda.Stream(device=eng.device)
+        self.comm_stream = torch.cuda.Stream(device=eng.device)
+        return eng
+
+    def _enter(self):
+        self.stream.wait_stream(torch.cuda.current_stream())
+        return torch.cuda.stream(self.stream)
+
+    def _exit(self):
+        torch.cuda.current_stream().wait_stream(self.stream)
+
+    # ---- API -----------------------------------------------------------------------------------------
+    def forward_only(self, real_A: torch.Tensor, real_B: torch.Tensor) -> "OrderedDict[str, torch.Tensor]":
+        eng = self._ensure_engine(real_A)
+        with self._enter():
+            eng.set_inputs(real_A, real_B)
+            eng.forward_cycle()
+            out = OrderedDict((k, eng.get_image(k)) for k in ("fake_B", "rec_A", "fake_A", "rec_B", "idt_A", "idt_B"))
+        self._exit()
+        return out
+
+    def backward_only(self, real_A: torch.Tensor, real_B: torch.Tensor) -> Dict[str, float]:
+        """forward + both backward phases, no optimiser step; gradients are left in `grads(name)`"""
+        eng = self._ensure_engine(real_A)
+        with self._enter():
+            eng.set_inputs(real_A, real_B)
+            eng.phase_generators()
+            eng.phase_discriminators()
+            losses = eng.losses()
+        self._exit()
+        return losses
+
+    def train_step(self, real_A: torch.Tensor, real_B: torch.Tensor) -> Dict[str, float]:
+        eng = self._ensure_engine(real_A)
+        if self.sync.world_size == 1:
+            if real_A.device.type == "cpu":
+                with self._enter():
+                    losses = eng.train_step_host(real_A.contiguous().float(), real_B.contiguous().float())
+                self._exit()
+                return losses
+            with self._enter():
+                eng.set_inputs(real_A, real_B)
+                eng.train_step()
+                losses = eng.losses()
+            self._exit()
+            return losses
+        return self._train_step_dp(eng, real_A, real_B)
+
+    def _train_step_dp(self, eng, real_A, real_B) -> Dict[str, float]:
+        self._train_step_dp_nosync(eng, real_A, real_B)
+        with torch.cuda.stream(self.stream):
+            losses = eng.losses()
+        torch.cuda.current_stream().wait_stream(self.stream)
+        return losses
+
+    def _train_step_dp_nosync(self, eng, real_A, real_B) -> None:
+        """one data-parallel step, fully asynchronous (no host read-back)"""
+        main, comm = self.stream, self.comm_stream
+        main.wait_stream(torch.cuda.current_stream())
+        ev_G, ev_D, ev_done = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+        with torch.cuda.stream(main):
+            eng.set_inputs(real_A, real_B)
+            eng.phase_generators()
+            ev_G.record(main)
+        with torch.cuda.stream(comm):
+            comm.wait_event(ev_G)
+            self.sync.all_reduce_(eng.grads[0])
+            eng.adam(0)
+        with torch.cuda.stream(main):
+            # needs only D weights and the pre-update fakes: overlaps the generator all-reduce + Adam
+            eng.phase_discriminators()
+            ev_D.record(main)
+        with torch.cuda.stream(comm):
+            comm.wait_event(ev_D)
+            self.sync.all_reduce_(eng.grads[1])
+            eng.adam(1)
+            ev_done.record(comm)
+        main.wait_event(ev_done)
+
+    # ---- introspection for tests ---------------------------------------------------------------------
+    def grads(self, net_name: str) -> "OrderedDict[str, torch.Tensor]":
+        net = dict(G_AB=0, G_BA=1, D_A=2, D_B=3)[net_name]
+        return self.engine.grad_views(net)
