@@ -204,20 +204,31 @@ static void run_step_eager(cgb_engine* e, cudaStream_t st) {
   e->prog_adam[1].run(st);
 }
 
+// same step with the lanes mapped to distinct streams (used under stream capture)
+static void run_step_lanes(cgb_engine* e, cudaStream_t st) {
+  e->lane_streams[0] = st;
+  for (int l = 1; l < kLanes; ++l)
+    if (!e->lane_streams[l]) CGB_CUDA(cudaStreamCreateWithFlags(&e->lane_streams[l], cudaStreamNonBlocking));
+  size_t next_event = 0;
+  const Program* seq[6] = {&e->prog_set_inputs, &e->prog_cycle, &e->prog_G, &e->prog_adam[0], &e->prog_D, &e->prog_adam[1]};
+  for (const Program* p : seq) p->run_lanes(e->lane_streams, e->events, &next_event);
+}
+
 int cgb_train_step(cgb_engine_t* e, void* stream) {
   CGB_API_BEGIN
   CGB_CHECK(e && e->bound, "engine not bound");
   cudaStream_t st = S(stream);
   static const bool no_graph = std::getenv("CGB_NO_GRAPH") != nullptr;
   // first call runs eagerly (configures kernel attributes, validates); the second call captures the
-  // step into a CUDA graph that later calls replay.  The legacy default stream cannot be captured.
+  // step into a CUDA graph (independent passes on parallel branches) that later calls replay.
+  // The legacy default stream cannot be captured.
   const bool can_graph = !no_graph && st != nullptr && !e->graph_failed;
   if (can_graph && e->graph == nullptr && e->step_calls >= 1) {
     cudaGraph_t g = nullptr;
     cudaError_t err = cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed);
     if (err == cudaSuccess) {
       try {
-        run_step_eager(e, st);
+        run_step_lanes(e, st);
       } catch (...) {
         cudaStreamEndCapture(st, &g);
         if (g) cudaGraphDestroy(g);
@@ -231,7 +242,9 @@ int cgb_train_step(cgb_engine_t* e, void* stream) {
     if (err != cudaSuccess) {
       e->graph = nullptr;
       e->graph_failed = true;
+      cgb::set_last_error(std::string("CUDA graph capture failed: ") + cudaGetErrorString(err));
       cudaGetLastError();
+      if (std::getenv("CGB_REQUIRE_GRAPH")) throw cgb::Error(cgb_last_error());
     }
   }
   ++e->step_calls;
@@ -425,7 +438,18 @@ int cgb_conv_layer_test(int n, int h, int w, int cin, int cout, int k, int strid
         pw.args.taps = tp;
         run(pw, 0);
       } else {
-        wgrad_direct(s, X, DY, g, 0);
+        const size_t ce = small_wgrad_col_elems(s, X, DY);
+        bf16* colbuf = static_cast<bf16*>(sc.alloc(ce * sizeof(bf16)));
+        SmallWgradPlan ps = plan_wgrad_small(s, X, DY, g, colbuf, ce, sm);
+        WTap* tp = static_cast<WTap*>(sc.alloc(ps.gemm.taps.size() * sizeof(WTap)));
+        CGB_CUDA(cudaMemcpy(tp, ps.gemm.taps.data(), ps.gemm.taps.size() * sizeof(WTap), cudaMemcpyHostToDevice));
+        ps.gemm.args.taps = tp;
+        if (!ps.row_map.empty()) {
+          int* rm = static_cast<int*>(sc.alloc(ps.row_map.size() * sizeof(int)));
+          CGB_CUDA(cudaMemcpy(rm, ps.row_map.data(), ps.row_map.size() * sizeof(int), cudaMemcpyHostToDevice));
+          ps.gemm.args.row_map = rm;
+        }
+        run(ps, 0);
       }
       std::vector<float> gm(wn), gt(wn);
       CGB_CUDA(cudaMemcpy(gm.data(), g, wn * sizeof(float), cudaMemcpyDeviceToHost));

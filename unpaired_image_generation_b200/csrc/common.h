@@ -86,6 +86,7 @@ struct WgradArgs {
   int tw_shift;            // TWk = 1 << tw_shift, THk = 64 >> tw_shift
   int split_k;             // number of K splits (gridDim.z)
   float* g;                // [Cout][T][Cin] fp32, accumulated with atomics (must be zeroed)
+  const int* row_map;      // optional: GEMM row m -> row of g (row length Cin, T ignored); < 0 = skip
 };
 
 enum Act { kActNone = 0, kActLeaky = 1, kActTanh = 2, kActRelu = 3 };

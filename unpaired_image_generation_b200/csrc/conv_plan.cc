@@ -58,7 +58,18 @@ static int choose_bn(int rows, int bk, long long ctas_per_nblock, int sm_count) 
 }
 
 static void set_tiles(IgemmPlan& p, int N, int Ho, int Wo) {
-  const int shift = std::max(3, std::min(7, ilog2_ceil(std::min(Wo, 128))));
+  // tile = TH x TW output pixels with TH * TW = 128: pick the shape that wastes the fewest pixels
+  // (e.g. the 66x66 padded-domain dgrads: 8x16 tiles -> 45 tiles instead of 66 of 1x128)
+  int shift = 7;
+  long long best = -1;
+  for (int sh = 7; sh >= 3; --sh) {
+    const int tw = 1 << sh, th = 128 >> sh;
+    const long long tiles = (long long)((Wo + tw - 1) / tw) * ((Ho + th - 1) / th);
+    if (best < 0 || tiles < best) {
+      best = tiles;
+      shift = sh;
+    }
+  }
   const int TW = 1 << shift, TH = 128 >> shift;
   p.args.tw_shift = shift;
   p.args.tiles_w = (Wo + TW - 1) / TW;
@@ -347,7 +358,7 @@ WgradPlan plan_wgrad(const ConvSpec& s, const TensorDesc& x, const TensorDesc& d
   p.args.num_taps = (int)p.taps.size();
   const long long total_chunks = (long long)p.args.N * p.args.tiles_w * p.args.tiles_h;
   const long long base_ctas = (long long)p.m_blocks * ((s.CinS + p.BNW - 1) / p.BNW) * T;
-  long long split = (2LL * sm_count + base_ctas - 1) / base_ctas;  // aim at ~2 waves
+  long long split = sm_count / base_ctas;  // aim at one full wave
   split = std::max(1LL, std::min(split, std::max(1LL, total_chunks / 4)));
   p.args.split_k = (int)split;
   p.flops = 2.0 * x.N * (double)PH * PW * s.Cout * s.Cin * T;

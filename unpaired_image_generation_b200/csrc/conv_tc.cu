@@ -292,8 +292,16 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
   } else if (kcnt > 0) {
     const int q = warp & 3;
     const int co = mblk * 128 + q * 32 + lane;
-    const bool valid = co < args.Cout;
-    float* grow = args.g + ((long long)co * args.T + tap.out_tap) * args.Cin;
+    bool valid = co < args.Cout;
+    long long row = (long long)co * args.T + tap.out_tap;
+    if (args.row_map != nullptr) {
+      const int rm = valid ? __ldg(args.row_map + co) : -1;
+      valid = rm >= 0;
+      row = rm;
+    }
+    float* grow = args.g + row * args.Cin;
+    // rows are 16-byte aligned when Cin % 4 == 0: use 4-wide vector reductions
+    const bool vec_ok = (args.Cin & 3) == 0;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
 #pragma unroll 1
@@ -303,9 +311,19 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
       tmem_ld_wait();
       if (valid) {
         const int ci0 = nblk * BNW + c;
+        if (vec_ok && ci0 + 32 <= args.Cin) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (ci0 + j < args.Cin) atomicAdd(grow + ci0 + j, __uint_as_float(r[j]));
+          for (int j = 0; j < 32; j += 4) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(grow + ci0 + j),
+                         "f"(__uint_as_float(r[j])), "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])),
+                         "f"(__uint_as_float(r[j + 3]))
+                         : "memory");
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (ci0 + j < args.Cin) atomicAdd(grow + ci0 + j, __uint_as_float(r[j]));
+          }
         }
       }
     }

@@ -29,6 +29,9 @@ long long align_up(long long v, long long a) { return (v + a - 1) / a * a; }
 
 cgb_engine::~cgb_engine() {
   if (graph) cudaGraphExecDestroy(graph);
+  for (cudaEvent_t ev : events) cudaEventDestroy(ev);
+  for (int l = 1; l < kLanes; ++l)
+    if (lane_streams[l]) cudaStreamDestroy(lane_streams[l]);
   if (meta) cudaFree(meta);
 }
 
@@ -155,32 +158,38 @@ void cgb_engine::layout(Arena& A) {
     D.stats = static_cast<float2*>(A.alloc(D.stats_bytes));
     D.bstats = static_cast<float2*>(A.alloc(D.stats_bytes));
   }
-  // generator backward scratch
-  dpre_head = A.tensor(N, S, S, 16, 0);
-  dxp_head = A.tensor(N, S + 6, S + 6, 64, 0);
-  dyF = A.tensor(N, S, S, 64, 0);
-  dxF = A.tensor(N, S, S, 64, 0);
-  dyH = A.tensor(N, H2, H2, 128, 0);
-  dxH = A.tensor(N, H2, H2, 128, 0);
-  dyQ = A.tensor(N, H4, H4, 256, 0);
-  GQ[0] = A.tensor(N, H4, H4, 256, 0);
-  GQ[1] = A.tensor(N, H4, H4, 256, 0);
-  dbpQ = A.tensor(N, H4 + 2, H4 + 2, 256, 0);
-  dxpQ = A.tensor(N, H4 + 2, H4 + 2, 256, 0);
+  for (GenScratch& g : gs) {  // one backward scratch set per lane
+    g.dpre_head = A.tensor(N, S, S, 16, 0);
+    g.dxp_head = A.tensor(N, S + 6, S + 6, 64, 0);
+    g.dyF = A.tensor(N, S, S, 64, 0);
+    g.dxF = A.tensor(N, S, S, 64, 0);
+    g.dyH = A.tensor(N, H2, H2, 128, 0);
+    g.dxH = A.tensor(N, H2, H2, 128, 0);
+    g.dyQ = A.tensor(N, H4, H4, 256, 0);
+    g.GQ[0] = A.tensor(N, H4, H4, 256, 0);
+    g.GQ[1] = A.tensor(N, H4, H4, 256, 0);
+    g.dbpQ = A.tensor(N, H4 + 2, H4 + 2, 256, 0);
+    g.dxpQ = A.tensor(N, H4 + 2, H4 + 2, 256, 0);
+    g.colbuf_elems = (size_t)N * (S + 6) * (S + 6) * 256;
+    g.colbuf = static_cast<bf16*>(A.alloc(g.colbuf_elems * sizeof(bf16)));
+  }
   for (int i = 0; i < 2; ++i) {
     dxp_img[i] = A.tensor(N, S + 6, S + 6, 16, 0);
     dx_D0[i] = A.tensor(N, S, S, 16, 0);
   }
-  // discriminator backward scratch
-  dlogits = A.tensor(N, H8 - 2, H8 - 2, 16, 0);
-  dx3 = A.tensor(N, H8 - 1, H8 - 1, 512, 0);
-  dy3 = A.tensor(N, H8 - 1, H8 - 1, 512, 0);
-  dx2 = A.tensor(N, H8, H8, 256, 0);
-  dy2 = A.tensor(N, H8, H8, 256, 0);
-  dx1 = A.tensor(N, H4, H4, 128, 0);
-  dy1 = A.tensor(N, H4, H4, 128, 0);
-  dx0 = A.tensor(N, H2, H2, 64, 0);
-  dpre0 = A.tensor(N, H2, H2, 64, 0);
+  for (DisScratch& d : ds) {
+    d.dlogits = A.tensor(N, H8 - 2, H8 - 2, 16, 0);
+    d.dx3 = A.tensor(N, H8 - 1, H8 - 1, 512, 0);
+    d.dy3 = A.tensor(N, H8 - 1, H8 - 1, 512, 0);
+    d.dx2 = A.tensor(N, H8, H8, 256, 0);
+    d.dy2 = A.tensor(N, H8, H8, 256, 0);
+    d.dx1 = A.tensor(N, H4, H4, 128, 0);
+    d.dy1 = A.tensor(N, H4, H4, 128, 0);
+    d.dx0 = A.tensor(N, H2, H2, 64, 0);
+    d.dpre0 = A.tensor(N, H2, H2, 64, 0);
+    d.colbuf_elems = (size_t)N * H2 * H2 * 64;
+    d.colbuf = static_cast<bf16*>(A.alloc(d.colbuf_elems * sizeof(bf16)));
+  }
   A.alloc(1024);  // tail guard
 }
 
@@ -220,7 +229,8 @@ void cgb_engine::record_programs() {
     pr.add([pp](cudaStream_t st) { run(*pp, st); }, 1, kOpIgemm, p.flops);
     *fl += p.flops;
   };
-  auto add_wgrad = [E](Program& pr, double* fl, const LayerParam& L, const TensorDesc& x, const TensorDesc& dy) {
+  auto add_wgrad = [E](Program& pr, double* fl, const LayerParam& L, const TensorDesc& x, const TensorDesc& dy,
+                       bf16* colbuf, size_t colbuf_elems) {
     float* g = E->G[L.group] + L.w_off;
     if (tc_supports_wgrad(L.spec)) {
       WgradPlan p = plan_wgrad(L.spec, x, dy, g, E->sm_count);
@@ -230,10 +240,15 @@ void cgb_engine::record_programs() {
       pr.add([pp](cudaStream_t st) { run(*pp, st); }, 1, kOpWgradTc, p.flops);
       *fl += p.flops;
     } else {
-      const ConvSpec s = L.spec;
-      const double f = 2.0 * dy.N * (double)dy.H * dy.W * s.Cout * s.Cin * s.taps();
-      pr.add([s, x, dy, g](cudaStream_t st) { wgrad_direct(s, x, dy, g, st); }, 1, kOpWgradDirect, f);
-      *fl += f;
+      // 3-/1-channel layers: explicit im2col of the skinny operand, then a plain tensor-core GEMM
+      SmallWgradPlan p = plan_wgrad_small(L.spec, x, dy, g, colbuf, colbuf_elems, E->sm_count);
+      p.gemm.args.taps = static_cast<const WTap*>(E->meta_upload(p.gemm.taps.data(), p.gemm.taps.size() * sizeof(WTap)));
+      if (!p.row_map.empty())
+        p.gemm.args.row_map = static_cast<const int*>(E->meta_upload(p.row_map.data(), p.row_map.size() * sizeof(int)));
+      E->small_wgrad_plans.push_back(p);
+      const SmallWgradPlan* pp = &E->small_wgrad_plans.back();
+      pr.add([pp](cudaStream_t st) { run(*pp, st); }, 2, kOpWgradDirect, p.flops);
+      *fl += p.flops;
     }
   };
   auto add_norm = [](Program& pr, const TensorDesc& y, float2* stats, int act, const TensorDesc* residual,
@@ -290,8 +305,8 @@ void cgb_engine::record_programs() {
   };
 
   // ---------------------------------------------------------------- generator backward
-  auto emit_gen_backward = [&](Program& pr, double* fl, GenPass& P, const TensorDesc* target, float l1_scale,
-                               int loss_slot, GradSrc gsrc, const TensorDesc* dxp_img_out) {
+  auto emit_gen_backward = [&](Program& pr, double* fl, GenPass& P, GenScratch& S, const TensorDesc* target,
+                               float l1_scale, int loss_slot, GradSrc gsrc, const TensorDesc* dxp_img_out) {
     const std::vector<LayerParam>& L = E->layers[P.net];
     float* Gg = E->G[CGB_GROUP_G];
     float2* st = P.stats;
@@ -299,7 +314,7 @@ void cgb_engine::record_programs() {
     pr.add([bs, bytes = P.stats_bytes](cudaStream_t s) { CGB_CUDA(cudaMemsetAsync(bs, 0, bytes, s)); }, 0, kOpMemset);
     const LayerParam& head = L[5 + 2 * nb];
     {
-      const TensorDesc out = P.out, dpre = E->dpre_head;
+      const TensorDesc out = P.out, dpre = S.dpre_head;
       float* slot = loss_slot >= 0 ? E->losses + loss_slot : nullptr;
       if (target) {
         const TensorDesc tg = *target;
@@ -310,59 +325,59 @@ void cgb_engine::record_programs() {
       float* gb = Gg + head.b_off;
       pr.add([dpre, gb](cudaStream_t s) { bias_grad(dpre, 3, gb, s); });
     }
-    add_wgrad(pr, fl, head, P.a_u2p, E->dpre_head);
-    add_dgrad(pr, fl, head, E->dpre_head, E->dxp_head);
+    add_wgrad(pr, fl, head, P.a_u2p, S.dpre_head, S.colbuf, S.colbuf_elems);
+    add_dgrad(pr, fl, head, S.dpre_head, S.dxp_head);
     GradSrc g;
-    g.g2 = &E->dxp_head;
+    g.g2 = &S.dxp_head;
     g.fold = 3;
-    add_in_bwd(pr, P.y_u2, st + P.stat_off[4 + 2 * nb], bs + P.stat_off[4 + 2 * nb], g, kActRelu, nullptr, E->dyF);
-    add_wgrad(pr, fl, L[4 + 2 * nb], P.a_u1, E->dyF);
-    add_dgrad(pr, fl, L[4 + 2 * nb], E->dyF, E->dxH);
+    add_in_bwd(pr, P.y_u2, st + P.stat_off[4 + 2 * nb], bs + P.stat_off[4 + 2 * nb], g, kActRelu, nullptr, S.dyF);
+    add_wgrad(pr, fl, L[4 + 2 * nb], P.a_u1, S.dyF, S.colbuf, S.colbuf_elems);
+    add_dgrad(pr, fl, L[4 + 2 * nb], S.dyF, S.dxH);
     g = GradSrc();
-    g.g1 = &E->dxH;
-    add_in_bwd(pr, P.y_u1, st + P.stat_off[3 + 2 * nb], bs + P.stat_off[3 + 2 * nb], g, kActRelu, nullptr, E->dyH);
-    add_wgrad(pr, fl, L[3 + 2 * nb], P.xp[nb], E->dyH);
+    g.g1 = &S.dxH;
+    add_in_bwd(pr, P.y_u1, st + P.stat_off[3 + 2 * nb], bs + P.stat_off[3 + 2 * nb], g, kActRelu, nullptr, S.dyH);
+    add_wgrad(pr, fl, L[3 + 2 * nb], P.xp[nb], S.dyH, S.colbuf, S.colbuf_elems);
     int cur = 0;
-    add_dgrad(pr, fl, L[3 + 2 * nb], E->dyH, E->GQ[cur]);  // G_nb: gradient w.r.t. the residual stream output
+    add_dgrad(pr, fl, L[3 + 2 * nb], S.dyH, S.GQ[cur]);  // G_nb: gradient w.r.t. the residual stream output
     for (int k = nb - 1; k >= 0; --k) {
       // gradient w.r.t. x_{k+1}: G_{k+1} = G_{k+2} + fold(dxp_{k+1})   (k == nb-1: G_nb as is)
       g = GradSrc();
-      g.g1 = &E->GQ[cur];
+      g.g1 = &S.GQ[cur];
       const TensorDesc* store = nullptr;
       if (k != nb - 1) {
-        g.g2 = &E->dxpQ;
+        g.g2 = &S.dxpQ;
         g.fold = 1;
-        store = &E->GQ[cur ^ 1];
+        store = &S.GQ[cur ^ 1];
       }
-      add_in_bwd(pr, P.y2[k], st + P.stat_off[4 + 2 * k], bs + P.stat_off[4 + 2 * k], g, kActNone, store, E->dyQ);
+      add_in_bwd(pr, P.y2[k], st + P.stat_off[4 + 2 * k], bs + P.stat_off[4 + 2 * k], g, kActNone, store, S.dyQ);
       if (store) cur ^= 1;
-      add_wgrad(pr, fl, L[4 + 2 * k], P.bp[k], E->dyQ);
-      add_dgrad(pr, fl, L[4 + 2 * k], E->dyQ, E->dbpQ);
+      add_wgrad(pr, fl, L[4 + 2 * k], P.bp[k], S.dyQ, S.colbuf, S.colbuf_elems);
+      add_dgrad(pr, fl, L[4 + 2 * k], S.dyQ, S.dbpQ);
       g = GradSrc();
-      g.g2 = &E->dbpQ;
+      g.g2 = &S.dbpQ;
       g.fold = 1;
-      add_in_bwd(pr, P.y1[k], st + P.stat_off[3 + 2 * k], bs + P.stat_off[3 + 2 * k], g, kActRelu, nullptr, E->dyQ);
-      add_wgrad(pr, fl, L[3 + 2 * k], P.xp[k], E->dyQ);
-      add_dgrad(pr, fl, L[3 + 2 * k], E->dyQ, E->dxpQ);
+      add_in_bwd(pr, P.y1[k], st + P.stat_off[3 + 2 * k], bs + P.stat_off[3 + 2 * k], g, kActRelu, nullptr, S.dyQ);
+      add_wgrad(pr, fl, L[3 + 2 * k], P.xp[k], S.dyQ, S.colbuf, S.colbuf_elems);
+      add_dgrad(pr, fl, L[3 + 2 * k], S.dyQ, S.dxpQ);
     }
     // down2 output feeds block 0 twice (conv path + skip): G_0 = G_1 + fold(dxp_0)
     g = GradSrc();
-    g.g1 = &E->GQ[cur];
-    g.g2 = &E->dxpQ;
+    g.g1 = &S.GQ[cur];
+    g.g2 = &S.dxpQ;
     g.fold = 1;
-    add_in_bwd(pr, P.y_d2, st + P.stat_off[2], bs + P.stat_off[2], g, kActRelu, &E->GQ[cur ^ 1], E->dyQ);
-    add_wgrad(pr, fl, L[2], P.a_d1, E->dyQ);
-    add_dgrad(pr, fl, L[2], E->dyQ, E->dxH);
+    add_in_bwd(pr, P.y_d2, st + P.stat_off[2], bs + P.stat_off[2], g, kActRelu, &S.GQ[cur ^ 1], S.dyQ);
+    add_wgrad(pr, fl, L[2], P.a_d1, S.dyQ, S.colbuf, S.colbuf_elems);
+    add_dgrad(pr, fl, L[2], S.dyQ, S.dxH);
     g = GradSrc();
-    g.g1 = &E->dxH;
-    add_in_bwd(pr, P.y_d1, st + P.stat_off[1], bs + P.stat_off[1], g, kActRelu, nullptr, E->dyH);
-    add_wgrad(pr, fl, L[1], P.a_stem, E->dyH);
-    add_dgrad(pr, fl, L[1], E->dyH, E->dxF);
+    g.g1 = &S.dxH;
+    add_in_bwd(pr, P.y_d1, st + P.stat_off[1], bs + P.stat_off[1], g, kActRelu, nullptr, S.dyH);
+    add_wgrad(pr, fl, L[1], P.a_stem, S.dyH, S.colbuf, S.colbuf_elems);
+    add_dgrad(pr, fl, L[1], S.dyH, S.dxF);
     g = GradSrc();
-    g.g1 = &E->dxF;
-    add_in_bwd(pr, P.y_stem, st + P.stat_off[0], bs + P.stat_off[0], g, kActRelu, nullptr, E->dyF);
-    add_wgrad(pr, fl, L[0], P.in, E->dyF);
-    if (dxp_img_out) add_dgrad(pr, fl, L[0], E->dyF, *dxp_img_out);
+    g.g1 = &S.dxF;
+    add_in_bwd(pr, P.y_stem, st + P.stat_off[0], bs + P.stat_off[0], g, kActRelu, nullptr, S.dyF);
+    add_wgrad(pr, fl, L[0], P.in, S.dyF, S.colbuf, S.colbuf_elems);
+    if (dxp_img_out) add_dgrad(pr, fl, L[0], S.dyF, *dxp_img_out);
   };
 
   // ---------------------------------------------------------------- discriminator
@@ -381,8 +396,8 @@ void cgb_engine::record_programs() {
     add_norm(pr, D.y3, st + D.stat_off[2], kActLeaky, nullptr, D.a3);
     add_fprop(pr, fl, L[4], D.a3, D.logits, kActNone);
   };
-  auto emit_dis_backward = [&](Program& pr, double* fl, DisPass& D, float target, float w, int loss_slot,
-                               bool weight_grads, const TensorDesc* dx_img_out) {
+  auto emit_dis_backward = [&](Program& pr, double* fl, DisPass& D, DisScratch& S, float target, float w,
+                               int loss_slot, bool weight_grads, const TensorDesc* dx_img_out) {
     const std::vector<LayerParam>& L = E->layers[D.net];
     float* Gd = E->G[CGB_GROUP_D];
     float2* st = D.stats;
@@ -390,40 +405,40 @@ void cgb_engine::record_programs() {
     pr.add([bs, bytes = D.stats_bytes](cudaStream_t s) { CGB_CUDA(cudaMemsetAsync(bs, 0, bytes, s)); }, 0, kOpMemset);
     {
       const TensorDesc lg = D.logits;
-      const TensorDesc* dl = &E->dlogits;
+      const TensorDesc* dl = &S.dlogits;
       float* slot = E->losses + loss_slot;
       pr.add([lg, target, w, slot, dl](cudaStream_t s) { mse_loss(lg, target, w, slot, dl, s); });
     }
     if (weight_grads) {
-      const TensorDesc dl = E->dlogits;
+      const TensorDesc dl = S.dlogits;
       float* gb = Gd + L[4].b_off;
       pr.add([dl, gb](cudaStream_t s) { bias_grad(dl, 1, gb, s); });
-      add_wgrad(pr, fl, L[4], D.a3, E->dlogits);
+      add_wgrad(pr, fl, L[4], D.a3, S.dlogits, S.colbuf, S.colbuf_elems);
     }
-    add_dgrad(pr, fl, L[4], E->dlogits, E->dx3);
+    add_dgrad(pr, fl, L[4], S.dlogits, S.dx3);
     GradSrc g;
-    g.g1 = &E->dx3;
-    add_in_bwd(pr, D.y3, st + D.stat_off[2], bs + D.stat_off[2], g, kActLeaky, nullptr, E->dy3);
-    if (weight_grads) add_wgrad(pr, fl, L[3], D.a2, E->dy3);
-    add_dgrad(pr, fl, L[3], E->dy3, E->dx2);
-    g.g1 = &E->dx2;
-    add_in_bwd(pr, D.y2, st + D.stat_off[1], bs + D.stat_off[1], g, kActLeaky, nullptr, E->dy2);
-    if (weight_grads) add_wgrad(pr, fl, L[2], D.a1, E->dy2);
-    add_dgrad(pr, fl, L[2], E->dy2, E->dx1);
-    g.g1 = &E->dx1;
-    add_in_bwd(pr, D.y1, st + D.stat_off[0], bs + D.stat_off[0], g, kActLeaky, nullptr, E->dy1);
-    if (weight_grads) add_wgrad(pr, fl, L[1], D.l0, E->dy1);
-    add_dgrad(pr, fl, L[1], E->dy1, E->dx0);
+    g.g1 = &S.dx3;
+    add_in_bwd(pr, D.y3, st + D.stat_off[2], bs + D.stat_off[2], g, kActLeaky, nullptr, S.dy3);
+    if (weight_grads) add_wgrad(pr, fl, L[3], D.a2, S.dy3, S.colbuf, S.colbuf_elems);
+    add_dgrad(pr, fl, L[3], S.dy3, S.dx2);
+    g.g1 = &S.dx2;
+    add_in_bwd(pr, D.y2, st + D.stat_off[1], bs + D.stat_off[1], g, kActLeaky, nullptr, S.dy2);
+    if (weight_grads) add_wgrad(pr, fl, L[2], D.a1, S.dy2, S.colbuf, S.colbuf_elems);
+    add_dgrad(pr, fl, L[2], S.dy2, S.dx1);
+    g.g1 = &S.dx1;
+    add_in_bwd(pr, D.y1, st + D.stat_off[0], bs + D.stat_off[0], g, kActLeaky, nullptr, S.dy1);
+    if (weight_grads) add_wgrad(pr, fl, L[1], D.l0, S.dy1, S.colbuf, S.colbuf_elems);
+    add_dgrad(pr, fl, L[1], S.dy1, S.dx0);
     {
-      const TensorDesc l0 = D.l0, dx0_ = E->dx0, dp = E->dpre0;
+      const TensorDesc l0 = D.l0, dx0_ = S.dx0, dp = S.dpre0;
       pr.add([l0, dx0_, dp](cudaStream_t s) { leaky_bwd(l0, dx0_, dp, s); });
       if (weight_grads) {
         float* gb = Gd + L[0].b_off;
         pr.add([dp, gb](cudaStream_t s) { bias_grad(dp, 64, gb, s); });
-        add_wgrad(pr, fl, L[0], D.in, E->dpre0);
+        add_wgrad(pr, fl, L[0], D.in, S.dpre0, S.colbuf, S.colbuf_elems);
       }
     }
-    if (dx_img_out) add_dgrad(pr, fl, L[0], E->dpre0, *dx_img_out);
+    if (dx_img_out) add_dgrad(pr, fl, L[0], S.dpre0, *dx_img_out);
   };
 
   // ---------------------------------------------------------------- step programs
@@ -441,51 +456,83 @@ void cgb_engine::record_programs() {
   }
   // pass order: 0 fake_B = G_AB(real_A), 1 rec_A = G_BA(fake_B), 2 fake_A = G_BA(real_B),
   //             3 rec_B = G_AB(fake_A), 4 idt_A = G_AB(real_B), 5 idt_B = G_BA(real_A)
-  emit_gen_forward(prog_cycle, flops, gen[0], CGB_NET_G_AB, real_A, img[CGB_IMG_FAKE_B], true);
-  emit_gen_forward(prog_cycle, flops, gen[1], CGB_NET_G_BA, fake_B, img[CGB_IMG_REC_A], false);
-  emit_gen_forward(prog_cycle, flops, gen[2], CGB_NET_G_BA, real_B, img[CGB_IMG_FAKE_A], true);
-  emit_gen_forward(prog_cycle, flops, gen[3], CGB_NET_G_AB, fake_A, img[CGB_IMG_REC_B], false);
-  emit_gen_forward(prog_cycle, flops, gen[4], CGB_NET_G_AB, real_B, img[CGB_IMG_IDT_A], false);
-  emit_gen_forward(prog_cycle, flops, gen[5], CGB_NET_G_BA, real_A, img[CGB_IMG_IDT_B], false);
+  // Independent passes are recorded on different lanes (parallel branches of the step graph).
+  {
+    Program& pr = prog_cycle;
+    pr.fork();
+    pr.cur_lane = 0;
+    emit_gen_forward(pr, flops, gen[0], CGB_NET_G_AB, real_A, img[CGB_IMG_FAKE_B], true);
+    pr.cur_lane = 1;
+    emit_gen_forward(pr, flops, gen[2], CGB_NET_G_BA, real_B, img[CGB_IMG_FAKE_A], true);
+    pr.cur_lane = 2;
+    emit_gen_forward(pr, flops, gen[4], CGB_NET_G_AB, real_B, img[CGB_IMG_IDT_A], false);
+    pr.cur_lane = 3;
+    emit_gen_forward(pr, flops, gen[5], CGB_NET_G_BA, real_A, img[CGB_IMG_IDT_B], false);
+    pr.cur_lane = 0;
+    emit_gen_forward(pr, flops, gen[1], CGB_NET_G_BA, fake_B, img[CGB_IMG_REC_A], false);
+    pr.cur_lane = 1;
+    emit_gen_forward(pr, flops, gen[3], CGB_NET_G_AB, fake_A, img[CGB_IMG_REC_B], false);
+    pr.join();
+    pr.cur_lane = 0;
+  }
 
   const float numel_img = (float)N * 3.f * S * S;
-  {  // ---- G phase
+  {  // ---- G phase (backward part; the six forwards are prog_cycle)
     Program& pr = prog_G;
     float* gG = G[CGB_GROUP_G];
     const size_t gbytes = (size_t)group_numel[CGB_GROUP_G] * sizeof(float);
     float* ls = losses;
+    pr.cur_lane = 0;
     pr.add([gG, gbytes](cudaStream_t s) { CGB_CUDA(cudaMemsetAsync(gG, 0, gbytes, s)); }, 0, kOpMemset);
     pr.add([ls](cudaStream_t s) { CGB_CUDA(cudaMemsetAsync(ls, 0, 64 * sizeof(float), s)); }, 0, kOpMemset);
-    // identity and cycle passes (L1 seeds)
-    emit_gen_backward(pr, flops, gen[4], &real_B, cfg.lambda_B * cfg.lambda_idt / numel_img, CGB_LOSS_IDT_A, GradSrc(), nullptr);
-    emit_gen_backward(pr, flops, gen[5], &real_A, cfg.lambda_A * cfg.lambda_idt / numel_img, CGB_LOSS_IDT_B, GradSrc(), nullptr);
-    emit_gen_backward(pr, flops, gen[1], &real_A, cfg.lambda_A / numel_img, CGB_LOSS_CYCLE_A, GradSrc(), &dxp_img[0]);
-    emit_gen_backward(pr, flops, gen[3], &real_B, cfg.lambda_B / numel_img, CGB_LOSS_CYCLE_B, GradSrc(), &dxp_img[1]);
-    // adversarial terms: D frozen, gradient flows through D into the fakes
+    pr.fork();
+    // identity passes (L1 seeds), then the adversarial terms (D frozen: input gradients only)
+    pr.cur_lane = 2;
+    emit_gen_backward(pr, flops, gen[4], gs[2], &real_B, cfg.lambda_B * cfg.lambda_idt / numel_img, CGB_LOSS_IDT_A, GradSrc(), nullptr);
     emit_dis_forward(pr, flops, dis[0], CGB_NET_D_A, fake_B);
-    emit_dis_backward(pr, flops, dis[0], 1.f, 1.f, CGB_LOSS_G_A, false, &dx_D0[0]);
+    emit_dis_backward(pr, flops, dis[0], ds[0], 1.f, 1.f, CGB_LOSS_G_A, false, &dx_D0[0]);
+    pr.cur_lane = 3;
+    emit_gen_backward(pr, flops, gen[5], gs[3], &real_A, cfg.lambda_A * cfg.lambda_idt / numel_img, CGB_LOSS_IDT_B, GradSrc(), nullptr);
     emit_dis_forward(pr, flops, dis[1], CGB_NET_D_B, fake_A);
-    emit_dis_backward(pr, flops, dis[1], 1.f, 1.f, CGB_LOSS_G_B, false, &dx_D0[1]);
+    emit_dis_backward(pr, flops, dis[1], ds[1], 1.f, 1.f, CGB_LOSS_G_B, false, &dx_D0[1]);
+    // cycle passes: also produce the gradient w.r.t. the fake images (padded domain of the next stem)
+    pr.cur_lane = 0;
+    emit_gen_backward(pr, flops, gen[1], gs[0], &real_A, cfg.lambda_A / numel_img, CGB_LOSS_CYCLE_A, GradSrc(), &dxp_img[0]);
+    pr.cur_lane = 1;
+    emit_gen_backward(pr, flops, gen[3], gs[1], &real_B, cfg.lambda_B / numel_img, CGB_LOSS_CYCLE_B, GradSrc(), &dxp_img[1]);
+    // the passes that produced the fakes: gradient = D's input gradient + folded stem gradient
+    pr.dep(2, 0);
+    pr.dep(3, 1);
     GradSrc g;
     g.g1 = &dx_D0[0];
     g.g2 = &dxp_img[0];
     g.fold = 3;
-    emit_gen_backward(pr, flops, gen[0], nullptr, 0.f, -1, g, nullptr);
+    pr.cur_lane = 0;
+    emit_gen_backward(pr, flops, gen[0], gs[0], nullptr, 0.f, -1, g, nullptr);
     g.g1 = &dx_D0[1];
     g.g2 = &dxp_img[1];
-    emit_gen_backward(pr, flops, gen[2], nullptr, 0.f, -1, g, nullptr);
+    pr.cur_lane = 1;
+    emit_gen_backward(pr, flops, gen[2], gs[1], nullptr, 0.f, -1, g, nullptr);
+    pr.join();
+    pr.cur_lane = 0;
   }
   {  // ---- D phase: real passes are new; the fake passes reuse the G-phase forward (D unchanged since)
     Program& pr = prog_D;
     float* gD = G[CGB_GROUP_D];
     const size_t gbytes = (size_t)group_numel[CGB_GROUP_D] * sizeof(float);
+    pr.cur_lane = 0;
     pr.add([gD, gbytes](cudaStream_t s) { CGB_CUDA(cudaMemsetAsync(gD, 0, gbytes, s)); }, 0, kOpMemset);
+    pr.fork(2);
+    pr.cur_lane = 0;
     emit_dis_forward(pr, flops, dis[2], CGB_NET_D_A, real_B);
-    emit_dis_backward(pr, flops, dis[2], 1.f, 0.5f, CGB_LOSS_D_A, true, nullptr);
-    emit_dis_backward(pr, flops, dis[0], 0.f, 0.5f, CGB_LOSS_D_A, true, nullptr);
+    emit_dis_backward(pr, flops, dis[2], ds[0], 1.f, 0.5f, CGB_LOSS_D_A, true, nullptr);
+    emit_dis_backward(pr, flops, dis[0], ds[0], 0.f, 0.5f, CGB_LOSS_D_A, true, nullptr);
+    pr.cur_lane = 1;
     emit_dis_forward(pr, flops, dis[3], CGB_NET_D_B, real_A);
-    emit_dis_backward(pr, flops, dis[3], 1.f, 0.5f, CGB_LOSS_D_B, true, nullptr);
-    emit_dis_backward(pr, flops, dis[1], 0.f, 0.5f, CGB_LOSS_D_B, true, nullptr);
+    emit_dis_backward(pr, flops, dis[3], ds[1], 1.f, 0.5f, CGB_LOSS_D_B, true, nullptr);
+    emit_dis_backward(pr, flops, dis[1], ds[1], 0.f, 0.5f, CGB_LOSS_D_B, true, nullptr);
+    pr.join(2);
+    pr.cur_lane = 0;
   }
   // ---- optimiser + bf16 weight refresh
   for (int g = 0; g < 2; ++g) {

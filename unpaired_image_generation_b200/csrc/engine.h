@@ -11,6 +11,7 @@
 #include "../../include/cyclegan_b200.h"
 #include "conv_plan.h"
 #include "pointwise.h"
+#include "small_wgrad.h"
 
 namespace cgb {
 
@@ -24,20 +25,59 @@ struct LayerParam {
 };
 
 typedef std::function<void(cudaStream_t)> Op;
-enum OpKind { kOpOther = 0, kOpIgemm = 1, kOpWgradTc = 2, kOpWgradDirect = 3, kOpNorm = 4, kOpMemset = 5, kNumOpKinds = 6 };
+enum OpKind { kOpOther = 0, kOpIgemm = 1, kOpWgradTc = 2, kOpWgradDirect = 3, kOpNorm = 4, kOpMemset = 5, kOpDep = 6, kNumOpKinds = 7 };
+constexpr int kLanes = 4;  // independent passes of the step run on parallel graph branches ("lanes")
+
+// A recorded launch sequence.  Each op belongs to a lane; `dep(a, b)` makes everything issued later on lane b
+// wait for everything issued so far on lane a.  Run on ONE stream the recorded order is already a valid
+// serialisation (eager mode); captured into a CUDA graph, lanes become parallel branches.
 struct Program {
   std::vector<Op> ops;
-  std::vector<int> kinds;
+  std::vector<int> kinds, lanes, dep_from;
   std::vector<double> flops;
   long long launches = 0;
+  int cur_lane = 0;
   void add(Op op, int n_launches = 1, int kind = kOpOther, double fl = 0.0) {
     ops.push_back(std::move(op));
     kinds.push_back(kind);
+    lanes.push_back(cur_lane);
+    dep_from.push_back(-1);
     flops.push_back(fl);
     launches += n_launches;
   }
+  void dep(int from, int to) {
+    ops.push_back(Op());
+    kinds.push_back(kOpDep);
+    lanes.push_back(to);
+    dep_from.push_back(from);
+    flops.push_back(0.0);
+  }
+  void fork(int n = kLanes) {
+    for (int l = 1; l < n; ++l) dep(0, l);
+  }
+  void join(int n = kLanes) {
+    for (int l = 1; l < n; ++l) dep(l, 0);
+  }
   void run(cudaStream_t st) const {
-    for (const Op& op : ops) op(st);
+    for (size_t i = 0; i < ops.size(); ++i)
+      if (kinds[i] != kOpDep) ops[i](st);
+  }
+  // lanes[l] are distinct streams (lane 0 = the caller's); events: one per dep op, created by the caller
+  void run_lanes(cudaStream_t* lane_streams, std::vector<cudaEvent_t>& events, size_t* next_event) const {
+    for (size_t i = 0; i < ops.size(); ++i) {
+      if (kinds[i] == kOpDep) {
+        if (*next_event >= events.size()) {
+          cudaEvent_t ev;
+          CGB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+          events.push_back(ev);
+        }
+        cudaEvent_t ev = events[(*next_event)++];
+        CGB_CUDA(cudaEventRecord(ev, lane_streams[dep_from[i]]));
+        CGB_CUDA(cudaStreamWaitEvent(lane_streams[lanes[i]], ev, 0));
+      } else {
+        ops[i](lane_streams[lanes[i]]);
+      }
+    }
   }
   // replay only the ops of one kind (profiling; data dependencies are ignored on purpose)
   void run_kind(int kind, cudaStream_t st, long long* count, double* fl) const {
@@ -93,6 +133,17 @@ struct DisPass {
   long long stat_off[3] = {0, 0, 0};
 };
 
+struct GenScratch {  // backward scratch of one generator pass (one set per lane)
+  TensorDesc dpre_head, dxp_head, dyF, dxF, dyH, dxH, dyQ, GQ[2], dbpQ, dxpQ;
+  bf16* colbuf = nullptr;  // im2col scratch of the 3-channel operands (stem / head weight gradients)
+  size_t colbuf_elems = 0;
+};
+struct DisScratch {
+  TensorDesc dlogits, dx3, dy3, dx2, dy2, dx1, dy1, dx0, dpre0;
+  bf16* colbuf = nullptr;  // conv0 / conv4 weight gradients
+  size_t colbuf_elems = 0;
+};
+
 }  // namespace cgb
 
 struct cgb_engine {
@@ -122,10 +173,9 @@ struct cgb_engine {
   float* adam_hyper[2] = {nullptr, nullptr};
   std::vector<cgb::GenPass> gen;  // 6 training passes + 1 module-forward pass
   std::vector<cgb::DisPass> dis;  // 4 training passes + 1 module-forward pass
-  // generator backward scratch
-  cgb::TensorDesc dpre_head, dxp_head, dyF, dxF, dyH, dxH, dyQ, GQ[2], dbpQ, dxpQ, dxp_img[2], dx_D0[2];
-  // discriminator backward scratch
-  cgb::TensorDesc dlogits, dx3, dy3, dx2, dy2, dx1, dy1, dx0, dpre0;
+  cgb::GenScratch gs[cgb::kLanes];
+  cgb::DisScratch ds[2];
+  cgb::TensorDesc dxp_img[2], dx_D0[2];  // gradients w.r.t. the fake images (from the cycle passes / from D)
 
   // library-owned small tables
   void* meta = nullptr;
@@ -136,10 +186,13 @@ struct cgb_engine {
 
   std::deque<cgb::IgemmPlan> igemm_plans;
   std::deque<cgb::WgradPlan> wgrad_plans;
+  std::deque<cgb::SmallWgradPlan> small_wgrad_plans;
   cgb::Program prog_set_inputs, prog_cycle, prog_G, prog_D, prog_adam[2], prog_refresh[2];
   cgb::Program prog_mod_gen[2], prog_mod_dis[2];
   double conv_flops = 0;  // accumulated while recording prog_cycle/prog_G/prog_D
 
+  cudaStream_t lane_streams[cgb::kLanes] = {nullptr, nullptr, nullptr, nullptr};  // [0] = caller's stream
+  std::vector<cudaEvent_t> events;
   cudaGraphExec_t graph = nullptr;
   bool graph_failed = false;
   int step_calls = 0;

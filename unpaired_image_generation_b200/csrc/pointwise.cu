@@ -225,9 +225,9 @@ __global__ void colsum_kernel(DevTensor y, float* __restrict__ out, int pix_per_
 }
 
 int pick_pix_per_block(int HW) {
-  int ppb = (HW + 127) / 128;
+  int ppb = (HW + 511) / 512;  // ~512 blocks per image: several CTAs per SM even at batch 1
   ppb = (ppb + 31) / 32 * 32;
-  return ppb < 64 ? 64 : ppb;
+  return ppb < 32 ? 32 : ppb;
 }
 
 // ------------------------------------------------------------------------------------------ IN apply
@@ -530,6 +530,38 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// ------------------------------------------------------------------------------------------ im2col (small C)
+// one thread per (pixel, 8-column chunk of dst)
+__global__ void im2col_small_kernel(DevTensor src, int C, int k, int stride, int sgn, int off, int use_halo,
+                                    DevTensor dst) {
+  const int C8 = dst.C / 8;
+  const long long total = (long long)dst.N * dst.H * dst.W * C8;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int j0 = (idx % C8) * 8;
+  long long r = idx / C8;
+  const int w = r % dst.W;
+  r /= dst.W;
+  const int h = r % dst.H;
+  const int n = r / dst.H;
+  const int lo = use_halo ? -src.halo : 0;
+  const int hiH = src.H + (use_halo ? src.halo : 0), hiW = src.W + (use_halo ? src.halo : 0);
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int j = j0 + i;
+    float val = 0.f;
+    if (j < k * k * C) {
+      const int t = j / C, c = j % C;
+      const int sh = h * stride + sgn * (t / k) + off, sw = w * stride + sgn * (t % k) + off;
+      if (sh >= lo && sh < hiH && sw >= lo && sw < hiW)
+        val = __bfloat162float(src.p[n * src.sN + sh * src.sH + sw * src.sW + c]);
+    }
+    v[i] = val;
+  }
+  store8(dst.p + n * dst.sN + h * dst.sH + w * dst.sW + j0, v);
+}
+
 // ------------------------------------------------------------------------------------------ direct wgrad
 // grid (pixel blocks, taps); thread <-> (cout, cin) pair(s); fp32 atomics into g[Cout][T][Cin].
 __global__ void wgrad_direct_kernel(DevTensor x, DevTensor dy, int Cin, int Cout, int k, int stride, int pad,
@@ -679,6 +711,15 @@ void adam_step(float* p, const float* g, float* m, float* v, long long n, float 
   adam_prep_kernel<<<1, 1, 0, st>>>(step_dev, hyper_dev, lr, beta1, beta2);
   CGB_CUDA(cudaGetLastError());
   adam_kernel<<<blocks_for((n + 3) / 4, 256), 256, 0, st>>>(p, g, m, v, n, beta1, beta2, eps, hyper_dev, grad_scale);
+  CGB_CUDA(cudaGetLastError());
+}
+
+void im2col_small(const TensorDesc& src, int C, int k, int stride, int sgn, int off, bool use_halo,
+                  const TensorDesc& dst, cudaStream_t st) {
+  CGB_CHECK(dst.C % 8 == 0 && dst.C >= k * k * C && dst.halo == 0, "im2col_small: bad destination");
+  const long long total = (long long)dst.N * dst.H * dst.W * (dst.C / 8);
+  im2col_small_kernel<<<blocks_for(total, 256), 256, 0, st>>>(dev(src), C, k, stride, sgn, off, use_halo ? 1 : 0,
+                                                               dev(dst));
   CGB_CUDA(cudaGetLastError());
 }
 

@@ -72,6 +72,14 @@ void pack_weights(const float* master, const PackEntry* entries_dev, int n_entri
 void adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                float eps, int* step_dev, float* hyper_dev, float grad_scale, cudaStream_t st);
 
+// ---- explicit im2col of a 16-stored-channel tensor (the 3- and 1-channel sides of stem / head / conv0 /
+// conv4), so that their weight gradients become plain tensor-core GEMMs:
+//   dst[n][h][w][t*C + c] = src[n][h*stride + sgn*r + off][w*stride + sgn*s + off][c],  t = r*k + s, c < C
+// (zero outside the valid region; with use_halo the reflect halo of src counts as valid).  dst has
+// dst.C >= k*k*C stored channels; the tail is zero-filled.
+void im2col_small(const TensorDesc& src, int C, int k, int stride, int sgn, int off, bool use_halo,
+                  const TensorDesc& dst, cudaStream_t st);
+
 // ---- CUDA-core convolution passes for the 3-channel / 1-channel layers ------------------------
 // g[Cout][T][Cin] += sum_pixels dy * x   (x may carry a reflect halo == pad; zero padding otherwise)
 void wgrad_direct(const ConvSpec& s, const TensorDesc& x, const TensorDesc& dy, float* g, cudaStream_t st);

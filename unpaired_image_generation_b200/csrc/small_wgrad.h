@@ -1,0 +1,27 @@
+// Weight gradients of the 3-/1-channel layers (generator stem and head, discriminator conv0 and conv4):
+// the skinny operand is expanded by an explicit im2col (pointwise.h: im2col_small) so that the reduction
+// over pixels becomes a plain tcgen05 GEMM (conv_tc.cu: wgrad_kernel) writing straight into the master
+// gradient layout g[Cout][T][Cin].
+#pragma once
+#include <vector>
+
+#include "conv_plan.h"
+
+namespace cgb {
+
+struct SmallWgradPlan {
+  WgradPlan gemm;            // gemm.args.taps / row_map must point at device copies before run()
+  std::vector<int> row_map;  // empty when rows map 1:1
+  // im2col parameters
+  TensorDesc src, col;
+  int C = 0, k = 0, stride = 1, sgn = 1, off = 0;
+  bool use_halo = false;
+  double flops = 0;
+};
+
+size_t small_wgrad_col_elems(const ConvSpec& s, const TensorDesc& x, const TensorDesc& dy);
+SmallWgradPlan plan_wgrad_small(const ConvSpec& s, const TensorDesc& x, const TensorDesc& dy, float* g, bf16* colbuf,
+                                size_t colbuf_elems, int sm_count);
+void run(const SmallWgradPlan& p, cudaStream_t stream);
+
+}  // namespace cgb
