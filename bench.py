@@ -267,11 +267,47 @@ def run_b200(args):
             "cpu_baseline": cpu,
             "losses_last_step": losses,
         }
+        # ---- secondary datum: the data-parallel per-GPU batch of BASELINE.json configs[2] (8 pairs per GPU)
+        if world == 1 and args.extra_batch > 0 and args.extra_batch != batch:
+            try:
+                line["extra_batch"] = measure_extra(cgb, torch, args.extra_batch, size, max(3, args.steps // 2), peaks)
+            except Exception as ex:  # never lose the headline line
+                line["extra_batch"] = {"error": str(ex)[:200]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return line
+
+
+def measure_extra(cgb, torch, batch, size, steps, peaks):
+    """device-resident throughput + conv roofline at another per-GPU batch (single GPU)"""
+    mods = (cgb.Generator(seed=1), cgb.Generator(seed=2), cgb.Discriminator(seed=3), cgb.Discriminator(seed=4))
+    tr = cgb.CycleGANTrainer(*mods)
+    g = torch.Generator().manual_seed(99)
+    dev_A = (torch.rand(batch, 3, size, size, generator=g) * 2 - 1).cuda()
+    dev_B = (torch.rand(batch, 3, size, size, generator=g) * 2 - 1).cuda()
+    eng = tr._ensure_engine(dev_A)
+    with torch.cuda.stream(tr.stream):
+        for _ in range(3):
+            eng.set_inputs(dev_A, dev_B)
+            eng.train_step()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(tr.stream)
+        for _ in range(steps):
+            eng.set_inputs(dev_A, dev_B)
+            eng.train_step()
+        ev1.record(tr.stream)
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1) / steps
+        ms_ig, n_ig, fl_ig = eng.profile_kind(1, reps=3)
+        ms_wg, n_wg, fl_wg = eng.profile_kind(2, reps=3)
+    return {"batch_per_gpu": batch, "value": batch / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+            "igemm_tflops": fl_ig / (ms_ig * 1e-3) / 1e12, "igemm_frac_of_peak": fl_ig / (ms_ig * 1e-3) / 1e12 / peaks["tf_sustained"],
+            "wgrad_tflops": fl_wg / (ms_wg * 1e-3) / 1e12,
+            "step_conv_tflops": eng.conv_flops_per_step / (ms * 1e-3) / 1e12,
+            "step_conv_frac_of_peak": eng.conv_flops_per_step / (ms * 1e-3) / 1e12 / peaks["tf_sustained"]}
 
 
 def main():
@@ -283,6 +319,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1, help="image pairs per GPU per step (configs[1]: 1)")
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--extra-batch", type=int, default=8, help="also report device throughput at this per-GPU batch (0 = off)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -12,7 +12,7 @@ for c in ${CASES:-res_small res down down2 dconv1 dconv3 up up2 stem head dconv0
   timeout 120 $BIN $c ${NBATCH:-1} >> $LOG 2>&1
   echo "exit $?" >> $LOG
 done
-echo "=== res BN=256" >> $LOG; timeout 120 $BIN res 1 256 >> $LOG 2>&1; echo "exit $?" >> $LOG
-echo "=== res BN=128" >> $LOG; timeout 120 $BIN res 1 128 >> $LOG 2>&1; echo "exit $?" >> $LOG
+echo "=== res no-cluster" >> $LOG; CGB_NO_CLUSTER=1 timeout 120 $BIN res 1 >> $LOG 2>&1; echo "exit $?" >> $LOG
+echo "=== res N=8 no-cluster" >> $LOG; CGB_NO_CLUSTER=1 timeout 120 $BIN res 8 >> $LOG 2>&1; echo "exit $?" >> $LOG
 echo "=== res N=8" >> $LOG; timeout 120 $BIN res 8 >> $LOG 2>&1; echo "exit $?" >> $LOG
 grep -E "^case|exit|OK|FAIL|us/launch|EXCEPTION|timeout|error" $LOG | tail -120

@@ -57,6 +57,7 @@ struct IgemmArgs {
   int k_count[kMaxClasses];
   long long out_off[kMaxClasses];  // element offset of the class's first output pixel
   int tiles_w, tiles_h;            // tiles per image (tile = TH x TW output pixels, TH*TW = 128)
+  int N;                           // images (tile indices past N * tiles are padding of a cluster launch)
   int tw_shift;                    // TW = 1 << tw_shift
   int Ho, Wo;                      // valid output extent in class-local coordinates
   int Cout;                        // channels actually stored (<= n_blocks * BN)

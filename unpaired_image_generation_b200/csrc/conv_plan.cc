@@ -2,6 +2,7 @@
 #include "conv_plan.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace cgb {
@@ -49,6 +50,10 @@ static CUtensorMap view_s2(const TensorDesc& t, int box_c, int box_w, int box_h)
 static int choose_bn(int rows, int bk, long long ctas_per_nblock, int sm_count) {
   if (rows <= 16) return 16;
   if (bk == 16) return 64;
+  if (const char* f = std::getenv("CGB_FORCE_BN")) {
+    const int bn = std::atoi(f);
+    if ((bn == 64 || bn == 128 || bn == 256) && rows % bn == 0) return bn;
+  }
   const int cands[3] = {256, 128, 64};
   for (int bn : cands) {
     if (rows % bn != 0) continue;
@@ -57,7 +62,45 @@ static int choose_bn(int rows, int bk, long long ctas_per_nblock, int sm_count) 
   return 64;
 }
 
+// Cluster shape for a (BN, BK, n_blocks, tiles) problem; must match an instantiation in conv_tc.cu.
+static void choose_cluster(int BN, int BK, int n_blocks, int num_tiles, int* CM, int* CN) {
+  *CM = 1;
+  *CN = 1;
+  // Measured on B200 (profiles/r01_c_cluster_multicast.txt): with <= 8-CTA clusters TMA multicast does not
+  // reduce L2 -> SM time (the microarchitecture notes say the same: multicast ~ unicast at cluster size <= 4),
+  // and the cross-CTA slot release couples the pipelines: res-block conv 18.6 us -> 33.5 us at batch 1,
+  // 53.6 -> 49.4 us at batch 8.  Kept behind CGB_CLUSTER=1 for experiments.
+  static const bool enabled = std::getenv("CGB_CLUSTER") != nullptr;
+  if (!enabled || BK != 64 || BN < 64) return;
+  int cn = 1;
+  if (BN == 64) cn = n_blocks % 4 == 0 ? 4 : (n_blocks % 2 == 0 ? 2 : 1);
+  else if (BN == 128) cn = n_blocks % 2 == 0 ? 2 : 1;
+  int cm = cn == 4 ? 2 : 4;
+  while (cm > 1 && num_tiles < 2 * cm) cm /= 2;
+  if (cm == 1 && cn > 1) return;  // (1 x CN) is only instantiated for BN = 64, CN = 4
+  *CM = cm;
+  *CN = cn;
+}
+
+enum ViewKind { kViewS1Interior, kViewS1Padded, kViewS2 };
+
+// choose the N tile and the cluster, then build both tensor maps with per-CTA slice boxes
+static void finalize(IgemmPlan& p, ViewKind vk, const TensorDesc& act, const bf16* w, int rows, int Kw, int sm_count) {
+  p.BN = choose_bn(rows, p.BK, (long long)p.num_tiles * p.n_classes, sm_count);
+  p.n_blocks = (padded_rows(rows) + p.BN - 1) / p.BN;
+  choose_cluster(p.BN, p.BK, p.n_blocks, p.num_tiles, &p.CM, &p.CN);
+  const int TW = 1 << p.args.tw_shift, TH = 128 >> p.args.tw_shift;
+  // A slice of a CTA: 128 / CN consecutive tile pixels = SH rows x SW columns
+  const int SH = TH >= p.CN ? TH / p.CN : 1;
+  const int SW = TH >= p.CN ? TW : TW * TH / p.CN;
+  CGB_CHECK(SH * SW * p.CN == 128 && SW >= 8, "cluster slice does not tile the 128-pixel M tile");
+  if (vk == kViewS2) p.tmA = view_s2(act, p.BK, SW, SH);
+  else p.tmA = view_s1(act, vk == kViewS1Padded, p.BK, SW, SH);
+  p.tmB = make_tmap_2d(w, padded_rows(rows), Kw, Kw, p.BK, p.BN / p.CM, p.BK * 2);
+}
+
 static void set_tiles(IgemmPlan& p, int N, int Ho, int Wo) {
+  p.args.N = N;
   // tile = TH x TW output pixels with TH * TW = 128: pick the shape that wastes the fewest pixels
   // (e.g. the 66x66 padded-domain dgrads: 8x16 tiles -> 45 tiles instead of 66 of 1x128)
   int shift = 7;
@@ -98,6 +141,7 @@ IgemmPlan plan_fprop(const ConvSpec& s, const TensorDesc& x, const bf16* wf, con
   p.args.act = act;
   p.args.Cout = s.CoutS;
   p.args.stats = nullptr;
+  ViewKind vk = kViewS1Interior;
 
   if (!s.transposed) {
     set_tiles(p, x.N, Ho, Wo);
@@ -106,10 +150,9 @@ IgemmPlan plan_fprop(const ConvSpec& s, const TensorDesc& x, const bf16* wf, con
     p.args.sW = y.sW();
     p.args.out_off[0] = 0;
     p.args.k_begin[0] = 0;
-    const int TW = 1 << p.args.tw_shift, TH = 128 >> p.args.tw_shift;
     if (s.stride == 1) {
       if (s.reflect) CGB_CHECK(x.halo == s.pad, "reflect conv input must carry a halo equal to the padding");
-      p.tmA = view_s1(x, s.reflect, BK, TW, TH);
+      vk = s.reflect ? kViewS1Padded : kViewS1Interior;
       for (int r = 0; r < k; ++r)
         for (int c = 0; c < k; ++c)
           for (int c0 = 0; c0 < s.CinS; c0 += BK) {
@@ -123,7 +166,7 @@ IgemmPlan plan_fprop(const ConvSpec& s, const TensorDesc& x, const bf16* wf, con
           }
     } else {
       CGB_CHECK(s.stride == 2 && !s.reflect, "only zero-padded stride-2 convs are supported");
-      p.tmA = view_s2(x, BK, TW, TH);
+      vk = kViewS2;
       for (int r = 0; r < k; ++r)
         for (int c = 0; c < k; ++c) {
           int hp, hy, wp, wx;
@@ -148,8 +191,7 @@ IgemmPlan plan_fprop(const ConvSpec& s, const TensorDesc& x, const bf16* wf, con
     p.n_classes = 4;
     p.args.sH = 2 * y.sH();
     p.args.sW = 2 * y.sW();
-    const int TW = 1 << p.args.tw_shift, TH = 128 >> p.args.tw_shift;
-    p.tmA = view_s1(x, false, BK, TW, TH);
+    vk = kViewS1Interior;
     for (int a = 0; a < 2; ++a)
       for (int b = 0; b < 2; ++b) {
         const int z = a * 2 + b;
@@ -173,9 +215,7 @@ IgemmPlan plan_fprop(const ConvSpec& s, const TensorDesc& x, const bf16* wf, con
         p.args.k_count[z] = (int)p.kiters.size() - p.args.k_begin[z];
       }
   }
-  p.BN = choose_bn(s.CoutS, BK, (long long)p.num_tiles * p.n_classes, sm_count);
-  p.n_blocks = (padded_rows(s.CoutS) + p.BN - 1) / p.BN;
-  p.tmB = make_tmap_2d(wf, padded_rows(s.CoutS), Kw, Kw, BK, p.BN, BK * 2);
+  finalize(p, vk, x, wf, s.CoutS, Kw, sm_count);
   p.flops = 2.0 * x.N * (s.transposed ? (double)x.H * x.W : (double)Ho * Wo) * s.Cout * s.Cin * T;
   return p;
 }
@@ -196,6 +236,7 @@ IgemmPlan plan_dgrad(const ConvSpec& s, const TensorDesc& dy, const bf16* wt, co
   p.args.act = kActNone;
   p.args.Cout = s.CinS;
   p.args.stats = nullptr;
+  ViewKind vk = kViewS1Interior;
 
   if (!s.transposed && s.stride == 1) {
     // zero pad:   dx[h]   = sum_r dy[h + p - r] w[r]
@@ -205,8 +246,6 @@ IgemmPlan plan_dgrad(const ConvSpec& s, const TensorDesc& dy, const bf16* wt, co
     p.n_classes = 1;
     p.args.sH = dx.sH();
     p.args.sW = dx.sW();
-    const int TW = 1 << p.args.tw_shift, TH = 128 >> p.args.tw_shift;
-    p.tmA = view_s1(dy, false, BK, TW, TH);
     for (int r = 0; r < k; ++r)
       for (int c = 0; c < k; ++c)
         for (int c0 = 0; c0 < s.CoutS; c0 += BK) {
@@ -228,8 +267,6 @@ IgemmPlan plan_dgrad(const ConvSpec& s, const TensorDesc& dy, const bf16* wt, co
     p.n_classes = 4;
     p.args.sH = 2 * dx.sH();
     p.args.sW = 2 * dx.sW();
-    const int TW = 1 << p.args.tw_shift, TH = 128 >> p.args.tw_shift;
-    p.tmA = view_s1(dy, false, BK, TW, TH);
     for (int a = 0; a < 2; ++a)
       for (int b = 0; b < 2; ++b) {
         const int z = a * 2 + b;
@@ -261,8 +298,7 @@ IgemmPlan plan_dgrad(const ConvSpec& s, const TensorDesc& dy, const bf16* wt, co
     p.n_classes = 1;
     p.args.sH = dx.sH();
     p.args.sW = dx.sW();
-    const int TW = 1 << p.args.tw_shift, TH = 128 >> p.args.tw_shift;
-    p.tmA = view_s2(dy, BK, TW, TH);
+    vk = kViewS2;
     for (int r = 0; r < k; ++r)
       for (int c = 0; c < k; ++c) {
         int hp, hy, wp, wx;
@@ -281,9 +317,7 @@ IgemmPlan plan_dgrad(const ConvSpec& s, const TensorDesc& dy, const bf16* wt, co
     p.args.k_begin[0] = 0;
     p.args.k_count[0] = (int)p.kiters.size();
   }
-  p.BN = choose_bn(s.CinS, BK, (long long)p.num_tiles * p.n_classes, sm_count);
-  p.n_blocks = (padded_rows(s.CinS) + p.BN - 1) / p.BN;
-  p.tmB = make_tmap_2d(wt, padded_rows(s.CinS), Kw, Kw, BK, p.BN, BK * 2);
+  finalize(p, vk, dy, wt, s.CinS, Kw, sm_count);
   const double out_px = s.transposed ? (double)dx.H * dx.W : (double)dy.H * dy.W;
   p.flops = 2.0 * dy.N * out_px * s.Cout * s.Cin * T;
   return p;
@@ -367,7 +401,8 @@ WgradPlan plan_wgrad(const ConvSpec& s, const TensorDesc& x, const TensorDesc& d
 
 void run(const IgemmPlan& p, cudaStream_t stream) {
   CGB_CHECK(p.args.kiters != nullptr, "igemm plan has no device K-iteration table");
-  launch_igemm(p.BN, p.BK, p.tmA, p.tmB, p.args, p.num_tiles, p.n_blocks, p.n_classes, stream);
+  for (int z = 0; z < p.n_classes; ++z) CGB_CHECK(p.args.k_count[z] <= 192, "K-iteration table exceeds the smem staging area");
+  launch_igemm(p.BN, p.BK, p.CM, p.CN, p.tmA, p.tmB, p.args, p.num_tiles, p.n_blocks, p.n_classes, stream);
 }
 
 void run(const WgradPlan& p, cudaStream_t stream) {

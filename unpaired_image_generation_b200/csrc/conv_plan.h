@@ -46,6 +46,7 @@ struct IgemmPlan {
   CUtensorMap tmA, tmB;
   IgemmArgs args;
   int BN = 0, BK = 0, num_tiles = 0, n_blocks = 0, n_classes = 1;
+  int CM = 1, CN = 1;         // thread-block cluster (M tiles x N blocks) sharing operands by TMA multicast
   std::vector<KIter> kiters;  // host copy; args.kiters must point at a device copy
   double flops = 0;           // algorithmic 2*MACs (for roofline accounting)
 };

@@ -28,20 +28,26 @@ struct IgemmCfg {
   static constexpr int kBBytes = (kBBytesTx + 1023) / 1024 * 1024;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = BN < 32 ? 32 : BN;
-  static constexpr int kSmemBytes = STAGES * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kMaxKIters = 192;  // K-iteration table staged in smem (largest layer: 128)
+  static constexpr int kSmemBytes = STAGES * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kMaxKIters * 16;
 };
 
-template <int BN, int BK, int STAGES>
+// CM x CN thread-block cluster: the CN CTAs that share an M tile (same blockIdx.x, consecutive N blocks) each
+// fetch 1/CN of the activation box and multicast it to the others; the CM CTAs that share an N block
+// (consecutive M tiles) do the same with the weight tile.  L2 -> SM operand traffic drops by CN (A) and CM (B).
+template <int BN, int BK, int STAGES, int CM, int CN>
 __global__ void __launch_bounds__(192, 1)
 igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const IgemmArgs args) {
   using Cfg = IgemmCfg<BN, BK, STAGES>;
+  constexpr bool kCluster = (CM * CN) > 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  KIter* s_kiters = reinterpret_cast<KIter*>(smem + STAGES * Cfg::kStageBytes + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -60,12 +66,27 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int n = t / args.tiles_h;
   const int wo0 = tw * TW, ho0 = th * TH;
 
+  // cluster geometry: rank = x + y * CM (x: M-tile direction, y: N-block direction)
+  uint32_t cx = 0, cy = 0;
+  uint16_t a_mask = 1, b_mask = 1, peer_mask = 1;
+  if constexpr (kCluster) {
+    const uint32_t rank = cluster_ctarank();
+    cx = rank % CM;
+    cy = rank / CM;
+    a_mask = 0;
+    b_mask = 0;
+    for (int y = 0; y < CN; ++y) a_mask |= (uint16_t)(1u << (cx + y * CM));  // CTAs sharing my M tile
+    for (int x = 0; x < CM; ++x) b_mask |= (uint16_t)(1u << (x + cy * CM));  // CTAs sharing my N block
+    peer_mask = a_mask | b_mask;
+  }
+  constexpr int kPeers = CM + CN - 1;
+
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], kPeers);  // every CTA that receives my slices must release the slot
     }
     mbar_init(tmem_full_bar, 1);
     fence_mbar_init();
@@ -75,22 +96,42 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (kCluster) cluster_sync_all();  // peers' barriers are initialised before anyone multicasts
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
+    // stage the K-iteration table in shared memory: a dependent global load per iteration in the single
+    // producer thread costs ~0.4 us and was the whole per-iteration time of the first version
+    for (int i = lane; i < kcnt; i += 32) s_kiters[i] = args.kiters[kbeg + i];
+    __syncwarp();
     if (lane == 0) {
       // ===================== TMA producer =====================
+      // A slice: rows [cy * 128/CN, ...) of the 128-pixel tile = SH x SW pixels; B slice: BN/CM weight rows
+      constexpr int kASliceRows = 128 / CN;
+      constexpr int kBSliceRows = BN / CM;
+      const int a_row0 = cy * kASliceRows;
+      const int a_dh = a_row0 >> args.tw_shift, a_dw = a_row0 & (TW - 1);
       for (int i = 0; i < kcnt; ++i) {
         const int s = i % STAGES;
         const uint32_t ph = (i / STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
-        const KIter kt = args.kiters[kbeg + i];
+        const KIter kt = s_kiters[i];
         uint8_t* sa = smem + s * Cfg::kStageBytes;
         uint8_t* sb = sa + Cfg::kABytes;
         mbar_arrive_expect_tx(&full_bar[s], Cfg::kABytes + Cfg::kBBytesTx);
-        tma_load_5d(sa, &tmA, &full_bar[s], kt.a_c, wo0 + kt.a_dx, kt.a_par, ho0 + kt.a_dy, n);
-        tma_load_2d(sb, &tmB, &full_bar[s], kt.b_k, nblk * BN);
+        if constexpr (CN > 1) {
+          tma_load_5d_mc(sa + a_row0 * Cfg::kSwizzle, &tmA, &full_bar[s], kt.a_c, wo0 + a_dw + kt.a_dx, kt.a_par,
+                         ho0 + a_dh + kt.a_dy, n, a_mask);
+        } else {
+          tma_load_5d(sa, &tmA, &full_bar[s], kt.a_c, wo0 + kt.a_dx, kt.a_par, ho0 + kt.a_dy, n);
+        }
+        if constexpr (CM > 1) {
+          tma_load_2d_mc(sb + cx * kBSliceRows * Cfg::kSwizzle, &tmB, &full_bar[s], kt.b_k,
+                         nblk * BN + cx * kBSliceRows, b_mask);
+        } else {
+          tma_load_2d(sb, &tmB, &full_bar[s], kt.b_k, nblk * BN);
+        }
       }
     }
   } else if (warp == 1) {
@@ -111,7 +152,12 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint64_t bd = make_smem_desc(b_addr + k * 32, 0, 8 * Cfg::kSwizzle, lt);
           umma_bf16(tmem_base, ad, bd, idesc, (i | k) != 0 ? 1u : 0u);
         }
-        umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs retire
+        // frees the smem slot once these MMAs retire (in every CTA that feeds this one)
+        if constexpr (kCluster) {
+          umma_commit_mc(&empty_bar[s], peer_mask);
+        } else {
+          umma_commit(&empty_bar[s]);
+        }
       }
       umma_commit(tmem_full_bar);
     }
@@ -121,7 +167,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int row = q * 32 + lane;
     const int ho = ho0 + (row >> args.tw_shift);
     const int wo = wo0 + (row & (TW - 1));
-    const bool valid = (ho < args.Ho) && (wo < args.Wo);
+    const bool valid = (ho < args.Ho) && (wo < args.Wo) && (n < args.N);
     bf16* orow = args.out + args.out_off[cls] + (long long)n * args.sN + (long long)ho * args.sH +
                  (long long)wo * args.sW;
     mbar_wait(tmem_full_bar, 0);
@@ -159,6 +205,41 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
         for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f);
       }
+      if (args.stats != nullptr) {
+        // InstanceNorm statistics of the bf16-rounded outputs, fused: per-column sums over this warp's 32
+        // pixel rows by a transposing butterfly (31 shuffles per quantity), then one atomic per column.
+        float a[CH], b[CH];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+          const float r = valid ? __bfloat162float(__float2bfloat16_rn(v[j])) : 0.f;
+          a[j] = r;
+          b[j] = r * r;
+        }
+#pragma unroll
+        for (int off = CH / 2; off >= 1; off >>= 1) {
+          const bool up = (lane & off) != 0;
+#pragma unroll
+          for (int j = 0; j < off; ++j) {
+            const float sa = up ? a[j] : a[j + off];
+            const float sb = up ? b[j] : b[j + off];
+            const float ka = up ? a[j + off] : a[j];
+            const float kb = up ? b[j + off] : b[j];
+            a[j] = ka + __shfl_xor_sync(0xffffffffu, sa, off);
+            b[j] = kb + __shfl_xor_sync(0xffffffffu, sb, off);
+          }
+        }
+        // lane l now holds column (l mod CH); for CH = 16 lanes l and l + 16 hold halves of the same column
+        if (CH == 16) {
+          a[0] += __shfl_xor_sync(0xffffffffu, a[0], 16);
+          b[0] += __shfl_xor_sync(0xffffffffu, b[0], 16);
+        }
+        const int col = co0 + (lane & (CH - 1));
+        if (n < args.N && col < args.Cout && (CH == 32 || lane < 16)) {
+          float* st = args.stats + ((long long)n * args.Cout + col) * 2;
+          atomicAdd(st, a[0]);
+          atomicAdd(st + 1, b[0]);
+        }
+      }
       if (valid) {
 #pragma unroll
         for (int j = 0; j < CH; j += 8) {
@@ -180,6 +261,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (kCluster) cluster_sync_all();  // no peer may still signal my barriers after I exit
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
@@ -339,39 +421,76 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
 // ------------------------------------------------------------------------------------------
 // Host launchers
 // ------------------------------------------------------------------------------------------
-template <int BN, int BK, int STAGES>
+template <int BN, int BK, int STAGES, int CM, int CN>
 static void launch_igemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmArgs& args, dim3 grid,
                            cudaStream_t stream) {
   using Cfg = IgemmCfg<BN, BK, STAGES>;
   static bool configured = false;
-  auto kern = igemm_conv_kernel<BN, BK, STAGES>;
+  auto kern = igemm_conv_kernel<BN, BK, STAGES, CM, CN>;
   if (!configured) {
     CGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
-  kern<<<grid, 192, Cfg::kSmemBytes, stream>>>(tmA, tmB, args);
+  if (CM * CN == 1) {
+    kern<<<grid, 192, Cfg::kSmemBytes, stream>>>(tmA, tmB, args);
+  } else {
+    grid.x = (grid.x + CM - 1) / CM * CM;  // padded tiles compute masked-out pixels
+    CGB_CHECK(grid.y % CN == 0, "cluster N extent must divide the number of N blocks");
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(192);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CM;
+    attr[0].val.clusterDim.y = CN;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CGB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, args));
+  }
   CGB_CUDA(cudaGetLastError());
 }
 
-void launch_igemm(int BN, int BK, const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmArgs& args,
-                  int num_tiles, int n_blocks, int n_classes, cudaStream_t stream) {
+#ifndef CGB_STAGES64
+#define CGB_STAGES64 4
+#endif
+#ifndef CGB_STAGES128
+#define CGB_STAGES128 4
+#endif
+constexpr int kStages64 = CGB_STAGES64;
+constexpr int kStages128 = CGB_STAGES128;
+
+void launch_igemm(int BN, int BK, int CM, int CN, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                  const IgemmArgs& args, int num_tiles, int n_blocks, int n_classes, cudaStream_t stream) {
   dim3 grid(num_tiles, n_blocks, n_classes);
-  if (BK == 64) {
-    switch (BN) {
-      case 256: return launch_igemm_t<256, 64, 4>(tmA, tmB, args, grid, stream);
-      case 128: return launch_igemm_t<128, 64, 4>(tmA, tmB, args, grid, stream);
-      case 64: return launch_igemm_t<64, 64, 4>(tmA, tmB, args, grid, stream);
-      case 16: return launch_igemm_t<16, 64, 6>(tmA, tmB, args, grid, stream);
-      default: break;
-    }
-  } else if (BK == 16) {
-    switch (BN) {
-      case 64: return launch_igemm_t<64, 16, 8>(tmA, tmB, args, grid, stream);
-      case 16: return launch_igemm_t<16, 16, 8>(tmA, tmB, args, grid, stream);
-      default: break;
-    }
+  const int key = BN * 1000000 + BK * 10000 + CM * 100 + CN;
+  switch (key) {
+    // single-CTA
+    case 256 * 1000000 + 64 * 10000 + 101: return launch_igemm_t<256, 64, 4, 1, 1>(tmA, tmB, args, grid, stream);
+    case 128 * 1000000 + 64 * 10000 + 101: return launch_igemm_t<128, 64, kStages128, 1, 1>(tmA, tmB, args, grid, stream);
+    case 64 * 1000000 + 64 * 10000 + 101: return launch_igemm_t<64, 64, kStages64, 1, 1>(tmA, tmB, args, grid, stream);
+    case 16 * 1000000 + 64 * 10000 + 101: return launch_igemm_t<16, 64, 6, 1, 1>(tmA, tmB, args, grid, stream);
+    case 64 * 1000000 + 16 * 10000 + 101: return launch_igemm_t<64, 16, 8, 1, 1>(tmA, tmB, args, grid, stream);
+    case 16 * 1000000 + 16 * 10000 + 101: return launch_igemm_t<16, 16, 8, 1, 1>(tmA, tmB, args, grid, stream);
+    // clusters with TMA multicast (BK = 64 layers)
+    case 64 * 1000000 + 64 * 10000 + 204: return launch_igemm_t<64, 64, 6, 2, 4>(tmA, tmB, args, grid, stream);
+    case 64 * 1000000 + 64 * 10000 + 104: return launch_igemm_t<64, 64, 6, 1, 4>(tmA, tmB, args, grid, stream);
+    case 64 * 1000000 + 64 * 10000 + 202: return launch_igemm_t<64, 64, 6, 2, 2>(tmA, tmB, args, grid, stream);
+    case 64 * 1000000 + 64 * 10000 + 402: return launch_igemm_t<64, 64, 6, 4, 2>(tmA, tmB, args, grid, stream);
+    case 64 * 1000000 + 64 * 10000 + 401: return launch_igemm_t<64, 64, 6, 4, 1>(tmA, tmB, args, grid, stream);
+    case 64 * 1000000 + 64 * 10000 + 201: return launch_igemm_t<64, 64, 6, 2, 1>(tmA, tmB, args, grid, stream);
+    case 128 * 1000000 + 64 * 10000 + 202: return launch_igemm_t<128, 64, 4, 2, 2>(tmA, tmB, args, grid, stream);
+    case 128 * 1000000 + 64 * 10000 + 402: return launch_igemm_t<128, 64, 4, 4, 2>(tmA, tmB, args, grid, stream);
+    case 128 * 1000000 + 64 * 10000 + 401: return launch_igemm_t<128, 64, 4, 4, 1>(tmA, tmB, args, grid, stream);
+    case 128 * 1000000 + 64 * 10000 + 201: return launch_igemm_t<128, 64, 4, 2, 1>(tmA, tmB, args, grid, stream);
+    case 256 * 1000000 + 64 * 10000 + 201: return launch_igemm_t<256, 64, 4, 2, 1>(tmA, tmB, args, grid, stream);
+    case 256 * 1000000 + 64 * 10000 + 401: return launch_igemm_t<256, 64, 4, 4, 1>(tmA, tmB, args, grid, stream);
+    default: break;
   }
-  CGB_CHECK(false, "launch_igemm: unsupported tile BN=" + std::to_string(BN) + " BK=" + std::to_string(BK));
+  CGB_CHECK(false, "launch_igemm: unsupported config BN=" + std::to_string(BN) + " BK=" + std::to_string(BK) +
+                       " cluster " + std::to_string(CM) + "x" + std::to_string(CN));
 }
 
 template <int BNW, int STAGES>

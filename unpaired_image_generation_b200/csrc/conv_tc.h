@@ -15,8 +15,10 @@ CUtensorMap make_tmap_act5d(const bf16* base, const int dims[5], const long long
 CUtensorMap make_tmap_2d(const bf16* base, long long rows, long long cols, long long pitch_elems, int box_cols,
                          int box_rows, int swizzle_bytes);
 
-void launch_igemm(int BN, int BK, const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmArgs& args,
-                  int num_tiles, int n_blocks, int n_classes, cudaStream_t stream);
+// CM x CN: thread-block cluster (M tiles x N blocks) sharing operands through TMA multicast; 1 x 1 = none.
+void launch_igemm(int BN, int BK, int CM, int CN, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                  const IgemmArgs& args, int num_tiles, int n_blocks, int n_classes, cudaStream_t stream);
+
 
 void launch_wgrad(int BNW, const CUtensorMap& tmDY, const CUtensorMap& tmX, const WgradArgs& args, int m_blocks,
                   cudaStream_t stream);

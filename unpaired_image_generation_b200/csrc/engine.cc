@@ -211,10 +211,12 @@ void cgb_engine::record_programs() {
   double* flops = &conv_flops;
   double dummy_flops = 0;
 
+  // stats != nullptr: InstanceNorm (sum, sumsq) accumulated by the conv epilogue
   auto add_fprop = [E](Program& pr, double* fl, const LayerParam& L, const TensorDesc& x, const TensorDesc& y,
-                       int act) {
+                       int act, float2* stats) {
     const float* bias = L.has_in ? nullptr : E->P[L.group] + L.b_off;
     IgemmPlan p = plan_fprop(L.spec, x, E->pack[L.group] + L.wf_off, y, bias, act, E->sm_count);
+    p.args.stats = reinterpret_cast<float*>(stats);
     p.args.kiters = static_cast<const KIter*>(E->meta_upload(p.kiters.data(), p.kiters.size() * sizeof(KIter)));
     E->igemm_plans.push_back(p);
     const IgemmPlan* pp = &E->igemm_plans.back();
@@ -253,7 +255,7 @@ void cgb_engine::record_programs() {
   };
   auto add_norm = [](Program& pr, const TensorDesc& y, float2* stats, int act, const TensorDesc* residual,
                      const TensorDesc& out) {
-    pr.add([y, stats](cudaStream_t st) { in_stats(y, stats, st); }, 1, kOpNorm);
+    // statistics were accumulated by the producing conv's epilogue
     if (residual) {
       const TensorDesc r = *residual;
       pr.add([y, stats, act, r, out](cudaStream_t st) { in_apply(y, stats, act, &r, out, st); }, 1, kOpNorm);
@@ -284,23 +286,23 @@ void cgb_engine::record_programs() {
     const std::vector<LayerParam>& L = E->layers[net];
     float2* st = P.stats;
     pr.add([st, bytes = P.stats_bytes](cudaStream_t s) { CGB_CUDA(cudaMemsetAsync(st, 0, bytes, s)); }, 0, kOpMemset);
-    add_fprop(pr, fl, L[0], in, P.y_stem, kActNone);
+    add_fprop(pr, fl, L[0], in, P.y_stem, kActNone, st + P.stat_off[0]);
     add_norm(pr, P.y_stem, st + P.stat_off[0], kActRelu, nullptr, P.a_stem);
-    add_fprop(pr, fl, L[1], P.a_stem, P.y_d1, kActNone);
+    add_fprop(pr, fl, L[1], P.a_stem, P.y_d1, kActNone, st + P.stat_off[1]);
     add_norm(pr, P.y_d1, st + P.stat_off[1], kActRelu, nullptr, P.a_d1);
-    add_fprop(pr, fl, L[2], P.a_d1, P.y_d2, kActNone);
+    add_fprop(pr, fl, L[2], P.a_d1, P.y_d2, kActNone, st + P.stat_off[2]);
     add_norm(pr, P.y_d2, st + P.stat_off[2], kActRelu, nullptr, P.xp[0]);
     for (int k = 0; k < nb; ++k) {
-      add_fprop(pr, fl, L[3 + 2 * k], P.xp[k], P.y1[k], kActNone);
+      add_fprop(pr, fl, L[3 + 2 * k], P.xp[k], P.y1[k], kActNone, st + P.stat_off[3 + 2 * k]);
       add_norm(pr, P.y1[k], st + P.stat_off[3 + 2 * k], kActRelu, nullptr, P.bp[k]);
-      add_fprop(pr, fl, L[4 + 2 * k], P.bp[k], P.y2[k], kActNone);
+      add_fprop(pr, fl, L[4 + 2 * k], P.bp[k], P.y2[k], kActNone, st + P.stat_off[4 + 2 * k]);
       add_norm(pr, P.y2[k], st + P.stat_off[4 + 2 * k], kActNone, &P.xp[k], P.xp[k + 1]);
     }
-    add_fprop(pr, fl, L[3 + 2 * nb], P.xp[nb], P.y_u1, kActNone);
+    add_fprop(pr, fl, L[3 + 2 * nb], P.xp[nb], P.y_u1, kActNone, st + P.stat_off[3 + 2 * nb]);
     add_norm(pr, P.y_u1, st + P.stat_off[3 + 2 * nb], kActRelu, nullptr, P.a_u1);
-    add_fprop(pr, fl, L[4 + 2 * nb], P.a_u1, P.y_u2, kActNone);
+    add_fprop(pr, fl, L[4 + 2 * nb], P.a_u1, P.y_u2, kActNone, st + P.stat_off[4 + 2 * nb]);
     add_norm(pr, P.y_u2, st + P.stat_off[4 + 2 * nb], kActRelu, nullptr, P.a_u2p);
-    add_fprop(pr, fl, L[5 + 2 * nb], P.a_u2p, out, kActTanh);
+    add_fprop(pr, fl, L[5 + 2 * nb], P.a_u2p, out, kActTanh, nullptr);
     if (fill_out_halo) pr.add([out](cudaStream_t s) { fill_reflect_halo(out, s); });
   };
 
@@ -387,14 +389,14 @@ void cgb_engine::record_programs() {
     const std::vector<LayerParam>& L = E->layers[net];
     float2* st = D.stats;
     pr.add([st, bytes = D.stats_bytes](cudaStream_t s) { CGB_CUDA(cudaMemsetAsync(st, 0, bytes, s)); }, 0, kOpMemset);
-    add_fprop(pr, fl, L[0], in, D.l0, kActLeaky);
-    add_fprop(pr, fl, L[1], D.l0, D.y1, kActNone);
+    add_fprop(pr, fl, L[0], in, D.l0, kActLeaky, nullptr);
+    add_fprop(pr, fl, L[1], D.l0, D.y1, kActNone, st + D.stat_off[0]);
     add_norm(pr, D.y1, st + D.stat_off[0], kActLeaky, nullptr, D.a1);
-    add_fprop(pr, fl, L[2], D.a1, D.y2, kActNone);
+    add_fprop(pr, fl, L[2], D.a1, D.y2, kActNone, st + D.stat_off[1]);
     add_norm(pr, D.y2, st + D.stat_off[1], kActLeaky, nullptr, D.a2);
-    add_fprop(pr, fl, L[3], D.a2, D.y3, kActNone);
+    add_fprop(pr, fl, L[3], D.a2, D.y3, kActNone, st + D.stat_off[2]);
     add_norm(pr, D.y3, st + D.stat_off[2], kActLeaky, nullptr, D.a3);
-    add_fprop(pr, fl, L[4], D.a3, D.logits, kActNone);
+    add_fprop(pr, fl, L[4], D.a3, D.logits, kActNone, nullptr);
   };
   auto emit_dis_backward = [&](Program& pr, double* fl, DisPass& D, DisScratch& S, float target, float w,
                                int loss_slot, bool weight_grads, const TensorDesc* dx_img_out) {

@@ -652,7 +652,9 @@ void in_bwd_reduce(const TensorDesc& y, const float2* stats, const GradSrc& g, i
                    float2* bstats, cudaStream_t st) {
   check_grad(y, g);
   const int HW = y.H * y.W;
-  const int ppb = pick_pix_per_block(HW);
+  // two pixels per thread: enough CTAs to cover the latency of the gather even at batch 1
+  const int lanes = std::min(256, y.C / 8);
+  const int ppb = std::max(2 * (256 / lanes), 8);
   dim3 grid((HW + ppb - 1) / ppb, y.N);
   in_bwd_reduce_kernel<<<grid, 256, 0, st>>>(dev(y), stats, dev(g), act, da_out ? dev(*da_out) : dev_null(),
                                              reinterpret_cast<float*>(bstats), ppb);

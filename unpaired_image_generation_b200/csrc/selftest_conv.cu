@@ -245,15 +245,10 @@ static int run_case(const std::string& name, ConvSpec s, int N, int H, int W, in
 
   if (passes & 1) {
     IgemmPlan p = plan_fprop(s, x, d_wf, y, d_bias, act, sm_count);
-    if (force_bn) {
-      p.BN = force_bn;
-      p.n_blocks = (padded_rows(s.CoutS) + p.BN - 1) / p.BN;
-      p.tmB = make_tmap_2d(d_wf, padded_rows(s.CoutS), (long long)T * s.CinS, (long long)T * s.CinS, p.BK, p.BN,
-                           p.BK * 2);
-    }
+    (void)force_bn;
     p.args.kiters = dev_upload(p.kiters);
-    printf("  fprop: BN=%d BK=%d tiles=%d nblk=%d classes=%d kiters=%zu\n", p.BN, p.BK, p.num_tiles, p.n_blocks,
-           p.n_classes, p.kiters.size());
+    printf("  fprop: BN=%d BK=%d cluster %dx%d tiles=%d nblk=%d classes=%d kiters=%zu\n", p.BN, p.BK, p.CM, p.CN,
+           p.num_tiles, p.n_blocks, p.n_classes, p.kiters.size());
     run(p, 0);
     CGB_CUDA(cudaDeviceSynchronize());
     std::vector<bf16> yb((size_t)y.elems());
@@ -296,8 +291,8 @@ static int run_case(const std::string& name, ConvSpec s, int N, int H, int W, in
     CGB_CUDA(cudaMemset(dx.ptr, 0xFF, dx.elems() * sizeof(bf16)));
     IgemmPlan p = plan_dgrad(s, dy, d_wt, dx, sm_count);
     p.args.kiters = dev_upload(p.kiters);
-    printf("  dgrad: BN=%d BK=%d tiles=%d nblk=%d classes=%d kiters=%zu out %dx%d\n", p.BN, p.BK, p.num_tiles,
-           p.n_blocks, p.n_classes, p.kiters.size(), DH, DW);
+    printf("  dgrad: BN=%d BK=%d cluster %dx%d tiles=%d nblk=%d classes=%d kiters=%zu out %dx%d\n", p.BN, p.BK, p.CM,
+           p.CN, p.num_tiles, p.n_blocks, p.n_classes, p.kiters.size(), DH, DW);
     run(p, 0);
     CGB_CUDA(cudaDeviceSynchronize());
     std::vector<bf16> db((size_t)dx.elems());
