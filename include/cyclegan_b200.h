@@ -96,6 +96,14 @@ int cgb_phase_discriminators(cgb_engine_t* e, void* stream);
 int cgb_adam(cgb_engine_t* e, int group, void* stream);
 /* whole step on one stream, replayed from a CUDA graph after the first call */
 int cgb_train_step(cgb_engine_t* e, void* stream);
+/* copies fp32 NCHW inputs (device or pinned host) into the engine's staging buffers, nothing else */
+int cgb_stage_inputs(cgb_engine_t* e, const float* real_A, const float* real_B, void* stream);
+/* graph-replayed segments of the step, for callers that interleave their own collectives (data parallel):
+ * CGB_SEG_STEP = whole step; CGB_SEG_G = staged inputs -> images, six forwards, G-phase backward;
+ * CGB_SEG_D = D-phase forward/backward; CGB_SEG_ADAM_G / CGB_SEG_ADAM_D = optimiser + bf16 weight refresh.
+ * First call of a segment runs eagerly, the second captures it (independent passes on parallel branches). */
+enum { CGB_SEG_STEP = 0, CGB_SEG_G = 1, CGB_SEG_D = 2, CGB_SEG_ADAM_G = 3, CGB_SEG_ADAM_D = 4, CGB_NUM_SEGMENTS = 5 };
+int cgb_run_segment(cgb_engine_t* e, int segment, void* stream);
 /* copies the CGB_NUM_LOSSES loss values to host memory (synchronises the stream) */
 int cgb_get_losses_host(cgb_engine_t* e, float* losses_host, void* stream);
 /* end-to-end convenience: pinned/pageable HOST inputs in, losses out (H2D + step + D2H, synchronous) */

@@ -48,6 +48,8 @@ SIGNATURES = {
     "cgb_phase_discriminators": (c_int, [_P, _P]),
     "cgb_adam": (c_int, [_P, c_int, _P]),
     "cgb_train_step": (c_int, [_P, _P]),
+    "cgb_stage_inputs": (c_int, [_P, _P, _P, _P]),
+    "cgb_run_segment": (c_int, [_P, c_int, _P]),
     "cgb_get_losses_host": (c_int, [_P, POINTER(c_float), _P]),
     "cgb_train_step_host": (c_int, [_P, _P, _P, POINTER(c_float), _P]),
     "cgb_launches_per_step": (c_longlong, [_P]),

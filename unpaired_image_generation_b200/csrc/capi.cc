@@ -117,10 +117,7 @@ int cgb_refresh_weights(cgb_engine_t* e, int group, void* stream) {
 int cgb_set_grad_scale(cgb_engine_t* e, float scale) {
   if (!e) return 1;
   e->grad_scale = scale;
-  if (e->graph) {  // the scale is a baked kernel argument: re-capture
-    cudaGraphExecDestroy(e->graph);
-    e->graph = nullptr;
-  }
+  e->drop_graphs();  // the scale is a baked kernel argument: re-capture
   return 0;
 }
 
@@ -195,64 +192,26 @@ int cgb_adam(cgb_engine_t* e, int group, void* stream) {
   CGB_API_END
 }
 
-static void run_step_eager(cgb_engine* e, cudaStream_t st) {
-  e->prog_set_inputs.run(st);
-  e->prog_cycle.run(st);
-  e->prog_G.run(st);
-  e->prog_adam[0].run(st);
-  e->prog_D.run(st);
-  e->prog_adam[1].run(st);
-}
-
-// same step with the lanes mapped to distinct streams (used under stream capture)
-static void run_step_lanes(cgb_engine* e, cudaStream_t st) {
-  e->lane_streams[0] = st;
-  for (int l = 1; l < kLanes; ++l)
-    if (!e->lane_streams[l]) CGB_CUDA(cudaStreamCreateWithFlags(&e->lane_streams[l], cudaStreamNonBlocking));
-  size_t next_event = 0;
-  const Program* seq[6] = {&e->prog_set_inputs, &e->prog_cycle, &e->prog_G, &e->prog_adam[0], &e->prog_D, &e->prog_adam[1]};
-  for (const Program* p : seq) p->run_lanes(e->lane_streams, e->events, &next_event);
-}
-
 int cgb_train_step(cgb_engine_t* e, void* stream) {
   CGB_API_BEGIN
   CGB_CHECK(e && e->bound, "engine not bound");
-  cudaStream_t st = S(stream);
-  static const bool no_graph = std::getenv("CGB_NO_GRAPH") != nullptr;
-  // first call runs eagerly (configures kernel attributes, validates); the second call captures the
-  // step into a CUDA graph (independent passes on parallel branches) that later calls replay.
-  // The legacy default stream cannot be captured.
-  const bool can_graph = !no_graph && st != nullptr && !e->graph_failed;
-  if (can_graph && e->graph == nullptr && e->step_calls >= 1) {
-    cudaGraph_t g = nullptr;
-    cudaError_t err = cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed);
-    if (err == cudaSuccess) {
-      try {
-        run_step_lanes(e, st);
-      } catch (...) {
-        cudaStreamEndCapture(st, &g);
-        if (g) cudaGraphDestroy(g);
-        e->graph_failed = true;
-        throw;
-      }
-      err = cudaStreamEndCapture(st, &g);
-      if (err == cudaSuccess) err = cudaGraphInstantiate(&e->graph, g, 0);
-      if (g) cudaGraphDestroy(g);
-    }
-    if (err != cudaSuccess) {
-      e->graph = nullptr;
-      e->graph_failed = true;
-      cgb::set_last_error(std::string("CUDA graph capture failed: ") + cudaGetErrorString(err));
-      cudaGetLastError();
-      if (std::getenv("CGB_REQUIRE_GRAPH")) throw cgb::Error(cgb_last_error());
-    }
-  }
-  ++e->step_calls;
-  if (e->graph) {
-    CGB_CUDA(cudaGraphLaunch(e->graph, st));
-  } else {
-    run_step_eager(e, st);
-  }
+  e->run_segment(CGB_SEG_STEP, S(stream));
+  CGB_API_END
+}
+
+int cgb_run_segment(cgb_engine_t* e, int segment, void* stream) {
+  CGB_API_BEGIN
+  CGB_CHECK(e && e->bound && segment >= 0 && segment < CGB_NUM_SEGMENTS, "bad argument / engine not bound");
+  e->run_segment(segment, S(stream));
+  CGB_API_END
+}
+
+int cgb_stage_inputs(cgb_engine_t* e, const float* real_A, const float* real_B, void* stream) {
+  CGB_API_BEGIN
+  CGB_CHECK(e && e->bound && real_A && real_B, "bad argument / engine not bound");
+  const size_t bytes = (size_t)e->cfg.batch * 3 * e->cfg.size * e->cfg.size * sizeof(float);
+  CGB_CUDA(cudaMemcpyAsync(e->staging[0], real_A, bytes, cudaMemcpyDefault, S(stream)));
+  CGB_CUDA(cudaMemcpyAsync(e->staging[1], real_B, bytes, cudaMemcpyDefault, S(stream)));
   CGB_API_END
 }
 

@@ -28,8 +28,10 @@ long long align_up(long long v, long long a) { return (v + a - 1) / a * a; }
 }  // namespace
 
 cgb_engine::~cgb_engine() {
-  if (graph) cudaGraphExecDestroy(graph);
+  drop_graphs();
   for (cudaEvent_t ev : events) cudaEventDestroy(ev);
+  for (auto& v : seg_events)
+    for (cudaEvent_t ev : v) cudaEventDestroy(ev);
   for (int l = 1; l < kLanes; ++l)
     if (lane_streams[l]) cudaStreamDestroy(lane_streams[l]);
   if (meta) cudaFree(meta);
@@ -191,6 +193,58 @@ void cgb_engine::layout(Arena& A) {
     d.colbuf = static_cast<bf16*>(A.alloc(d.colbuf_elems * sizeof(bf16)));
   }
   A.alloc(1024);  // tail guard
+}
+
+void cgb_engine::drop_graphs() {
+  for (Segment& s : segments) {
+    if (s.exec) cudaGraphExecDestroy(s.exec);
+    s.exec = nullptr;
+  }
+}
+
+// First call: eager on `st` (configures kernel attributes, validates).  Second call: stream-capture the
+// sequence with the lanes mapped to distinct streams, instantiate, launch.  Later calls: replay.
+// The legacy default stream cannot be captured (eager then).
+void cgb_engine::run_segment(int seg, cudaStream_t st) {
+  Segment& S = segments[seg];
+  static const bool no_graph = std::getenv("CGB_NO_GRAPH") != nullptr;
+  const bool can_graph = !no_graph && st != nullptr && !S.failed;
+  if (can_graph && S.exec == nullptr && S.calls >= 1) {
+    lane_streams[0] = st;
+    for (int l = 1; l < kLanes; ++l)
+      if (!lane_streams[l]) CGB_CUDA(cudaStreamCreateWithFlags(&lane_streams[l], cudaStreamNonBlocking));
+    cudaGraph_t g = nullptr;
+    cudaError_t err = cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed);
+    if (err == cudaSuccess) {
+      try {
+        size_t next_event = 0;
+        std::vector<cudaEvent_t>& evs = seg_events[seg];
+        for (const Program* p : S.seq) p->run_lanes(lane_streams, evs, &next_event);
+      } catch (...) {
+        cudaStreamEndCapture(st, &g);
+        if (g) cudaGraphDestroy(g);
+        S.failed = true;
+        throw;
+      }
+      err = cudaStreamEndCapture(st, &g);
+      if (err == cudaSuccess) err = cudaGraphInstantiate(&S.exec, g, 0);
+      if (g) cudaGraphDestroy(g);
+    }
+    if (err != cudaSuccess) {
+      S.exec = nullptr;
+      S.failed = true;
+      cudaGetLastError();
+      const std::string msg = std::string("CUDA graph capture failed: ") + cudaGetErrorString(err);
+      set_last_error(msg);
+      if (std::getenv("CGB_REQUIRE_GRAPH")) throw Error(msg);
+    }
+  }
+  ++S.calls;
+  if (S.exec) {
+    CGB_CUDA(cudaGraphLaunch(S.exec, st));
+  } else {
+    for (const Program* p : S.seq) p->run(st);
+  }
 }
 
 void* cgb_engine::meta_upload(const void* src, size_t bytes) {
@@ -573,6 +627,11 @@ void cgb_engine::record_programs() {
         2);
     prog_adam[g].add([p, tb, cnt, mx, arena](cudaStream_t s) { pack_weights(p, tb, cnt, mx, arena, s); });
   }
+  segments[CGB_SEG_STEP].seq = {&prog_set_inputs, &prog_cycle, &prog_G, &prog_adam[0], &prog_D, &prog_adam[1]};
+  segments[CGB_SEG_G].seq = {&prog_set_inputs, &prog_cycle, &prog_G};
+  segments[CGB_SEG_D].seq = {&prog_D};
+  segments[CGB_SEG_ADAM_G].seq = {&prog_adam[0]};
+  segments[CGB_SEG_ADAM_D].seq = {&prog_adam[1]};
   // ---- module-level forward programs (Generator.forward / Discriminator.forward)
   for (int net = 0; net < 2; ++net) {
     emit_gen_forward(prog_mod_gen[net], &dummy_flops, gen[6], net, mod_in, mod_out, false);

@@ -193,9 +193,16 @@ struct cgb_engine {
 
   cudaStream_t lane_streams[cgb::kLanes] = {nullptr, nullptr, nullptr, nullptr};  // [0] = caller's stream
   std::vector<cudaEvent_t> events;
-  cudaGraphExec_t graph = nullptr;
-  bool graph_failed = false;
-  int step_calls = 0;
+  std::vector<cudaEvent_t> seg_events[CGB_NUM_SEGMENTS];
+  struct Segment {  // a graph-replayable sequence of programs
+    std::vector<const cgb::Program*> seq;
+    cudaGraphExec_t exec = nullptr;
+    bool failed = false;
+    int calls = 0;
+  };
+  Segment segments[CGB_NUM_SEGMENTS];
+  void run_segment(int seg, cudaStream_t st);
+  void drop_graphs();
 
   ~cgb_engine();
   void build_inventory();

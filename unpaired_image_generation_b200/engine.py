@@ -162,6 +162,16 @@ class StepEngine:
         _lib.check(self.lib.cgb_set_inputs(self._h, _ptr(a), _ptr(b), _stream()))
         self._keep = (a, b)  # keep alive until the async copies ran
 
+    def stage_inputs(self, real_A: torch.Tensor, real_B: torch.Tensor):
+        """copy the inputs into the engine's staging buffers (the graph segments read them from there)"""
+        a, b = self._check_img(real_A), self._check_img(real_B)
+        _lib.check(self.lib.cgb_stage_inputs(self._h, _ptr(a), _ptr(b), _stream()))
+        self._keep = (a, b)
+
+    def run_segment(self, segment: int):
+        """graph-replayed part of the step: 0 whole step, 1 G phase (incl. forwards), 2 D phase, 3/4 Adam G/D"""
+        _lib.check(self.lib.cgb_run_segment(self._h, segment, _stream()))
+
     def forward_cycle(self):
         _lib.check(self.lib.cgb_forward_cycle(self._h, _stream()))
 

@@ -107,21 +107,21 @@ class CycleGANTrainer:
         main.wait_stream(torch.cuda.current_stream())
         ev_G, ev_D, ev_done = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
         with torch.cuda.stream(main):
-            eng.set_inputs(real_A, real_B)
-            eng.phase_generators()
+            eng.stage_inputs(real_A, real_B)
+            eng.run_segment(1)  # images, six forwards, G-phase backward (one CUDA graph)
             ev_G.record(main)
         with torch.cuda.stream(comm):
             comm.wait_event(ev_G)
             self.sync.all_reduce_(eng.grads[0])
-            eng.adam(0)
+            eng.run_segment(3)  # Adam(G) * 1/world + bf16 weight refresh
         with torch.cuda.stream(main):
             # needs only D weights and the pre-update fakes: overlaps the generator all-reduce + Adam
-            eng.phase_discriminators()
+            eng.run_segment(2)
             ev_D.record(main)
         with torch.cuda.stream(comm):
             comm.wait_event(ev_D)
             self.sync.all_reduce_(eng.grads[1])
-            eng.adam(1)
+            eng.run_segment(4)
             ev_done.record(comm)
         main.wait_event(ev_done)
 
