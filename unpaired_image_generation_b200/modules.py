@@ -1,4 +1,4 @@
-"""Generator / Discriminator with the stand-in's module API (oracle/cyclegan_standin.py:118,165):
+"""Generator / Discriminator with the stand-in's module API (oracle/cyclegan_standin.py:129,172):
 `forward(x)`, `state_dict()`, `load_state_dict()`, `named_parameters()`, `parameters()`.
 Parameters are fp32 torch tensors; once a module is attached to a step engine they become views of
 the engine's flat parameter buffer, so training is visible through `state_dict()`.
