@@ -228,6 +228,18 @@ def run_b200(args):
             ms_wg, n_wg, fl_wg = eng.profile_kind(2, reps=5)
             ms_wd, n_wd, fl_wd = eng.profile_kind(3, reps=3)
             ms_pw, n_pw, _ = eng.profile_kind(4, reps=5)
+            # graph-replayed segments timed separately (forward only / whole G phase / D phase / optimisers)
+            seg_ms = {}
+            for name, seg in (("forward_6_generators", 5), ("G_phase_incl_forward", 1), ("D_phase", 2), ("adam_G", 3), ("adam_D", 4)):
+                for _ in range(3):
+                    eng.run_segment(seg)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(tr.stream)
+                for _ in range(5):
+                    eng.run_segment(seg)
+                e1.record(tr.stream)
+                torch.cuda.synchronize()
+                seg_ms[name] = e0.elapsed_time(e1) / 5
         achieved = fl_ig / (ms_ig * 1e-3) / 1e12
         roofline = {
             "bound": "tensor", "kernel": "igemm_conv_kernel (tcgen05 implicit-GEMM conv fprop/dgrad, all layer shapes)",
@@ -241,6 +253,7 @@ def run_b200(args):
                                                    "tflops": fl_wd / (ms_wd * 1e-3) / 1e12 if ms_wd > 0 else None},
                 "instnorm_pointwise": {"ms_per_step": ms_pw, "launches": n_pw},
             },
+            "segments_ms": seg_ms,
             "step_conv_tflops": eng.conv_flops_per_step / (ms_step * 1e-3) / 1e12,
             "step_conv_frac_of_peak": eng.conv_flops_per_step / (ms_step * 1e-3) / 1e12 / peaks["tf_sustained"],
         }

@@ -102,7 +102,8 @@ int cgb_stage_inputs(cgb_engine_t* e, const float* real_A, const float* real_B, 
  * CGB_SEG_STEP = whole step; CGB_SEG_G = staged inputs -> images, six forwards, G-phase backward;
  * CGB_SEG_D = D-phase forward/backward; CGB_SEG_ADAM_G / CGB_SEG_ADAM_D = optimiser + bf16 weight refresh.
  * First call of a segment runs eagerly, the second captures it (independent passes on parallel branches). */
-enum { CGB_SEG_STEP = 0, CGB_SEG_G = 1, CGB_SEG_D = 2, CGB_SEG_ADAM_G = 3, CGB_SEG_ADAM_D = 4, CGB_NUM_SEGMENTS = 5 };
+enum { CGB_SEG_STEP = 0, CGB_SEG_G = 1, CGB_SEG_D = 2, CGB_SEG_ADAM_G = 3, CGB_SEG_ADAM_D = 4,
+       CGB_SEG_FORWARD = 5 /* staged inputs -> images + the six generator forwards */, CGB_NUM_SEGMENTS = 6 };
 int cgb_run_segment(cgb_engine_t* e, int segment, void* stream);
 /* copies the CGB_NUM_LOSSES loss values to host memory (synchronises the stream) */
 int cgb_get_losses_host(cgb_engine_t* e, float* losses_host, void* stream);
@@ -121,6 +122,10 @@ double cgb_conv_flops_per_step(const cgb_engine_t* e);    /* algorithmic 2*MACs 
  * FLOPs per step-equivalent.  Synchronises the stream. */
 int cgb_profile_kind(cgb_engine_t* e, int kind, int reps, void* stream, float* ms_per_step, long long* launches,
                      double* flops);
+
+/* Development profiling: replays the whole step as a CUDA graph with event-record nodes at the pass boundaries and
+ * writes "label lane ms" lines (time since the step began) into buf.  Synchronises the stream. */
+int cgb_profile_timeline(cgb_engine_t* e, void* stream, char* buf, int buf_cap);
 
 /* ---- single-layer harness used by the parity tests (allocates its own scratch with cudaMalloc) -------------- */
 /* Runs fprop (+bias, +act), and when dy != NULL also dgrad and wgrad, of one layer through the same plans the

@@ -55,6 +55,7 @@ SIGNATURES = {
     "cgb_launches_per_step": (c_longlong, [_P]),
     "cgb_conv_flops_per_step": (c_double, [_P]),
     "cgb_profile_kind": (c_int, [_P, c_int, c_int, _P, POINTER(c_float), POINTER(c_longlong), POINTER(c_double)]),
+    "cgb_profile_timeline": (c_int, [_P, _P, c_char_p, c_int]),
     "cgb_conv_layer_test": (c_int, [c_int] * 11 + [_P] * 8),
     "cgb_instnorm_test": (c_int, [c_int] * 5 + [_P] * 5),
 }

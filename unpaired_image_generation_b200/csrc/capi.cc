@@ -272,6 +272,15 @@ int cgb_profile_kind(cgb_engine_t* e, int kind, int reps, void* stream, float* m
   CGB_API_END
 }
 
+int cgb_profile_timeline(cgb_engine_t* e, void* stream, char* buf, int buf_cap) {
+  CGB_API_BEGIN
+  CGB_CHECK(e && e->bound && buf && buf_cap > 0, "bad argument / engine not bound");
+  const std::string t = e->timeline(S(stream));
+  std::strncpy(buf, t.c_str(), buf_cap - 1);
+  buf[buf_cap - 1] = 0;
+  CGB_API_END
+}
+
 double cgb_conv_flops_per_step(const cgb_engine_t* e) { return (e && e->bound) ? e->conv_flops : -1.0; }
 
 // ------------------------------------------------------------------------------------------------

@@ -67,6 +67,7 @@ struct IgemmArgs {
   int bias_n;                      // number of valid bias entries
   int act;                         // 0 none, 1 LeakyReLU(0.2), 2 tanh
   float* stats;                    // optional [N][Cout][2] fp32 (sum, sumsq) accumulated with atomics
+  long long* prof;                 // optional [ctas][8] clock64 timestamps (development profiling)
 };
 
 // One filter tap of the weight-gradient GEMM: offsets for both operands.

@@ -54,10 +54,15 @@ static int choose_bn(int rows, int bk, long long ctas_per_nblock, int sm_count) 
     const int bn = std::atoi(f);
     if ((bn == 64 || bn == 128 || bn == 256) && rows % bn == 0) return bn;
   }
+  // The widest N tile that still yields `target` CTAs.  Wide tiles cost the least SM time per FLOP (the MMA
+  // issue loop is paid per K block regardless of N), and the step graph keeps several independent convs in
+  // flight, so the target is a fraction of the machine rather than all of it.
+  static const double frac = std::getenv("CGB_CTA_FRAC") ? std::atof(std::getenv("CGB_CTA_FRAC")) : 0.55;
+  const long long target = (long long)(sm_count * frac);
   const int cands[3] = {256, 128, 64};
   for (int bn : cands) {
     if (rows % bn != 0) continue;
-    if (ctas_per_nblock * (rows / bn) >= (long long)(sm_count * 0.85)) return bn;
+    if (ctas_per_nblock * (rows / bn) >= target) return bn;
   }
   return 64;
 }
@@ -76,8 +81,9 @@ static void choose_cluster(int BN, int BK, int n_blocks, int num_tiles, int* CM,
   if (BN == 64) cn = n_blocks % 4 == 0 ? 4 : (n_blocks % 2 == 0 ? 2 : 1);
   else if (BN == 128) cn = n_blocks % 2 == 0 ? 2 : 1;
   int cm = cn == 4 ? 2 : 4;
-  while (cm > 1 && num_tiles < 2 * cm) cm /= 2;
-  if (cm == 1 && cn > 1) return;  // (1 x CN) is only instantiated for BN = 64, CN = 4
+  if (num_tiles < 2 * cm) return;
+  // instantiated: BN 64: 2x4, 4x2, 4x1; BN 128: 4x2, 4x1; BN 256: 4x1
+  if (BN == 256) cn = 1;
   *CM = cm;
   *CN = cn;
 }
@@ -392,7 +398,10 @@ WgradPlan plan_wgrad(const ConvSpec& s, const TensorDesc& x, const TensorDesc& d
   p.args.num_taps = (int)p.taps.size();
   const long long total_chunks = (long long)p.args.N * p.args.tiles_w * p.args.tiles_h;
   const long long base_ctas = (long long)p.m_blocks * ((s.CinS + p.BNW - 1) / p.BNW) * T;
-  long long split = sm_count / base_ctas;  // aim at one full wave
+  // split-K so that the launch has about `frac` of a wave of CTAs: long K per CTA amortises the prologue and
+  // the fp32 reduction epilogue, and leaves room for the other lanes of the step graph
+  static const double frac = std::getenv("CGB_CTA_FRAC") ? std::atof(std::getenv("CGB_CTA_FRAC")) : 0.85;
+  long long split = (long long)(sm_count * frac) / base_ctas;
   split = std::max(1LL, std::min(split, std::max(1LL, total_chunks / 4)));
   p.args.split_k = (int)split;
   p.flops = 2.0 * x.N * (double)PH * PW * s.Cout * s.Cin * T;

@@ -20,26 +20,33 @@ namespace cgb {
 
 using namespace ptx;
 
-template <int BN, int BK, int STAGES>
+// KPS = K iterations (tap x channel-chunk boxes) carried by one pipeline stage: one full/empty barrier round
+// trip and one tcgen05.commit per stage instead of per K iteration (the round trip costs ~350 cycles, which
+// dominates narrow tiles and the 49-tap 7x7 layers).
+template <int BN, int BK, int STAGES, int KPS>
 struct IgemmCfg {
   static constexpr int kSwizzle = BK * 2;  // bytes per smem row == swizzle span
   static constexpr int kABytes = 128 * kSwizzle;
   static constexpr int kBBytesTx = BN * kSwizzle;
   static constexpr int kBBytes = (kBBytesTx + 1023) / 1024 * 1024;
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kSubBytes = kABytes + kBBytes;  // one K iteration
+  static constexpr int kStageBytes = KPS * kSubBytes;
   static constexpr int kTmemCols = BN < 32 ? 32 : BN;
   static constexpr int kMaxKIters = 192;  // K-iteration table staged in smem (largest layer: 128)
-  static constexpr int kSmemBytes = STAGES * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kMaxKIters * 16;
+  static constexpr int kSmemBytes =
+      STAGES * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kMaxKIters * 16 + 1024 /*bias*/;
+  static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
+  static_assert(STAGES * kStageBytes >= 128 * BN * 2 || BN < 64, "epilogue staging does not fit");
 };
 
 // CM x CN thread-block cluster: the CN CTAs that share an M tile (same blockIdx.x, consecutive N blocks) each
 // fetch 1/CN of the activation box and multicast it to the others; the CM CTAs that share an N block
 // (consecutive M tiles) do the same with the weight tile.  L2 -> SM operand traffic drops by CN (A) and CM (B).
-template <int BN, int BK, int STAGES, int CM, int CN>
+template <int BN, int BK, int STAGES, int KPS, int CM, int CN>
 __global__ void __launch_bounds__(192, 1)
 igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const IgemmArgs args) {
-  using Cfg = IgemmCfg<BN, BK, STAGES>;
+  using Cfg = IgemmCfg<BN, BK, STAGES, KPS>;
   constexpr bool kCluster = (CM * CN) > 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -48,11 +55,14 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
   KIter* s_kiters = reinterpret_cast<KIter*>(smem + STAGES * Cfg::kStageBytes + 256);
+  float* s_bias = reinterpret_cast<float*>(smem + STAGES * Cfg::kStageBytes + 256 + Cfg::kMaxKIters * 16);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int cls = blockIdx.z;
   const int nblk = blockIdx.y;
+  long long* prof = args.prof ? args.prof + 16 * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) : nullptr;
+  if (prof && threadIdx.x == 0) prof[0] = clock64();
   const int kbeg = args.k_begin[cls];
   const int kcnt = args.k_count[cls];
 
@@ -99,58 +109,74 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if constexpr (kCluster) cluster_sync_all();  // peers' barriers are initialised before anyone multicasts
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  if (prof && threadIdx.x == 0) prof[1] = clock64();
 
   if (warp == 0) {
-    // stage the K-iteration table in shared memory: a dependent global load per iteration in the single
-    // producer thread costs ~0.4 us and was the whole per-iteration time of the first version
+    // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
     for (int i = lane; i < kcnt; i += 32) s_kiters[i] = args.kiters[kbeg + i];
     __syncwarp();
-    if (lane == 0) {
-      // ===================== TMA producer =====================
-      // A slice: rows [cy * 128/CN, ...) of the 128-pixel tile = SH x SW pixels; B slice: BN/CM weight rows
-      constexpr int kASliceRows = 128 / CN;
-      constexpr int kBSliceRows = BN / CM;
-      const int a_row0 = cy * kASliceRows;
-      const int a_dh = a_row0 >> args.tw_shift, a_dw = a_row0 & (TW - 1);
-      for (int i = 0; i < kcnt; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        const KIter kt = s_kiters[i];
-        uint8_t* sa = smem + s * Cfg::kStageBytes;
-        uint8_t* sb = sa + Cfg::kABytes;
-        mbar_arrive_expect_tx(&full_bar[s], Cfg::kABytes + Cfg::kBBytesTx);
-        if constexpr (CN > 1) {
-          tma_load_5d_mc(sa + a_row0 * Cfg::kSwizzle, &tmA, &full_bar[s], kt.a_c, wo0 + a_dw + kt.a_dx, kt.a_par,
-                         ho0 + a_dh + kt.a_dy, n, a_mask);
-        } else {
-          tma_load_5d(sa, &tmA, &full_bar[s], kt.a_c, wo0 + kt.a_dx, kt.a_par, ho0 + kt.a_dy, n);
-        }
-        if constexpr (CM > 1) {
-          tma_load_2d_mc(sb + cx * kBSliceRows * Cfg::kSwizzle, &tmB, &full_bar[s], kt.b_k,
-                         nblk * BN + cx * kBSliceRows, b_mask);
-        } else {
-          tma_load_2d(sb, &tmB, &full_bar[s], kt.b_k, nblk * BN);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN < 16 ? 16 : BN, 0, 0);
-      constexpr uint32_t lt = swizzle_layout_type(Cfg::kSwizzle);
-      for (int i = 0; i < kcnt; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
-        const uint32_t b_addr = a_addr + Cfg::kABytes;
+    // A slice: rows [cy * 128/CN, ...) of the 128-pixel tile = SH x SW pixels; B slice: BN/CM weight rows
+    constexpr int kASliceRows = 128 / CN;
+    constexpr int kBSliceRows = BN / CM;
+    const int a_row0 = cy * kASliceRows;
+    const int a_dh = a_row0 >> args.tw_shift, a_dw = a_row0 & (TW - 1);
+    const int nstages = (kcnt + KPS - 1) / KPS;
+    for (int i = 0; i < nstages; ++i) {
+      const int s = i % STAGES;
+      const uint32_t ph = (i / STAGES) & 1;
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      if (elect_one()) {
+        const int nk = min(KPS, kcnt - i * KPS);
+        mbar_arrive_expect_tx(&full_bar[s], nk * (Cfg::kABytes + Cfg::kBBytesTx));
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          const uint64_t ad = make_smem_desc(a_addr + k * 32, 0, 8 * Cfg::kSwizzle, lt);
-          const uint64_t bd = make_smem_desc(b_addr + k * 32, 0, 8 * Cfg::kSwizzle, lt);
-          umma_bf16(tmem_base, ad, bd, idesc, (i | k) != 0 ? 1u : 0u);
+        for (int j = 0; j < KPS; ++j) {
+          if (j < nk) {
+            const KIter kt = s_kiters[i * KPS + j];
+            uint8_t* sa = smem + s * Cfg::kStageBytes + j * Cfg::kSubBytes;
+            uint8_t* sb = sa + Cfg::kABytes;
+            if constexpr (CN > 1) {
+              tma_load_5d_mc(sa + a_row0 * Cfg::kSwizzle, &tmA, &full_bar[s], kt.a_c, wo0 + a_dw + kt.a_dx, kt.a_par,
+                             ho0 + a_dh + kt.a_dy, n, a_mask);
+            } else {
+              tma_load_5d(sa, &tmA, &full_bar[s], kt.a_c, wo0 + kt.a_dx, kt.a_par, ho0 + kt.a_dy, n);
+            }
+            if constexpr (CM > 1) {
+              tma_load_2d_mc(sb + cx * kBSliceRows * Cfg::kSwizzle, &tmB, &full_bar[s], kt.b_k,
+                             nblk * BN + cx * kBSliceRows, b_mask);
+            } else {
+              tma_load_2d(sb, &tmB, &full_bar[s], kt.b_k, nblk * BN);
+            }
+          }
+        }
+        if (prof && i == 0) prof[2] = clock64();
+      }
+      __syncwarp();
+    }
+    if (prof && lane == 0) prof[3] = clock64();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
+    constexpr uint32_t idesc = make_idesc_bf16(128, BN < 16 ? 16 : BN, 0, 0);
+    constexpr uint32_t desc_hi = smem_desc_hi(8 * Cfg::kSwizzle, swizzle_layout_type(Cfg::kSwizzle));
+    const uint32_t lo0 = smem_u32(smem) >> 4;  // smem addresses are < 256 KB: 14 bits after the shift
+    const int nstages = (kcnt + KPS - 1) / KPS;
+    for (int i = 0; i < nstages; ++i) {
+      const int s = i % STAGES;
+      const uint32_t ph = (i / STAGES) & 1;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const int nk = min(KPS, kcnt - i * KPS);
+#pragma unroll
+        for (int j = 0; j < KPS; ++j) {
+          if (j < nk) {
+            const uint32_t a_lo = lo0 + s * (Cfg::kStageBytes >> 4) + j * (Cfg::kSubBytes >> 4);
+            const uint32_t b_lo = a_lo + (Cfg::kABytes >> 4);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {  // +32 bytes (2 units) per 16-element K step inside the swizzle atom
+              umma_bf16(tmem_base, smem_desc_join(a_lo + 2 * k, desc_hi), smem_desc_join(b_lo + 2 * k, desc_hi), idesc,
+                        (i | j | k) != 0 ? 1u : 0u);
+            }
+          }
         }
         // frees the smem slot once these MMAs retire (in every CTA that feeds this one)
         if constexpr (kCluster) {
@@ -158,9 +184,11 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         } else {
           umma_commit(&empty_bar[s]);
         }
+        if (i == nstages - 1) umma_commit(tmem_full_bar);
       }
-      umma_commit(tmem_full_bar);
+      __syncwarp();
     }
+    if (prof && lane == 0) prof[4] = clock64();
   } else if (kcnt > 0) {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
@@ -170,9 +198,23 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const bool valid = (ho < args.Ho) && (wo < args.Wo) && (n < args.N);
     bf16* orow = args.out + args.out_off[cls] + (long long)n * args.sN + (long long)ho * args.sH +
                  (long long)wo * args.sW;
-    mbar_wait(tmem_full_bar, 0);
+    // this CTA's slice of the bias vector -> shared memory (read back as warp-wide broadcasts)
+    if (args.bias != nullptr) {
+      for (int j = threadIdx.x - 64; j < BN; j += 128) {
+        const int co = nblk * BN + j;
+        s_bias[j] = co < args.bias_n ? __ldg(args.bias + co) : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
+    }
+    mbar_wait_relaxed(tmem_full_bar, 0);
     tc_fence_after();
+    if (prof && threadIdx.x == 64) prof[5] = clock64();
     constexpr int CH = BN >= 32 ? 32 : 16;
+    // BN >= 64: rows are staged in shared memory (the pipeline buffers are idle once the accumulator is
+    // complete) and written out with every warp instruction covering whole 128-byte lines of one pixel.
+    constexpr bool kStaged = BN >= 64;
+    constexpr int kRowBytes = BN * 2;
+    uint8_t* stage_base = smem + (size_t)q * 32 * kRowBytes;  // this warp's 32 rows
 #pragma unroll 1
     for (int c = 0; c < BN; c += CH) {
       float v[CH];
@@ -185,14 +227,19 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tmem_ld16(taddr, r);
         }
         tmem_ld_wait();
+        if (prof && threadIdx.x == 64 && c == 0) prof[8] = clock64();
 #pragma unroll
         for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
       }
       const int co0 = nblk * BN + c;
       if (args.bias != nullptr) {
 #pragma unroll
-        for (int j = 0; j < CH; ++j) {
-          if (co0 + j < args.bias_n) v[j] += __ldg(args.bias + co0 + j);
+        for (int j = 0; j < CH; j += 4) {
+          const float4 bv = *reinterpret_cast<const float4*>(s_bias + c + j);
+          v[j] += bv.x;
+          v[j + 1] += bv.y;
+          v[j + 2] += bv.z;
+          v[j + 3] += bv.w;
         }
       }
       if (args.act == kActLeaky) {
@@ -236,11 +283,24 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int col = co0 + (lane & (CH - 1));
         if (n < args.N && col < args.Cout && (CH == 32 || lane < 16)) {
           float* st = args.stats + ((long long)n * args.Cout + col) * 2;
-          atomicAdd(st, a[0]);
-          atomicAdd(st + 1, b[0]);
+          asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(st), "f"(a[0]), "f"(b[0]) : "memory");
         }
       }
-      if (valid) {
+      if (prof && threadIdx.x == 64 && c == 0) prof[9] = clock64();
+      if constexpr (kStaged) {
+        // 16-byte pieces, XOR-swizzled by the row so that the 32 lanes of a store spread over all banks
+        uint8_t* srow = stage_base + (size_t)lane * kRowBytes;
+#pragma unroll
+        for (int j = 0; j < CH; j += 8) {
+          uint4 pk;
+          pk.x = pack_bf16x2(v[j + 0], v[j + 1]);
+          pk.y = pack_bf16x2(v[j + 2], v[j + 3]);
+          pk.z = pack_bf16x2(v[j + 4], v[j + 5]);
+          pk.w = pack_bf16x2(v[j + 6], v[j + 7]);
+          const int piece = (c + j) >> 3;  // 16-byte piece index within the row
+          *reinterpret_cast<uint4*>(srow + (((piece & ~7) | ((piece ^ lane) & 7)) << 4)) = pk;
+        }
+      } else if (valid) {
 #pragma unroll
         for (int j = 0; j < CH; j += 8) {
           if (co0 + j + 8 <= args.Cout) {
@@ -258,9 +318,29 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
     }
+    if (prof && threadIdx.x == 64) prof[10] = clock64();
+    if constexpr (kStaged) {
+      __syncwarp();
+      // each warp instruction writes kRowsPerInst whole pixel rows of BN channels (>= 128 contiguous bytes each)
+      constexpr int kLanesPerRow = kRowBytes / 16;  // 8, 16 or 32
+      constexpr int kRowsPerInst = 32 / kLanesPerRow;
+      const int sub = lane / kLanesPerRow, piece = lane % kLanesPerRow;
+      const unsigned long long optr = reinterpret_cast<unsigned long long>(orow + nblk * BN);
+#pragma unroll 4
+      for (int r0 = 0; r0 < 32; r0 += kRowsPerInst) {
+        const int r = r0 + sub;
+        const unsigned long long p = __shfl_sync(0xffffffffu, optr, r);
+        const int ok = __shfl_sync(0xffffffffu, valid ? 1 : 0, r);
+        const uint4 val = *reinterpret_cast<const uint4*>(stage_base + (size_t)r * kRowBytes +
+                                                          (((piece & ~7) | ((piece ^ r) & 7)) << 4));
+        if (ok) *reinterpret_cast<uint4*>(p + (unsigned long long)piece * 16) = val;
+      }
+    }
   }
+  if (prof && threadIdx.x == 64) prof[6] = clock64();
   tc_fence_before();
   __syncthreads();
+  if (prof && threadIdx.x == 0) prof[7] = clock64();
   if constexpr (kCluster) cluster_sync_all();  // no peer may still signal my barriers after I exit
   if (warp == 1) {
     tc_fence_after();
@@ -327,11 +407,12 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {
-      for (int i = 0; i < kcnt; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
+    // TMA producer: whole warp converged, one elected lane issues
+    for (int i = 0; i < kcnt; ++i) {
+      const int s = i % STAGES;
+      const uint32_t ph = (i / STAGES) & 1;
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      if (elect_one()) {
         int c = cbeg + i;
         const int tw = c % args.tiles_w;
         c /= args.tiles_w;
@@ -350,26 +431,31 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
           tma_load_5d(sb + j * Cfg::kAtomBytes, &tmX, &full_bar[s], tap.b_c + nblk * BNW + j * 64, w0 + tap.b_dx,
                       tap.b_par, h0 + tap.b_dy, n);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BNW, 1, 1);
-      for (int i = 0; i < kcnt; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
-        const uint32_t b_addr = a_addr + Cfg::kABytes;
+    // MMA issuer: MN-major SWIZZLE_128B operands, LBO = one 64-channel atom (8 KB), SBO = 8 pixel rows (1 KB)
+    constexpr uint32_t idesc = make_idesc_bf16(128, BNW, 1, 1);
+    constexpr uint32_t desc_hi = smem_desc_hi(1024, 2);
+    constexpr uint32_t lbo_lo = (Cfg::kAtomBytes >> 4) << 16;
+    const uint32_t lo0 = smem_u32(smem) >> 4;
+    for (int i = 0; i < kcnt; ++i) {
+      const int s = i % STAGES;
+      const uint32_t ph = (i / STAGES) & 1;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a_lo = (lo0 + s * (Cfg::kStageBytes >> 4)) | lbo_lo;
+        const uint32_t b_lo = a_lo + (Cfg::kABytes >> 4);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {  // 64 pixels per stage, UMMA_K = 16 pixels = 16 rows of 128 B
-          const uint64_t ad = make_smem_desc(a_addr + k * 2048, Cfg::kAtomBytes, 1024, 2);
-          const uint64_t bd = make_smem_desc(b_addr + k * 2048, Cfg::kAtomBytes, 1024, 2);
-          umma_bf16(tmem_base, ad, bd, idesc, (i | k) != 0 ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) {  // 64 pixels per stage, UMMA_K = 16 pixels = 16 rows of 128 B = 2 KB
+          umma_bf16(tmem_base, smem_desc_join(a_lo + k * 128, desc_hi), smem_desc_join(b_lo + k * 128, desc_hi), idesc,
+                    (i | k) != 0 ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);
+        if (i == kcnt - 1) umma_commit(tmem_full_bar);
       }
-      if (kcnt > 0) umma_commit(tmem_full_bar);
+      __syncwarp();
     }
   } else if (kcnt > 0) {
     const int q = warp & 3;
@@ -384,7 +470,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
     float* grow = args.g + row * args.Cin;
     // rows are 16-byte aligned when Cin % 4 == 0: use 4-wide vector reductions
     const bool vec_ok = (args.Cin & 3) == 0;
-    mbar_wait(tmem_full_bar, 0);
+    mbar_wait_relaxed(tmem_full_bar, 0);
     tc_fence_after();
 #pragma unroll 1
     for (int c = 0; c < BNW; c += 32) {
@@ -421,12 +507,12 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
 // ------------------------------------------------------------------------------------------
 // Host launchers
 // ------------------------------------------------------------------------------------------
-template <int BN, int BK, int STAGES, int CM, int CN>
+template <int BN, int BK, int STAGES, int KPS, int CM, int CN>
 static void launch_igemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmArgs& args, dim3 grid,
                            cudaStream_t stream) {
-  using Cfg = IgemmCfg<BN, BK, STAGES>;
+  using Cfg = IgemmCfg<BN, BK, STAGES, KPS>;
   static bool configured = false;
-  auto kern = igemm_conv_kernel<BN, BK, STAGES, CM, CN>;
+  auto kern = igemm_conv_kernel<BN, BK, STAGES, KPS, CM, CN>;
   if (!configured) {
     CGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
@@ -453,40 +539,25 @@ static void launch_igemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const
   CGB_CUDA(cudaGetLastError());
 }
 
-#ifndef CGB_STAGES64
-#define CGB_STAGES64 4
-#endif
-#ifndef CGB_STAGES128
-#define CGB_STAGES128 4
-#endif
-constexpr int kStages64 = CGB_STAGES64;
-constexpr int kStages128 = CGB_STAGES128;
-
 void launch_igemm(int BN, int BK, int CM, int CN, const CUtensorMap& tmA, const CUtensorMap& tmB,
                   const IgemmArgs& args, int num_tiles, int n_blocks, int n_classes, cudaStream_t stream) {
   dim3 grid(num_tiles, n_blocks, n_classes);
   const int key = BN * 1000000 + BK * 10000 + CM * 100 + CN;
   switch (key) {
-    // single-CTA
-    case 256 * 1000000 + 64 * 10000 + 101: return launch_igemm_t<256, 64, 4, 1, 1>(tmA, tmB, args, grid, stream);
-    case 128 * 1000000 + 64 * 10000 + 101: return launch_igemm_t<128, 64, kStages128, 1, 1>(tmA, tmB, args, grid, stream);
-    case 64 * 1000000 + 64 * 10000 + 101: return launch_igemm_t<64, 64, kStages64, 1, 1>(tmA, tmB, args, grid, stream);
-    case 16 * 1000000 + 64 * 10000 + 101: return launch_igemm_t<16, 64, 6, 1, 1>(tmA, tmB, args, grid, stream);
-    case 64 * 1000000 + 16 * 10000 + 101: return launch_igemm_t<64, 16, 8, 1, 1>(tmA, tmB, args, grid, stream);
-    case 16 * 1000000 + 16 * 10000 + 101: return launch_igemm_t<16, 16, 8, 1, 1>(tmA, tmB, args, grid, stream);
-    // clusters with TMA multicast (BK = 64 layers)
-    case 64 * 1000000 + 64 * 10000 + 204: return launch_igemm_t<64, 64, 6, 2, 4>(tmA, tmB, args, grid, stream);
-    case 64 * 1000000 + 64 * 10000 + 104: return launch_igemm_t<64, 64, 6, 1, 4>(tmA, tmB, args, grid, stream);
-    case 64 * 1000000 + 64 * 10000 + 202: return launch_igemm_t<64, 64, 6, 2, 2>(tmA, tmB, args, grid, stream);
-    case 64 * 1000000 + 64 * 10000 + 402: return launch_igemm_t<64, 64, 6, 4, 2>(tmA, tmB, args, grid, stream);
-    case 64 * 1000000 + 64 * 10000 + 401: return launch_igemm_t<64, 64, 6, 4, 1>(tmA, tmB, args, grid, stream);
-    case 64 * 1000000 + 64 * 10000 + 201: return launch_igemm_t<64, 64, 6, 2, 1>(tmA, tmB, args, grid, stream);
-    case 128 * 1000000 + 64 * 10000 + 202: return launch_igemm_t<128, 64, 4, 2, 2>(tmA, tmB, args, grid, stream);
-    case 128 * 1000000 + 64 * 10000 + 402: return launch_igemm_t<128, 64, 4, 4, 2>(tmA, tmB, args, grid, stream);
-    case 128 * 1000000 + 64 * 10000 + 401: return launch_igemm_t<128, 64, 4, 4, 1>(tmA, tmB, args, grid, stream);
-    case 128 * 1000000 + 64 * 10000 + 201: return launch_igemm_t<128, 64, 4, 2, 1>(tmA, tmB, args, grid, stream);
-    case 256 * 1000000 + 64 * 10000 + 201: return launch_igemm_t<256, 64, 4, 2, 1>(tmA, tmB, args, grid, stream);
-    case 256 * 1000000 + 64 * 10000 + 401: return launch_igemm_t<256, 64, 4, 4, 1>(tmA, tmB, args, grid, stream);
+    // single-CTA (BN, BK, stages, K iterations per stage)
+    case 256 * 1000000 + 64 * 10000 + 101: return launch_igemm_t<256, 64, 4, 1, 1, 1>(tmA, tmB, args, grid, stream);
+    case 128 * 1000000 + 64 * 10000 + 101: return launch_igemm_t<128, 64, 3, 2, 1, 1>(tmA, tmB, args, grid, stream);
+    case 64 * 1000000 + 64 * 10000 + 101: return launch_igemm_t<64, 64, 4, 2, 1, 1>(tmA, tmB, args, grid, stream);
+    case 16 * 1000000 + 64 * 10000 + 101: return launch_igemm_t<16, 64, 3, 4, 1, 1>(tmA, tmB, args, grid, stream);
+    case 64 * 1000000 + 16 * 10000 + 101: return launch_igemm_t<64, 16, 4, 7, 1, 1>(tmA, tmB, args, grid, stream);
+    case 16 * 1000000 + 16 * 10000 + 101: return launch_igemm_t<16, 16, 4, 7, 1, 1>(tmA, tmB, args, grid, stream);
+    // clusters with TMA multicast (experimental, CGB_CLUSTER=1)
+    case 64 * 1000000 + 64 * 10000 + 204: return launch_igemm_t<64, 64, 6, 1, 2, 4>(tmA, tmB, args, grid, stream);
+    case 64 * 1000000 + 64 * 10000 + 402: return launch_igemm_t<64, 64, 6, 1, 4, 2>(tmA, tmB, args, grid, stream);
+    case 64 * 1000000 + 64 * 10000 + 401: return launch_igemm_t<64, 64, 6, 1, 4, 1>(tmA, tmB, args, grid, stream);
+    case 128 * 1000000 + 64 * 10000 + 402: return launch_igemm_t<128, 64, 4, 1, 4, 2>(tmA, tmB, args, grid, stream);
+    case 128 * 1000000 + 64 * 10000 + 401: return launch_igemm_t<128, 64, 4, 1, 4, 1>(tmA, tmB, args, grid, stream);
+    case 256 * 1000000 + 64 * 10000 + 401: return launch_igemm_t<256, 64, 4, 1, 4, 1>(tmA, tmB, args, grid, stream);
     default: break;
   }
   CGB_CHECK(false, "launch_igemm: unsupported config BN=" + std::to_string(BN) + " BK=" + std::to_string(BK) +

@@ -247,6 +247,44 @@ void cgb_engine::run_segment(int seg, cudaStream_t st) {
   }
 }
 
+// Captures the whole step with external event-record nodes at the program markers, replays it, and returns
+// "label lane ms" lines (ms since the first marker).  Development profiling only.
+std::string cgb_engine::timeline(cudaStream_t st) {
+  CGB_CHECK(st != nullptr, "timeline needs a non-default stream");
+  lane_streams[0] = st;
+  for (int l = 1; l < kLanes; ++l)
+    if (!lane_streams[l]) CGB_CUDA(cudaStreamCreateWithFlags(&lane_streams[l], cudaStreamNonBlocking));
+  cudaStream_t mapped[kLanes];
+  const int max_lanes = std::getenv("CGB_MAX_LANES") ? std::atoi(std::getenv("CGB_MAX_LANES")) : kLanes;
+  for (int l = 0; l < kLanes; ++l) mapped[l] = lane_streams[l % std::max(1, max_lanes)];
+  for (const Program* p : segments[CGB_SEG_STEP].seq) p->run(st);  // eager warm-up
+  CGB_CUDA(cudaStreamSynchronize(st));
+  std::vector<Program::Mark> marks;
+  std::vector<cudaEvent_t> evs;
+  size_t next_event = 0;
+  cudaGraph_t g = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  CGB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+  for (const Program* p : segments[CGB_SEG_STEP].seq) p->run_lanes(mapped, evs, &next_event, &marks);
+  CGB_CUDA(cudaStreamEndCapture(st, &g));
+  CGB_CUDA(cudaGraphInstantiate(&exec, g, 0));
+  for (int i = 0; i < 3; ++i) CGB_CUDA(cudaGraphLaunch(exec, st));
+  CGB_CUDA(cudaStreamSynchronize(st));
+  std::string out;
+  for (const Program::Mark& m : marks) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, marks[0].ev, m.ev);
+    char line[160];
+    snprintf(line, sizeof(line), "%-32s lane %d  %8.3f ms\n", m.label.c_str(), m.lane, ms);
+    out += line;
+  }
+  for (const Program::Mark& m : marks) cudaEventDestroy(m.ev);
+  for (cudaEvent_t ev : evs) cudaEventDestroy(ev);
+  cudaGraphExecDestroy(exec);
+  cudaGraphDestroy(g);
+  return out;
+}
+
 void* cgb_engine::meta_upload(const void* src, size_t bytes) {
   meta_off = (meta_off + 255) & ~size_t(255);
   CGB_CHECK(meta_off + bytes <= meta_cap, "engine meta buffer exhausted");
@@ -285,8 +323,8 @@ void cgb_engine::record_programs() {
     pr.add([pp](cudaStream_t st) { run(*pp, st); }, 1, kOpIgemm, p.flops);
     *fl += p.flops;
   };
-  auto add_wgrad = [E](Program& pr, double* fl, const LayerParam& L, const TensorDesc& x, const TensorDesc& dy,
-                       bf16* colbuf, size_t colbuf_elems) {
+  auto add_wgrad_on_lane = [E](Program& pr, double* fl, const LayerParam& L, const TensorDesc& x, const TensorDesc& dy,
+                               bf16* colbuf, size_t colbuf_elems) {
     float* g = E->G[L.group] + L.w_off;
     if (tc_supports_wgrad(L.spec)) {
       WgradPlan p = plan_wgrad(L.spec, x, dy, g, E->sm_count);
@@ -318,8 +356,8 @@ void cgb_engine::record_programs() {
     }
   };
   // InstanceNorm + activation backward; da_store (engine-owned tensor) receives the assembled gradient
-  auto add_in_bwd = [](Program& pr, const TensorDesc& y, const float2* stats, float2* bstats, GradSrc g, int act,
-                       const TensorDesc* da_store, const TensorDesc& dy) {
+  auto add_in_bwd_raw = [](Program& pr, const TensorDesc& y, const float2* stats, float2* bstats, GradSrc g, int act,
+                           const TensorDesc* da_store, const TensorDesc& dy) {
     pr.add([y, stats, bstats, g, act, da_store](cudaStream_t st) { in_bwd_reduce(y, stats, g, act, da_store, bstats, st); },
            1, kOpNorm);
     GradSrc g2 = g;
@@ -367,6 +405,21 @@ void cgb_engine::record_programs() {
     float* Gg = E->G[CGB_GROUP_G];
     float2* st = P.stats;
     float2* bs = P.bstats;
+    const int main_lane = pr.cur_lane, wlane = pr.cur_lane + kPassLanes;
+    // weight gradient on the side lane, beside the input gradient of the same layer
+    auto add_wgrad = [&](Program& pr_, double* fl_, const LayerParam& Lp, const TensorDesc& x, const TensorDesc& dy,
+                         bf16* colbuf, size_t colbuf_elems) {
+      pr_.dep(main_lane, wlane);
+      pr_.cur_lane = wlane;
+      add_wgrad_on_lane(pr_, fl_, Lp, x, dy, colbuf, colbuf_elems);
+      pr_.cur_lane = main_lane;
+    };
+    // the next layer overwrites the dy buffer: wait for the side lane first
+    auto add_in_bwd = [&](Program& pr_, const TensorDesc& y, const float2* stats, float2* bstats, GradSrc g, int act,
+                          const TensorDesc* da_store, const TensorDesc& dy) {
+      pr_.dep(wlane, main_lane);
+      add_in_bwd_raw(pr_, y, stats, bstats, g, act, da_store, dy);
+    };
     pr.add([bs, bytes = P.stats_bytes](cudaStream_t s) { CGB_CUDA(cudaMemsetAsync(bs, 0, bytes, s)); }, 0, kOpMemset);
     const LayerParam& head = L[5 + 2 * nb];
     {
@@ -434,6 +487,7 @@ void cgb_engine::record_programs() {
     add_in_bwd(pr, P.y_stem, st + P.stat_off[0], bs + P.stat_off[0], g, kActRelu, nullptr, S.dyF);
     add_wgrad(pr, fl, L[0], P.in, S.dyF, S.colbuf, S.colbuf_elems);
     if (dxp_img_out) add_dgrad(pr, fl, L[0], S.dyF, *dxp_img_out);
+    pr.dep(wlane, main_lane);
   };
 
   // ---------------------------------------------------------------- discriminator
@@ -458,6 +512,19 @@ void cgb_engine::record_programs() {
     float* Gd = E->G[CGB_GROUP_D];
     float2* st = D.stats;
     float2* bs = D.bstats;
+    const int main_lane = pr.cur_lane, wlane = pr.cur_lane + kPassLanes;
+    auto add_wgrad = [&](Program& pr_, double* fl_, const LayerParam& Lp, const TensorDesc& x, const TensorDesc& dy,
+                         bf16* colbuf, size_t colbuf_elems) {
+      pr_.dep(main_lane, wlane);
+      pr_.cur_lane = wlane;
+      add_wgrad_on_lane(pr_, fl_, Lp, x, dy, colbuf, colbuf_elems);
+      pr_.cur_lane = main_lane;
+    };
+    auto add_in_bwd = [&](Program& pr_, const TensorDesc& y, const float2* stats, float2* bstats, GradSrc g, int act,
+                          const TensorDesc* da_store, const TensorDesc& dy) {
+      pr_.dep(wlane, main_lane);
+      add_in_bwd_raw(pr_, y, stats, bstats, g, act, da_store, dy);
+    };
     pr.add([bs, bytes = D.stats_bytes](cudaStream_t s) { CGB_CUDA(cudaMemsetAsync(bs, 0, bytes, s)); }, 0, kOpMemset);
     {
       const TensorDesc lg = D.logits;
@@ -495,6 +562,7 @@ void cgb_engine::record_programs() {
       }
     }
     if (dx_img_out) add_dgrad(pr, fl, L[0], S.dpre0, *dx_img_out);
+    pr.dep(wlane, main_lane);
   };
 
   // ---------------------------------------------------------------- step programs
@@ -515,21 +583,29 @@ void cgb_engine::record_programs() {
   // Independent passes are recorded on different lanes (parallel branches of the step graph).
   {
     Program& pr = prog_cycle;
+    pr.mark("cycle begin");
     pr.fork();
     pr.cur_lane = 0;
     emit_gen_forward(pr, flops, gen[0], CGB_NET_G_AB, real_A, img[CGB_IMG_FAKE_B], true);
+    pr.mark("fwd fake_B done");
     pr.cur_lane = 1;
     emit_gen_forward(pr, flops, gen[2], CGB_NET_G_BA, real_B, img[CGB_IMG_FAKE_A], true);
+    pr.mark("fwd fake_A done");
     pr.cur_lane = 2;
     emit_gen_forward(pr, flops, gen[4], CGB_NET_G_AB, real_B, img[CGB_IMG_IDT_A], false);
+    pr.mark("fwd idt_A done");
     pr.cur_lane = 3;
     emit_gen_forward(pr, flops, gen[5], CGB_NET_G_BA, real_A, img[CGB_IMG_IDT_B], false);
+    pr.mark("fwd idt_B done");
     pr.cur_lane = 0;
     emit_gen_forward(pr, flops, gen[1], CGB_NET_G_BA, fake_B, img[CGB_IMG_REC_A], false);
+    pr.mark("fwd rec_A done");
     pr.cur_lane = 1;
     emit_gen_forward(pr, flops, gen[3], CGB_NET_G_AB, fake_A, img[CGB_IMG_REC_B], false);
+    pr.mark("fwd rec_B done");
     pr.join();
     pr.cur_lane = 0;
+    pr.mark("cycle end");
   }
 
   const float numel_img = (float)N * 3.f * S * S;
@@ -545,17 +621,23 @@ void cgb_engine::record_programs() {
     // identity passes (L1 seeds), then the adversarial terms (D frozen: input gradients only)
     pr.cur_lane = 2;
     emit_gen_backward(pr, flops, gen[4], gs[2], &real_B, cfg.lambda_B * cfg.lambda_idt / numel_img, CGB_LOSS_IDT_A, GradSrc(), nullptr);
+    pr.mark("bwd idt_A done");
     emit_dis_forward(pr, flops, dis[0], CGB_NET_D_A, fake_B);
     emit_dis_backward(pr, flops, dis[0], ds[0], 1.f, 1.f, CGB_LOSS_G_A, false, &dx_D0[0]);
+    pr.mark("D_A(fake_B) fwd+dgrad done");
     pr.cur_lane = 3;
     emit_gen_backward(pr, flops, gen[5], gs[3], &real_A, cfg.lambda_A * cfg.lambda_idt / numel_img, CGB_LOSS_IDT_B, GradSrc(), nullptr);
+    pr.mark("bwd idt_B done");
     emit_dis_forward(pr, flops, dis[1], CGB_NET_D_B, fake_A);
     emit_dis_backward(pr, flops, dis[1], ds[1], 1.f, 1.f, CGB_LOSS_G_B, false, &dx_D0[1]);
+    pr.mark("D_B(fake_A) fwd+dgrad done");
     // cycle passes: also produce the gradient w.r.t. the fake images (padded domain of the next stem)
     pr.cur_lane = 0;
     emit_gen_backward(pr, flops, gen[1], gs[0], &real_A, cfg.lambda_A / numel_img, CGB_LOSS_CYCLE_A, GradSrc(), &dxp_img[0]);
+    pr.mark("bwd rec_A done");
     pr.cur_lane = 1;
     emit_gen_backward(pr, flops, gen[3], gs[1], &real_B, cfg.lambda_B / numel_img, CGB_LOSS_CYCLE_B, GradSrc(), &dxp_img[1]);
+    pr.mark("bwd rec_B done");
     // the passes that produced the fakes: gradient = D's input gradient + folded stem gradient
     pr.dep(2, 0);
     pr.dep(3, 1);
@@ -565,12 +647,15 @@ void cgb_engine::record_programs() {
     g.fold = 3;
     pr.cur_lane = 0;
     emit_gen_backward(pr, flops, gen[0], gs[0], nullptr, 0.f, -1, g, nullptr);
+    pr.mark("bwd fake_B done");
     g.g1 = &dx_D0[1];
     g.g2 = &dxp_img[1];
     pr.cur_lane = 1;
     emit_gen_backward(pr, flops, gen[2], gs[1], nullptr, 0.f, -1, g, nullptr);
+    pr.mark("bwd fake_A done");
     pr.join();
     pr.cur_lane = 0;
+    pr.mark("G phase end");
   }
   {  // ---- D phase: real passes are new; the fake passes reuse the G-phase forward (D unchanged since)
     Program& pr = prog_D;
@@ -578,7 +663,7 @@ void cgb_engine::record_programs() {
     const size_t gbytes = (size_t)group_numel[CGB_GROUP_D] * sizeof(float);
     pr.cur_lane = 0;
     pr.add([gD, gbytes](cudaStream_t s) { CGB_CUDA(cudaMemsetAsync(gD, 0, gbytes, s)); }, 0, kOpMemset);
-    pr.fork(2);
+    pr.fork();
     pr.cur_lane = 0;
     emit_dis_forward(pr, flops, dis[2], CGB_NET_D_A, real_B);
     emit_dis_backward(pr, flops, dis[2], ds[0], 1.f, 0.5f, CGB_LOSS_D_A, true, nullptr);
@@ -587,8 +672,9 @@ void cgb_engine::record_programs() {
     emit_dis_forward(pr, flops, dis[3], CGB_NET_D_B, real_A);
     emit_dis_backward(pr, flops, dis[3], ds[1], 1.f, 0.5f, CGB_LOSS_D_B, true, nullptr);
     emit_dis_backward(pr, flops, dis[1], ds[1], 0.f, 0.5f, CGB_LOSS_D_B, true, nullptr);
-    pr.join(2);
+    pr.join();
     pr.cur_lane = 0;
+    pr.mark("D phase end");
   }
   // ---- optimiser + bf16 weight refresh
   for (int g = 0; g < 2; ++g) {
@@ -632,6 +718,7 @@ void cgb_engine::record_programs() {
   segments[CGB_SEG_D].seq = {&prog_D};
   segments[CGB_SEG_ADAM_G].seq = {&prog_adam[0]};
   segments[CGB_SEG_ADAM_D].seq = {&prog_adam[1]};
+  segments[CGB_SEG_FORWARD].seq = {&prog_set_inputs, &prog_cycle};
   // ---- module-level forward programs (Generator.forward / Discriminator.forward)
   for (int net = 0; net < 2; ++net) {
     emit_gen_forward(prog_mod_gen[net], &dummy_flops, gen[6], net, mod_in, mod_out, false);

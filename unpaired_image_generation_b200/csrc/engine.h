@@ -25,8 +25,10 @@ struct LayerParam {
 };
 
 typedef std::function<void(cudaStream_t)> Op;
-enum OpKind { kOpOther = 0, kOpIgemm = 1, kOpWgradTc = 2, kOpWgradDirect = 3, kOpNorm = 4, kOpMemset = 5, kOpDep = 6, kNumOpKinds = 7 };
-constexpr int kLanes = 4;  // independent passes of the step run on parallel graph branches ("lanes")
+enum OpKind { kOpOther = 0, kOpIgemm = 1, kOpWgradTc = 2, kOpWgradDirect = 3, kOpNorm = 4, kOpMemset = 5, kOpDep = 6, kOpMarker = 7, kNumOpKinds = 8 };
+constexpr int kLanes = 8;  // parallel graph branches: lanes 0-3 carry independent passes, lane l+4 the weight
+                           // gradients of the pass on lane l (wgrad runs beside the dgrad of the same layer)
+constexpr int kPassLanes = 4;
 
 // A recorded launch sequence.  Each op belongs to a lane; `dep(a, b)` makes everything issued later on lane b
 // wait for everything issued so far on lane a.  Run on ONE stream the recorded order is already a valid
@@ -52,6 +54,16 @@ struct Program {
     dep_from.push_back(from);
     flops.push_back(0.0);
   }
+  // timeline marker (profiling): an external event record on the current lane when `timeline` is set
+  std::vector<std::string> labels;
+  void mark(const std::string& label) {
+    ops.push_back(Op());
+    kinds.push_back(kOpMarker);
+    lanes.push_back(cur_lane);
+    dep_from.push_back((int)labels.size());
+    flops.push_back(0.0);
+    labels.push_back(label);
+  }
   void fork(int n = kLanes) {
     for (int l = 1; l < n; ++l) dep(0, l);
   }
@@ -60,12 +72,27 @@ struct Program {
   }
   void run(cudaStream_t st) const {
     for (size_t i = 0; i < ops.size(); ++i)
-      if (kinds[i] != kOpDep) ops[i](st);
+      if (kinds[i] != kOpDep && kinds[i] != kOpMarker) ops[i](st);
   }
   // lanes[l] are distinct streams (lane 0 = the caller's); events: one per dep op, created by the caller
-  void run_lanes(cudaStream_t* lane_streams, std::vector<cudaEvent_t>& events, size_t* next_event) const {
+  struct Mark {
+    std::string label;
+    int lane;
+    cudaEvent_t ev;
+  };
+  void run_lanes(cudaStream_t* lane_streams, std::vector<cudaEvent_t>& events, size_t* next_event,
+                 std::vector<Mark>* timeline = nullptr) const {
     for (size_t i = 0; i < ops.size(); ++i) {
-      if (kinds[i] == kOpDep) {
+      if (kinds[i] == kOpMarker) {
+        if (timeline) {
+          Mark m;
+          m.label = labels[dep_from[i]];
+          m.lane = lanes[i];
+          CGB_CUDA(cudaEventCreate(&m.ev));
+          CGB_CUDA(cudaEventRecordWithFlags(m.ev, lane_streams[lanes[i]], cudaEventRecordExternal));
+          timeline->push_back(m);
+        }
+      } else if (kinds[i] == kOpDep) {
         if (*next_event >= events.size()) {
           cudaEvent_t ev;
           CGB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -82,7 +109,7 @@ struct Program {
   // replay only the ops of one kind (profiling; data dependencies are ignored on purpose)
   void run_kind(int kind, cudaStream_t st, long long* count, double* fl) const {
     for (size_t i = 0; i < ops.size(); ++i)
-      if (kinds[i] == kind) {
+      if (kinds[i] == kind && kind != kOpDep && kind != kOpMarker) {
         ops[i](st);
         if (count) ++*count;
         if (fl) *fl += flops[i];
@@ -173,7 +200,7 @@ struct cgb_engine {
   float* adam_hyper[2] = {nullptr, nullptr};
   std::vector<cgb::GenPass> gen;  // 6 training passes + 1 module-forward pass
   std::vector<cgb::DisPass> dis;  // 4 training passes + 1 module-forward pass
-  cgb::GenScratch gs[cgb::kLanes];
+  cgb::GenScratch gs[cgb::kPassLanes];
   cgb::DisScratch ds[2];
   cgb::TensorDesc dxp_img[2], dx_D0[2];  // gradients w.r.t. the fake images (from the cycle passes / from D)
 
@@ -191,7 +218,7 @@ struct cgb_engine {
   cgb::Program prog_mod_gen[2], prog_mod_dis[2];
   double conv_flops = 0;  // accumulated while recording prog_cycle/prog_G/prog_D
 
-  cudaStream_t lane_streams[cgb::kLanes] = {nullptr, nullptr, nullptr, nullptr};  // [0] = caller's stream
+  cudaStream_t lane_streams[cgb::kLanes] = {};  // [0] = caller's stream
   std::vector<cudaEvent_t> events;
   std::vector<cudaEvent_t> seg_events[CGB_NUM_SEGMENTS];
   struct Segment {  // a graph-replayable sequence of programs
@@ -203,6 +230,7 @@ struct cgb_engine {
   Segment segments[CGB_NUM_SEGMENTS];
   void run_segment(int seg, cudaStream_t st);
   void drop_graphs();
+  std::string timeline(cudaStream_t st);
 
   ~cgb_engine();
   void build_inventory();

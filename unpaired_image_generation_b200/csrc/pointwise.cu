@@ -68,6 +68,10 @@ __device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
   for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
   *reinterpret_cast<uint4*>(p) = u;
 }
+// one 16-byte reduction instead of four scalar atomics (same-address fp32 atomics serialise in L2)
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ float round_bf16(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
 // gradient w.r.t. the activation at interior pixel (n, h, w), channels [c0, c0+8)
@@ -213,8 +217,7 @@ __global__ void colsum_kernel(DevTensor y, float* __restrict__ out, int pix_per_
       for (int i = 0; i < 8; ++i) {
         const int c = cb * 8 + i;
         if (MODE == 0) {
-          atomicAdd(out + ((long long)n * y.C + c) * 2, s[i]);
-          atomicAdd(out + ((long long)n * y.C + c) * 2 + 1, ss[i]);
+          if ((i & 1) == 0) red_add_v4(out + ((long long)n * y.C + c) * 2, s[i], ss[i], s[i + 1], ss[i + 1]);
         } else if (c < Cvalid) {
           atomicAdd(out + c, s[i]);
         }
@@ -231,35 +234,47 @@ int pick_pix_per_block(int HW) {
 }
 
 // ------------------------------------------------------------------------------------------ IN apply
-__global__ void in_apply_kernel(DevTensor y, const float2* __restrict__ stats, int act, DevTensor res, DevTensor out) {
-  const int HP = out.H + 2 * out.halo, WP = out.W + 2 * out.halo, C8 = out.C / 8;
-  const long long total = (long long)out.N * HP * WP * C8;
-  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int c0 = (idx % C8) * 8;
-  long long r = idx / C8;
-  const int wp = r % WP;
-  r /= WP;
-  const int hp = r % HP;
-  const int n = r / HP;
-  const int h = reflect_idx(hp - out.halo, out.H), w = reflect_idx(wp - out.halo, out.W);
-  float v[8];
-  load8(y.p + n * y.sN + h * y.sH + w * y.sW + c0, v);
+// Block = 256 threads = (C/8 channel lanes) x (pixel rows); a thread keeps ONE 8-channel chunk, so mean / rstd
+// are computed once and reused over `ppt` pixels (grid.x * rows * ppt covers the padded output pixels).
+__global__ void in_apply_kernel(DevTensor y, const float2* __restrict__ stats, int act, DevTensor res, DevTensor out,
+                                int ppt) {
+  const int C8 = out.C / 8;
+  const int lanes = C8 < 256 ? C8 : 256;
+  const int rows = 256 / lanes;
+  const int cl = threadIdx.x % lanes, pr = threadIdx.x / lanes;
+  const int n = blockIdx.y;
+  const int HP = out.H + 2 * out.halo, WP = out.W + 2 * out.halo;
+  const int total = HP * WP;
   const float inv = 1.f / (float)(y.H * y.W);
+  for (int cb = cl; cb < C8; cb += lanes) {
+    const int c0 = cb * 8;
+    float mean[8], rstd[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float2 st = __ldg(stats + (long long)n * y.C + c0 + i);
-    const float mean = st.x * inv;
-    const float var = fmaxf(st.y * inv - mean * mean, 0.f);
-    v[i] = act_fwd((v[i] - mean) * rsqrtf(var + 1e-5f), act);
-  }
-  if (res.p != nullptr) {
-    float rv[8];
-    load8(res.p + n * res.sN + h * res.sH + w * res.sW + c0, rv);
+    for (int i = 0; i < 8; ++i) {
+      const float2 st = __ldg(stats + (long long)n * y.C + c0 + i);
+      mean[i] = st.x * inv;
+      rstd[i] = rsqrtf(fmaxf(st.y * inv - mean[i] * mean[i], 0.f) + 1e-5f);
+    }
+    const int p_begin = (blockIdx.x * rows + pr) * ppt;
+#pragma unroll 4
+    for (int k = 0; k < ppt; ++k) {
+      const int p = p_begin + k;
+      if (p >= total) break;
+      const int hp = p / WP, wp = p - hp * WP;
+      const int h = reflect_idx(hp - out.halo, out.H), w = reflect_idx(wp - out.halo, out.W);
+      float v[8];
+      load8(y.p + n * y.sN + h * y.sH + w * y.sW + c0, v);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] += rv[i];
+      for (int i = 0; i < 8; ++i) v[i] = act_fwd((v[i] - mean[i]) * rstd[i], act);
+      if (res.p != nullptr) {
+        float rv[8];
+        load8(res.p + n * res.sN + h * res.sH + w * res.sW + c0, rv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += rv[i];
+      }
+      store8(out.p + n * out.sN + (hp - out.halo) * out.sH + (wp - out.halo) * out.sW + c0, v);
+    }
   }
-  store8(out.p + n * out.sN + (hp - out.halo) * out.sH + (wp - out.halo) * out.sW + c0, v);
 }
 
 // ------------------------------------------------------------------------------------------ IN backward
@@ -319,10 +334,9 @@ __global__ void in_bwd_reduce_kernel(DevTensor y, const float2* __restrict__ sta
         }
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 8; i += 2) {
         const int c = cb * 8 + i;
-        atomicAdd(bstats + ((long long)n * y.C + c) * 2, s1[i]);
-        atomicAdd(bstats + ((long long)n * y.C + c) * 2 + 1, s2[i]);
+        red_add_v4(bstats + ((long long)n * y.C + c) * 2, s1[i], s2[i], s1[i + 1], s2[i + 1]);
       }
     }
     __syncthreads();
@@ -330,32 +344,44 @@ __global__ void in_bwd_reduce_kernel(DevTensor y, const float2* __restrict__ sta
 }
 
 __global__ void in_bwd_apply_kernel(DevTensor y, const float2* __restrict__ stats, const float2* __restrict__ bstats,
-                                    DevGrad g, int act, DevTensor dy) {
+                                    DevGrad g, int act, DevTensor dy, int ppt) {
   const int C8 = y.C / 8;
-  const long long total = (long long)y.N * y.H * y.W * C8;
-  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int c0 = (idx % C8) * 8;
-  long long r = idx / C8;
-  const int w = r % y.W;
-  r /= y.W;
-  const int h = r % y.H;
-  const int n = r / y.H;
-  const float inv = 1.f / (float)(y.H * y.W);
-  float v[8], gr[8];
-  load8(y.p + n * y.sN + h * y.sH + w * y.sW + c0, v);
-  load_grad8(g, n, h, w, c0, y.H, y.W, gr);
+  const int lanes = C8 < 256 ? C8 : 256;
+  const int rows = 256 / lanes;
+  const int cl = threadIdx.x % lanes, pr = threadIdx.x / lanes;
+  const int n = blockIdx.y;
+  const int total = y.H * y.W;
+  const float inv = 1.f / (float)total;
+  for (int cb = cl; cb < C8; cb += lanes) {
+    const int c0 = cb * 8;
+    float mean[8], rstd[8], m1[8], m2[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float2 st = __ldg(stats + (long long)n * y.C + c0 + i);
-    const float2 bs = __ldg(bstats + (long long)n * y.C + c0 + i);
-    const float mean = st.x * inv;
-    const float rstd = rsqrtf(fmaxf(st.y * inv - mean * mean, 0.f) + 1e-5f);
-    const float xh = (v[i] - mean) * rstd;
-    const float dz = gr[i] * act_grad(xh, act);
-    v[i] = rstd * (dz - bs.x * inv - xh * bs.y * inv);
+    for (int i = 0; i < 8; ++i) {
+      const float2 st = __ldg(stats + (long long)n * y.C + c0 + i);
+      const float2 bs = __ldg(bstats + (long long)n * y.C + c0 + i);
+      mean[i] = st.x * inv;
+      rstd[i] = rsqrtf(fmaxf(st.y * inv - mean[i] * mean[i], 0.f) + 1e-5f);
+      m1[i] = bs.x * inv;
+      m2[i] = bs.y * inv;
+    }
+    const int p_begin = (blockIdx.x * rows + pr) * ppt;
+#pragma unroll 4
+    for (int k = 0; k < ppt; ++k) {
+      const int p = p_begin + k;
+      if (p >= total) break;
+      const int h = p / y.W, w = p - h * y.W;
+      float v[8], gr[8];
+      load8(y.p + n * y.sN + h * y.sH + w * y.sW + c0, v);
+      load_grad8(g, n, h, w, c0, y.H, y.W, gr);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float xh = (v[i] - mean[i]) * rstd[i];
+        const float dz = gr[i] * act_grad(xh, act);
+        v[i] = rstd[i] * (dz - m1[i] - xh * m2[i]);
+      }
+      store8(dy.p + n * dy.sN + h * dy.sH + w * dy.sW + c0, v);
+    }
   }
-  store8(dy.p + n * dy.sN + h * dy.sH + w * dy.sW + c0, v);
 }
 
 // ------------------------------------------------------------------------------------------ head / losses
@@ -634,9 +660,11 @@ void bias_grad(const TensorDesc& dy, int C, float* gbias, cudaStream_t st) {
 void in_apply(const TensorDesc& y, const float2* stats, int act, const TensorDesc* residual, const TensorDesc& out,
               cudaStream_t st) {
   CGB_CHECK(y.C == out.C && y.H == out.H && y.W == out.W && y.N == out.N, "in_apply: shape mismatch");
-  const long long total = (long long)out.N * (out.H + 2 * out.halo) * (out.W + 2 * out.halo) * (out.C / 8);
-  in_apply_kernel<<<blocks_for(total, 256), 256, 0, st>>>(dev(y), stats, act, residual ? dev(*residual) : dev_null(),
-                                                          dev(out));
+  const int total = (out.H + 2 * out.halo) * (out.W + 2 * out.halo);
+  const int lanes = std::min(256, out.C / 8), rows = 256 / lanes;
+  const int ppt = total >= 16384 ? 8 : 4;  // pixels per thread
+  dim3 grid((total + rows * ppt - 1) / (rows * ppt), out.N);
+  in_apply_kernel<<<grid, 256, 0, st>>>(dev(y), stats, act, residual ? dev(*residual) : dev_null(), dev(out), ppt);
   CGB_CUDA(cudaGetLastError());
 }
 
@@ -654,7 +682,7 @@ void in_bwd_reduce(const TensorDesc& y, const float2* stats, const GradSrc& g, i
   const int HW = y.H * y.W;
   // two pixels per thread: enough CTAs to cover the latency of the gather even at batch 1
   const int lanes = std::min(256, y.C / 8);
-  const int ppb = std::max(2 * (256 / lanes), 8);
+  const int ppb = std::max(4 * (256 / lanes), 16);  // four pixels per thread
   dim3 grid((HW + ppb - 1) / ppb, y.N);
   in_bwd_reduce_kernel<<<grid, 256, 0, st>>>(dev(y), stats, dev(g), act, da_out ? dev(*da_out) : dev_null(),
                                              reinterpret_cast<float*>(bstats), ppb);
@@ -664,8 +692,11 @@ void in_bwd_reduce(const TensorDesc& y, const float2* stats, const GradSrc& g, i
 void in_bwd_apply(const TensorDesc& y, const float2* stats, const float2* bstats, const GradSrc& g, int act,
                   const TensorDesc& dy, cudaStream_t st) {
   check_grad(y, g);
-  const long long total = (long long)y.N * y.H * y.W * (y.C / 8);
-  in_bwd_apply_kernel<<<blocks_for(total, 256), 256, 0, st>>>(dev(y), stats, bstats, dev(g), act, dev(dy));
+  const int total = y.H * y.W;
+  const int lanes = std::min(256, y.C / 8), rows = 256 / lanes;
+  const int ppt = total >= 16384 ? 8 : 4;
+  dim3 grid((total + rows * ppt - 1) / (rows * ppt), y.N);
+  in_bwd_apply_kernel<<<grid, 256, 0, st>>>(dev(y), stats, bstats, dev(g), act, dev(dy), ppt);
   CGB_CUDA(cudaGetLastError());
 }
 

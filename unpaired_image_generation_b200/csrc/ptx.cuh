@@ -20,6 +20,18 @@ __device__ __forceinline__ uint32_t lane_id() {
   return l;
 }
 
+// one lane of a CONVERGED warp (keeps the warp uniform: descriptors and TMA/MMA operands stay in uniform
+// registers instead of being re-broadcast around every asynchronous instruction)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -59,6 +71,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 #endif
+}
+
+// Long waits (epilogue warps waiting for the whole main loop): let the hardware suspend the thread instead of
+// spinning, so the polling warps do not steal issue slots from the producer / MMA warps on their sub-partition.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  uint32_t spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+        : "memory");
+    if (ok) break;
+    __nanosleep(256);
+#ifndef CGB_UNBOUNDED_WAIT
+    if (++spins > (1u << 22)) {
+      printf("cgb: relaxed mbarrier wait timeout block(%d,%d,%d) thread %d\n", blockIdx.x, blockIdx.y, blockIdx.z,
+             threadIdx.x);
+      __trap();
+    }
+#endif
+  }
 }
 
 // ---------------------------------------------------------------- TMA
@@ -187,6 +224,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(layout_type & 7u) << 61;
   return d;
+}
+// high / low 32-bit halves, for loops that only advance the start address
+__host__ __device__ constexpr uint32_t smem_desc_hi(uint32_t sbo_bytes, uint32_t layout_type) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | ((layout_type & 7u) << 29);
+}
+__device__ __forceinline__ uint64_t smem_desc_join(uint32_t lo, uint32_t hi) {
+  return (static_cast<uint64_t>(hi) << 32) | lo;
 }
 __host__ __device__ constexpr uint32_t swizzle_layout_type(int swizzle_bytes) {
   return swizzle_bytes == 128 ? 2u : swizzle_bytes == 64 ? 4u : swizzle_bytes == 32 ? 6u : 0u;

@@ -281,6 +281,26 @@ static int run_case(const std::string& name, ConvSpec s, int N, int H, int W, in
     float ms;
     cudaEventElapsedTime(&ms, e0, e1);
     printf("  fprop: %.2f us/launch, %.1f TFLOP/s (algorithmic)\n", ms / reps * 1e3, p.flops / (ms / reps * 1e-3) * 1e-12);
+    if (getenv("CGB_PROF")) {
+      const int ctas = p.num_tiles * p.n_blocks * p.n_classes;
+      long long* d_prof;
+      CGB_CUDA(cudaMalloc(&d_prof, (size_t)ctas * 16 * sizeof(long long)));
+      CGB_CUDA(cudaMemset(d_prof, 0, (size_t)ctas * 16 * sizeof(long long)));
+      p.args.prof = d_prof;
+      run(p, 0);
+      CGB_CUDA(cudaDeviceSynchronize());
+      std::vector<long long> hp((size_t)ctas * 16);
+      CGB_CUDA(cudaMemcpy(hp.data(), d_prof, hp.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+      double acc[16] = {0};
+      for (int c = 0; c < ctas; ++c)
+        for (int j = 1; j < 16; ++j) acc[j] += (double)(hp[c * 16 + j] - hp[c * 16]);
+      printf("  fprop phases (mean cycles from CTA start over %d CTAs): setup %.0f | first TMA issued %.0f | producer done %.0f | "
+             "MMA issue done %.0f | accumulator ready %.0f | epilogue done %.0f | teardown %.0f\n",
+             ctas, acc[1] / ctas, acc[2] / ctas, acc[3] / ctas, acc[4] / ctas, acc[5] / ctas, acc[6] / ctas, acc[7] / ctas);
+      printf("  epilogue detail: first tmem.ld done %.0f | first chunk math done %.0f | all chunks staged %.0f\n", acc[8] / ctas,
+             acc[9] / ctas, acc[10] / ctas);
+      p.args.prof = nullptr;
+    }
   }
   if (passes & 2) {
     int DH, DW;

@@ -212,6 +212,12 @@ class StepEngine:
                                              ctypes.byref(fl)))
         return ms.value, n.value, fl.value
 
+    def timeline(self) -> str:
+        """pass-boundary timestamps of one graph-replayed step (development profiling)"""
+        buf = ctypes.create_string_buffer(8192)
+        _lib.check(self.lib.cgb_profile_timeline(self._h, _stream(), buf, 8192))
+        return buf.value.decode()
+
     @property
     def launches_per_step(self) -> int:
         return int(self.lib.cgb_launches_per_step(self._h))
