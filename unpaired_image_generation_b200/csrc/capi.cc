@@ -275,7 +275,7 @@ int cgb_profile_kind(cgb_engine_t* e, int kind, int reps, void* stream, float* m
 int cgb_profile_timeline(cgb_engine_t* e, void* stream, char* buf, int buf_cap) {
   CGB_API_BEGIN
   CGB_CHECK(e && e->bound && buf && buf_cap > 0, "bad argument / engine not bound");
-  const std::string t = e->timeline(S(stream));
+  const std::string t = buf_cap < 0 ? std::string() : (std::getenv("CGB_PROFILE_OPS") ? e->profile_ops(S(stream), 5) : e->timeline(S(stream)));
   std::strncpy(buf, t.c_str(), buf_cap - 1);
   buf[buf_cap - 1] = 0;
   CGB_API_END
@@ -352,7 +352,7 @@ int cgb_conv_layer_test(int n, int h, int w, int cin, int cout, int k, int strid
   bf16* arena = static_cast<bf16*>(sc.alloc((size_t)(wf_elems + wt_elems + 1024) * sizeof(bf16)));
   PackEntry pe{};
   pe.src_off = 0; pe.wf_off = 0; pe.wt_off = (wf_elems + 511) / 512 * 512;
-  pe.Cout = cout; pe.Cin = cin; pe.T = T; pe.CinS = s.CinS; pe.CoutS = s.CoutS;
+  pe.Cout = cout; pe.Cin = cin; pe.T = T; pe.CinS = s.CinS; pe.CoutS = s.CoutS; pe.wx_off = -1; pe.wx_pitch = 0;
   PackEntry* d_pe = static_cast<PackEntry*>(sc.alloc(sizeof(PackEntry)));
   CGB_CUDA(cudaMemcpy(d_pe, &pe, sizeof(pe), cudaMemcpyHostToDevice));
   pack_weights(d_master, d_pe, 1, (int)wn, arena, 0);
@@ -416,6 +416,11 @@ int cgb_conv_layer_test(int n, int h, int w, int cin, int cout, int k, int strid
           int* rm = static_cast<int*>(sc.alloc(ps.row_map.size() * sizeof(int)));
           CGB_CUDA(cudaMemcpy(rm, ps.row_map.data(), ps.row_map.size() * sizeof(int), cudaMemcpyHostToDevice));
           ps.gemm.args.row_map = rm;
+        }
+        if (!ps.col_map.empty()) {
+          int* cm = static_cast<int*>(sc.alloc(ps.col_map.size() * sizeof(int)));
+          CGB_CUDA(cudaMemcpy(cm, ps.col_map.data(), ps.col_map.size() * sizeof(int), cudaMemcpyHostToDevice));
+          ps.gemm.args.col_map = cm;
         }
         run(ps, 0);
       }

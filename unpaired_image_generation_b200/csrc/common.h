@@ -89,6 +89,8 @@ struct WgradArgs {
   int split_k;             // number of K splits (gridDim.z)
   float* g;                // [Cout][T][Cin] fp32, accumulated with atomics (must be zeroed)
   const int* row_map;      // optional: GEMM row m -> row of g (row length Cin, T ignored); < 0 = skip
+  const int* col_map;      // optional: GEMM column -> column of g (< 0 = skip); forces the scalar epilogue
+  int ncols;               // GEMM N extent (0: same as Cin)
 };
 
 enum Act { kActNone = 0, kActLeaky = 1, kActTanh = 2, kActRelu = 3 };

@@ -374,7 +374,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n_blocks = (args.Cin + BNW - 1) / BNW;
+  const int ncols = args.ncols > 0 ? args.ncols : args.Cin;
+  const int n_blocks = (ncols + BNW - 1) / BNW;
   const int mblk = blockIdx.x / n_blocks;
   const int nblk = blockIdx.x % n_blocks;
   const WTap tap = args.taps[blockIdx.y];
@@ -469,7 +470,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
     }
     float* grow = args.g + row * args.Cin;
     // rows are 16-byte aligned when Cin % 4 == 0: use 4-wide vector reductions
-    const bool vec_ok = (args.Cin & 3) == 0;
+    const bool vec_ok = (args.Cin & 3) == 0 && args.col_map == nullptr;
     mbar_wait_relaxed(tmem_full_bar, 0);
     tc_fence_after();
 #pragma unroll 1
@@ -490,7 +491,11 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            if (ci0 + j < args.Cin) atomicAdd(grow + ci0 + j, __uint_as_float(r[j]));
+            int cc = ci0 + j;
+            if (cc < ncols) {
+              if (args.col_map != nullptr) cc = __ldg(args.col_map + cc);
+              if (cc >= 0 && cc < args.Cin) atomicAdd(grow + cc, __uint_as_float(r[j]));
+            }
           }
         }
       }
@@ -580,7 +585,7 @@ static void launch_wgrad_t(const CUtensorMap& tmDY, const CUtensorMap& tmX, cons
 
 void launch_wgrad(int BNW, const CUtensorMap& tmDY, const CUtensorMap& tmX, const WgradArgs& args, int m_blocks,
                   cudaStream_t stream) {
-  const int n_blocks = (args.Cin + BNW - 1) / BNW;
+  const int n_blocks = ((args.ncols > 0 ? args.ncols : args.Cin) + BNW - 1) / BNW;
   dim3 grid(m_blocks * n_blocks, args.num_taps, args.split_k);
   switch (BNW) {
     case 256: return launch_wgrad_t<256, 4>(tmDY, tmX, args, grid, stream);

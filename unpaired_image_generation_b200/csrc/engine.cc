@@ -86,6 +86,10 @@ void cgb_engine::build_inventory() {
         poff = align_up(poff + packed_wf_elems(p.spec), 512);
         p.wt_off = poff;
         poff = align_up(poff + packed_wt_elems(p.spec), 512);
+        if (p.spec.Cin <= 4 && p.spec.reflect && p.spec.k == 7) {  // generator stem
+          p.wx_off = poff;
+          poff = align_up(poff + (long long)padded_rows(p.spec.CoutS) * 256, 512);
+        }
       }
     group_numel[g] = off;
     pack_elems[g] = poff;
@@ -179,6 +183,7 @@ void cgb_engine::layout(Arena& A) {
     dxp_img[i] = A.tensor(N, S + 6, S + 6, 16, 0);
     dx_D0[i] = A.tensor(N, S, S, 16, 0);
   }
+  for (int i = 0; i < 4; ++i) xcol[i] = A.tensor(N, S, S, 256, 0);
   for (DisScratch& d : ds) {
     d.dlogits = A.tensor(N, H8 - 2, H8 - 2, 16, 0);
     d.dx3 = A.tensor(N, H8 - 1, H8 - 1, 512, 0);
@@ -285,6 +290,40 @@ std::string cgb_engine::timeline(cudaStream_t st) {
   return out;
 }
 
+// Times every convolution launch of ONE generator pass and one discriminator pass individually (CUDA events,
+// `reps` back-to-back launches each) and returns "name us TFLOP/s" lines.  Development profiling only.
+std::string cgb_engine::profile_ops(cudaStream_t st, int reps) {
+  std::string out;
+  cudaEvent_t e0, e1;
+  CGB_CUDA(cudaEventCreate(&e0));
+  CGB_CUDA(cudaEventCreate(&e1));
+  const Program* progs[3] = {&prog_cycle, &prog_G, &prog_D};
+  std::vector<std::string> seen;
+  for (const Program* p : progs)
+    for (size_t i = 0; i < p->ops.size(); ++i) {
+      if (p->names[i].empty()) continue;
+      bool dup = false;
+      for (const std::string& s : seen) dup = dup || s == p->names[i];
+      if (dup) continue;
+      seen.push_back(p->names[i]);
+      p->ops[i](st);
+      CGB_CUDA(cudaEventRecord(e0, st));
+      for (int r = 0; r < reps; ++r) p->ops[i](st);
+      CGB_CUDA(cudaEventRecord(e1, st));
+      CGB_CUDA(cudaStreamSynchronize(st));
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e0, e1);
+      const double us = ms * 1e3 / reps;
+      char line[200];
+      snprintf(line, sizeof(line), "%-44s %9.2f us %8.1f TFLOP/s\n", p->names[i].c_str(), us,
+               p->flops[i] / (us * 1e-6) * 1e-12);
+      out += line;
+    }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return out;
+}
+
 void* cgb_engine::meta_upload(const void* src, size_t bytes) {
   meta_off = (meta_off + 255) & ~size_t(255);
   CGB_CHECK(meta_off + bytes <= meta_cap, "engine meta buffer exhausted");
@@ -312,7 +351,9 @@ void cgb_engine::record_programs() {
     p.args.kiters = static_cast<const KIter*>(E->meta_upload(p.kiters.data(), p.kiters.size() * sizeof(KIter)));
     E->igemm_plans.push_back(p);
     const IgemmPlan* pp = &E->igemm_plans.back();
+    pr.cur_name = "fprop " + L.name + " BN" + std::to_string(p.BN) + " ctas" + std::to_string(p.num_tiles * p.n_blocks * p.n_classes);
     pr.add([pp](cudaStream_t st) { run(*pp, st); }, 1, kOpIgemm, p.flops);
+    pr.cur_name.clear();
     *fl += p.flops;
   };
   auto add_dgrad = [E](Program& pr, double* fl, const LayerParam& L, const TensorDesc& dy, const TensorDesc& dx) {
@@ -320,28 +361,36 @@ void cgb_engine::record_programs() {
     p.args.kiters = static_cast<const KIter*>(E->meta_upload(p.kiters.data(), p.kiters.size() * sizeof(KIter)));
     E->igemm_plans.push_back(p);
     const IgemmPlan* pp = &E->igemm_plans.back();
+    pr.cur_name = "dgrad " + L.name + " BN" + std::to_string(p.BN) + " ctas" + std::to_string(p.num_tiles * p.n_blocks * p.n_classes);
     pr.add([pp](cudaStream_t st) { run(*pp, st); }, 1, kOpIgemm, p.flops);
+    pr.cur_name.clear();
     *fl += p.flops;
   };
   auto add_wgrad_on_lane = [E](Program& pr, double* fl, const LayerParam& L, const TensorDesc& x, const TensorDesc& dy,
-                               bf16* colbuf, size_t colbuf_elems) {
+                               bf16* colbuf, size_t colbuf_elems, const TensorDesc* precol) {
     float* g = E->G[L.group] + L.w_off;
     if (tc_supports_wgrad(L.spec)) {
       WgradPlan p = plan_wgrad(L.spec, x, dy, g, E->sm_count);
       p.args.taps = static_cast<const WTap*>(E->meta_upload(p.taps.data(), p.taps.size() * sizeof(WTap)));
       E->wgrad_plans.push_back(p);
       const WgradPlan* pp = &E->wgrad_plans.back();
+      pr.cur_name = "wgrad " + L.name + " split" + std::to_string(p.args.split_k);
       pr.add([pp](cudaStream_t st) { run(*pp, st); }, 1, kOpWgradTc, p.flops);
+      pr.cur_name.clear();
       *fl += p.flops;
     } else {
       // 3-/1-channel layers: explicit im2col of the skinny operand, then a plain tensor-core GEMM
-      SmallWgradPlan p = plan_wgrad_small(L.spec, x, dy, g, colbuf, colbuf_elems, E->sm_count);
+      SmallWgradPlan p = plan_wgrad_small(L.spec, x, dy, g, colbuf, colbuf_elems, E->sm_count, precol);
       p.gemm.args.taps = static_cast<const WTap*>(E->meta_upload(p.gemm.taps.data(), p.gemm.taps.size() * sizeof(WTap)));
       if (!p.row_map.empty())
         p.gemm.args.row_map = static_cast<const int*>(E->meta_upload(p.row_map.data(), p.row_map.size() * sizeof(int)));
+      if (!p.col_map.empty())
+        p.gemm.args.col_map = static_cast<const int*>(E->meta_upload(p.col_map.data(), p.col_map.size() * sizeof(int)));
       E->small_wgrad_plans.push_back(p);
       const SmallWgradPlan* pp = &E->small_wgrad_plans.back();
+      pr.cur_name = "wgrad(im2col) " + L.name;
       pr.add([pp](cudaStream_t st) { run(*pp, st); }, 2, kOpWgradDirect, p.flops);
+      pr.cur_name.clear();
       *fl += p.flops;
     }
   };
@@ -370,15 +419,28 @@ void cgb_engine::record_programs() {
   };
 
   // ---------------------------------------------------------------- generator forward
+  // xcol_in: shared im2col4 of `in` (stem as a GEMM) or nullptr (stem as a 49-tap implicit GEMM);
+  // xcol_out: when non-null the im2col4 of the generated image is produced for the pass that consumes it
   auto emit_gen_forward = [&](Program& pr, double* fl, GenPass& P, int net, const TensorDesc& in,
-                              const TensorDesc& out, bool fill_out_halo) {
+                              const TensorDesc& out, bool fill_out_halo, const TensorDesc* xcol_in,
+                              const TensorDesc* xcol_out) {
     P.net = net;
     P.in = in;
     P.out = out;
+    P.xcol = xcol_in;
     const std::vector<LayerParam>& L = E->layers[net];
     float2* st = P.stats;
     pr.add([st, bytes = P.stats_bytes](cudaStream_t s) { CGB_CUDA(cudaMemsetAsync(st, 0, bytes, s)); }, 0, kOpMemset);
-    add_fprop(pr, fl, L[0], in, P.y_stem, kActNone, st + P.stat_off[0]);
+    if (xcol_in) {
+      // stem as a plain GEMM over the im2col4 matrix: K = 256 (49 taps x 4 channels, zero padded)
+      LayerParam Lx = L[0];
+      Lx.name = "stem(gemm)";
+      Lx.spec.Cin = L[0].spec.Cin * L[0].spec.taps(); Lx.spec.CinS = 256; Lx.spec.k = 1; Lx.spec.stride = 1; Lx.spec.pad = 0; Lx.spec.reflect = false;
+      Lx.wf_off = L[0].wx_off;
+      add_fprop(pr, fl, Lx, *xcol_in, P.y_stem, kActNone, st + P.stat_off[0]);
+    } else {
+      add_fprop(pr, fl, L[0], in, P.y_stem, kActNone, st + P.stat_off[0]);
+    }
     add_norm(pr, P.y_stem, st + P.stat_off[0], kActRelu, nullptr, P.a_stem);
     add_fprop(pr, fl, L[1], P.a_stem, P.y_d1, kActNone, st + P.stat_off[1]);
     add_norm(pr, P.y_d1, st + P.stat_off[1], kActRelu, nullptr, P.a_d1);
@@ -396,6 +458,10 @@ void cgb_engine::record_programs() {
     add_norm(pr, P.y_u2, st + P.stat_off[4 + 2 * nb], kActRelu, nullptr, P.a_u2p);
     add_fprop(pr, fl, L[5 + 2 * nb], P.a_u2p, out, kActTanh, nullptr);
     if (fill_out_halo) pr.add([out](cudaStream_t s) { fill_reflect_halo(out, s); });
+    if (xcol_out) {
+      const TensorDesc xc = *xcol_out;
+      pr.add([out, xc](cudaStream_t s) { im2col4(out, 7, 1, +1, -3, true, xc, s); }, 1, kOpNorm);
+    }
   };
 
   // ---------------------------------------------------------------- generator backward
@@ -408,10 +474,10 @@ void cgb_engine::record_programs() {
     const int main_lane = pr.cur_lane, wlane = pr.cur_lane + kPassLanes;
     // weight gradient on the side lane, beside the input gradient of the same layer
     auto add_wgrad = [&](Program& pr_, double* fl_, const LayerParam& Lp, const TensorDesc& x, const TensorDesc& dy,
-                         bf16* colbuf, size_t colbuf_elems) {
+                         bf16* colbuf, size_t colbuf_elems, const TensorDesc* precol = nullptr) {
       pr_.dep(main_lane, wlane);
       pr_.cur_lane = wlane;
-      add_wgrad_on_lane(pr_, fl_, Lp, x, dy, colbuf, colbuf_elems);
+      add_wgrad_on_lane(pr_, fl_, Lp, x, dy, colbuf, colbuf_elems, precol);
       pr_.cur_lane = main_lane;
     };
     // the next layer overwrites the dy buffer: wait for the side lane first
@@ -485,7 +551,7 @@ void cgb_engine::record_programs() {
     g = GradSrc();
     g.g1 = &S.dxF;
     add_in_bwd(pr, P.y_stem, st + P.stat_off[0], bs + P.stat_off[0], g, kActRelu, nullptr, S.dyF);
-    add_wgrad(pr, fl, L[0], P.in, S.dyF, S.colbuf, S.colbuf_elems);
+    add_wgrad(pr, fl, L[0], P.in, S.dyF, S.colbuf, S.colbuf_elems, P.xcol);
     if (dxp_img_out) add_dgrad(pr, fl, L[0], S.dyF, *dxp_img_out);
     pr.dep(wlane, main_lane);
   };
@@ -514,10 +580,10 @@ void cgb_engine::record_programs() {
     float2* bs = D.bstats;
     const int main_lane = pr.cur_lane, wlane = pr.cur_lane + kPassLanes;
     auto add_wgrad = [&](Program& pr_, double* fl_, const LayerParam& Lp, const TensorDesc& x, const TensorDesc& dy,
-                         bf16* colbuf, size_t colbuf_elems) {
+                         bf16* colbuf, size_t colbuf_elems, const TensorDesc* precol = nullptr) {
       pr_.dep(main_lane, wlane);
       pr_.cur_lane = wlane;
-      add_wgrad_on_lane(pr_, fl_, Lp, x, dy, colbuf, colbuf_elems);
+      add_wgrad_on_lane(pr_, fl_, Lp, x, dy, colbuf, colbuf_elems, precol);
       pr_.cur_lane = main_lane;
     };
     auto add_in_bwd = [&](Program& pr_, const TensorDesc& y, const float2* stats, float2* bstats, GradSrc g, int act,
@@ -577,6 +643,10 @@ void cgb_engine::record_programs() {
     const TensorDesc ra = real_A, rb = real_B;
     prog_set_inputs.add([sa, ra](cudaStream_t s) { nchw_to_nhwc(sa, 3, ra, s); });
     prog_set_inputs.add([sb, rb](cudaStream_t s) { nchw_to_nhwc(sb, 3, rb, s); });
+    // one im2col per distinct input image serves the stem forward and the stem weight gradient of every pass
+    const TensorDesc xa = xcol[0], xb = xcol[1];
+    prog_set_inputs.add([ra, xa](cudaStream_t s) { im2col4(ra, 7, 1, +1, -3, true, xa, s); }, 1, kOpNorm);
+    prog_set_inputs.add([rb, xb](cudaStream_t s) { im2col4(rb, 7, 1, +1, -3, true, xb, s); }, 1, kOpNorm);
   }
   // pass order: 0 fake_B = G_AB(real_A), 1 rec_A = G_BA(fake_B), 2 fake_A = G_BA(real_B),
   //             3 rec_B = G_AB(fake_A), 4 idt_A = G_AB(real_B), 5 idt_B = G_BA(real_A)
@@ -586,22 +656,22 @@ void cgb_engine::record_programs() {
     pr.mark("cycle begin");
     pr.fork();
     pr.cur_lane = 0;
-    emit_gen_forward(pr, flops, gen[0], CGB_NET_G_AB, real_A, img[CGB_IMG_FAKE_B], true);
+    emit_gen_forward(pr, flops, gen[0], CGB_NET_G_AB, real_A, img[CGB_IMG_FAKE_B], true, &xcol[0], &xcol[2]);
     pr.mark("fwd fake_B done");
     pr.cur_lane = 1;
-    emit_gen_forward(pr, flops, gen[2], CGB_NET_G_BA, real_B, img[CGB_IMG_FAKE_A], true);
+    emit_gen_forward(pr, flops, gen[2], CGB_NET_G_BA, real_B, img[CGB_IMG_FAKE_A], true, &xcol[1], &xcol[3]);
     pr.mark("fwd fake_A done");
     pr.cur_lane = 2;
-    emit_gen_forward(pr, flops, gen[4], CGB_NET_G_AB, real_B, img[CGB_IMG_IDT_A], false);
+    emit_gen_forward(pr, flops, gen[4], CGB_NET_G_AB, real_B, img[CGB_IMG_IDT_A], false, &xcol[1], nullptr);
     pr.mark("fwd idt_A done");
     pr.cur_lane = 3;
-    emit_gen_forward(pr, flops, gen[5], CGB_NET_G_BA, real_A, img[CGB_IMG_IDT_B], false);
+    emit_gen_forward(pr, flops, gen[5], CGB_NET_G_BA, real_A, img[CGB_IMG_IDT_B], false, &xcol[0], nullptr);
     pr.mark("fwd idt_B done");
     pr.cur_lane = 0;
-    emit_gen_forward(pr, flops, gen[1], CGB_NET_G_BA, fake_B, img[CGB_IMG_REC_A], false);
+    emit_gen_forward(pr, flops, gen[1], CGB_NET_G_BA, fake_B, img[CGB_IMG_REC_A], false, &xcol[2], nullptr);
     pr.mark("fwd rec_A done");
     pr.cur_lane = 1;
-    emit_gen_forward(pr, flops, gen[3], CGB_NET_G_AB, fake_A, img[CGB_IMG_REC_B], false);
+    emit_gen_forward(pr, flops, gen[3], CGB_NET_G_AB, fake_A, img[CGB_IMG_REC_B], false, &xcol[3], nullptr);
     pr.mark("fwd rec_B done");
     pr.join();
     pr.cur_lane = 0;
@@ -691,6 +761,8 @@ void cgb_engine::record_programs() {
         e.T = p.spec.taps();
         e.CinS = p.spec.CinS;
         e.CoutS = p.spec.CoutS;
+        e.wx_off = p.wx_off;
+        e.wx_pitch = 256;
         table.push_back(e);
         max_elems = std::max(max_elems, e.Cout * e.Cin * e.T);
       }
@@ -721,7 +793,7 @@ void cgb_engine::record_programs() {
   segments[CGB_SEG_FORWARD].seq = {&prog_set_inputs, &prog_cycle};
   // ---- module-level forward programs (Generator.forward / Discriminator.forward)
   for (int net = 0; net < 2; ++net) {
-    emit_gen_forward(prog_mod_gen[net], &dummy_flops, gen[6], net, mod_in, mod_out, false);
+    emit_gen_forward(prog_mod_gen[net], &dummy_flops, gen[6], net, mod_in, mod_out, false, nullptr, nullptr);
     emit_dis_forward(prog_mod_dis[net], &dummy_flops, dis[4], 2 + net, mod_in);
   }
 }

@@ -22,6 +22,7 @@ struct LayerParam {
   int net = 0, group = 0;
   long long w_off = 0, b_off = 0;    // element offsets in the group's flat fp32 buffers
   long long wf_off = 0, wt_off = 0;  // element offsets in the group's bf16 pack arena
+  long long wx_off = -1;             // stem only: Wx[Cout][256] for the GEMM over the shared im2col4 matrix
 };
 
 typedef std::function<void(cudaStream_t)> Op;
@@ -37,6 +38,8 @@ struct Program {
   std::vector<Op> ops;
   std::vector<int> kinds, lanes, dep_from;
   std::vector<double> flops;
+  std::vector<std::string> names;  // per op (profiling)
+  std::string cur_name;            // label attached to the ops added next
   long long launches = 0;
   int cur_lane = 0;
   void add(Op op, int n_launches = 1, int kind = kOpOther, double fl = 0.0) {
@@ -45,6 +48,7 @@ struct Program {
     lanes.push_back(cur_lane);
     dep_from.push_back(-1);
     flops.push_back(fl);
+    names.push_back(cur_name);
     launches += n_launches;
   }
   void dep(int from, int to) {
@@ -53,6 +57,7 @@ struct Program {
     lanes.push_back(to);
     dep_from.push_back(from);
     flops.push_back(0.0);
+    names.push_back("");
   }
   // timeline marker (profiling): an external event record on the current lane when `timeline` is set
   std::vector<std::string> labels;
@@ -62,6 +67,7 @@ struct Program {
     lanes.push_back(cur_lane);
     dep_from.push_back((int)labels.size());
     flops.push_back(0.0);
+    names.push_back("");
     labels.push_back(label);
   }
   void fork(int n = kLanes) {
@@ -142,6 +148,7 @@ struct Arena {
 struct GenPass {  // activations of one generator forward pass, kept for its backward
   int net = 0;
   TensorDesc in, out;  // image tensors (not owned)
+  const TensorDesc* xcol = nullptr;  // shared im2col4 matrix of `in` (stem fprop / wgrad as GEMMs), or null
   TensorDesc y_stem, a_stem, y_d1, a_d1, y_d2, y_u1, a_u1, y_u2, a_u2p;
   std::vector<TensorDesc> xp, y1, bp, y2;
   float2* stats = nullptr;   // forward IN statistics of all 5 + 2*nb layers, [layer][N][C]
@@ -203,6 +210,7 @@ struct cgb_engine {
   cgb::GenScratch gs[cgb::kPassLanes];
   cgb::DisScratch ds[2];
   cgb::TensorDesc dxp_img[2], dx_D0[2];  // gradients w.r.t. the fake images (from the cycle passes / from D)
+  cgb::TensorDesc xcol[4];               // im2col4 (7x7 taps x 4 channels -> 256 columns) of real_A, real_B, fake_B, fake_A
 
   // library-owned small tables
   void* meta = nullptr;
@@ -231,6 +239,7 @@ struct cgb_engine {
   void run_segment(int seg, cudaStream_t st);
   void drop_graphs();
   std::string timeline(cudaStream_t st);
+  std::string profile_ops(cudaStream_t st, int reps);
 
   ~cgb_engine();
   void build_inventory();

@@ -512,6 +512,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ master, const Pack
     const bf16 v = __float2bfloat16_rn(master[e.src_off + i]);
     arena[e.wf_off + ((long long)co * e.T + t) * e.CinS + ci] = v;
     arena[e.wt_off + ((long long)ci * e.T + t) * e.CoutS + co] = v;
+    if (e.wx_off >= 0) arena[e.wx_off + (long long)co * e.wx_pitch + t * 4 + ci] = v;
   }
 }
 
@@ -556,36 +557,27 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
-// ------------------------------------------------------------------------------------------ im2col (small C)
-// one thread per (pixel, 8-column chunk of dst)
-__global__ void im2col_small_kernel(DevTensor src, int C, int k, int stride, int sgn, int off, int use_halo,
-                                    DevTensor dst) {
-  const int C8 = dst.C / 8;
-  const long long total = (long long)dst.N * dst.H * dst.W * C8;
+// ------------------------------------------------------------------------------------------ im2col (<= 4 channels)
+// one thread per (pixel, tap): an 8-byte load (channels 0..3) and an 8-byte store; the taps of a pixel are
+// consecutive threads, so stores are contiguous
+__global__ void im2col4_kernel(DevTensor src, int k, int stride, int sgn, int off, int use_halo, DevTensor dst) {
+  const int T = k * k;
+  const long long total = (long long)dst.N * dst.H * dst.W * T;
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int j0 = (idx % C8) * 8;
-  long long r = idx / C8;
+  const int t = idx % T;
+  long long r = idx / T;
   const int w = r % dst.W;
   r /= dst.W;
   const int h = r % dst.H;
   const int n = r / dst.H;
   const int lo = use_halo ? -src.halo : 0;
   const int hiH = src.H + (use_halo ? src.halo : 0), hiW = src.W + (use_halo ? src.halo : 0);
-  float v[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int j = j0 + i;
-    float val = 0.f;
-    if (j < k * k * C) {
-      const int t = j / C, c = j % C;
-      const int sh = h * stride + sgn * (t / k) + off, sw = w * stride + sgn * (t % k) + off;
-      if (sh >= lo && sh < hiH && sw >= lo && sw < hiW)
-        val = __bfloat162float(src.p[n * src.sN + sh * src.sH + sw * src.sW + c]);
-    }
-    v[i] = val;
-  }
-  store8(dst.p + n * dst.sN + h * dst.sH + w * dst.sW + j0, v);
+  const int sh = h * stride + sgn * (t / k) + off, sw = w * stride + sgn * (t % k) + off;
+  uint2 v = make_uint2(0u, 0u);
+  if (sh >= lo && sh < hiH && sw >= lo && sw < hiW)
+    v = *reinterpret_cast<const uint2*>(src.p + n * src.sN + sh * src.sH + sw * src.sW);
+  *reinterpret_cast<uint2*>(dst.p + n * dst.sN + h * dst.sH + w * dst.sW + t * 4) = v;
 }
 
 // ------------------------------------------------------------------------------------------ direct wgrad
@@ -747,12 +739,11 @@ void adam_step(float* p, const float* g, float* m, float* v, long long n, float 
   CGB_CUDA(cudaGetLastError());
 }
 
-void im2col_small(const TensorDesc& src, int C, int k, int stride, int sgn, int off, bool use_halo,
-                  const TensorDesc& dst, cudaStream_t st) {
-  CGB_CHECK(dst.C % 8 == 0 && dst.C >= k * k * C && dst.halo == 0, "im2col_small: bad destination");
-  const long long total = (long long)dst.N * dst.H * dst.W * (dst.C / 8);
-  im2col_small_kernel<<<blocks_for(total, 256), 256, 0, st>>>(dev(src), C, k, stride, sgn, off, use_halo ? 1 : 0,
-                                                               dev(dst));
+void im2col4(const TensorDesc& src, int k, int stride, int sgn, int off, bool use_halo, const TensorDesc& dst,
+             cudaStream_t st) {
+  CGB_CHECK(src.C >= 4 && dst.C >= 4 * k * k && dst.halo == 0, "im2col4: bad source / destination");
+  const long long total = (long long)dst.N * dst.H * dst.W * k * k;
+  im2col4_kernel<<<blocks_for(total, 256), 256, 0, st>>>(dev(src), k, stride, sgn, off, use_halo ? 1 : 0, dev(dst));
   CGB_CUDA(cudaGetLastError());
 }
 

@@ -59,6 +59,8 @@ struct PackEntry {
   long long src_off;  // offset (elements) of the fp32 master weight [Cout][T][Cin] in the flat buffer
   long long wf_off;   // offset (elements) into the bf16 pack arena of Wf [CoutP][T][CinS]
   long long wt_off;   // offset of Wt [CinP][T][CoutS]
+  long long wx_off;   // >= 0: extra pack Wx[Cout][wx_pitch] with column t*4 + ci (GEMM over an im2col4 matrix)
+  int wx_pitch;
   int Cout, Cin, T, CinS, CoutS;
   int pad;
 };
@@ -72,13 +74,13 @@ void pack_weights(const float* master, const PackEntry* entries_dev, int n_entri
 void adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                float eps, int* step_dev, float* hyper_dev, float grad_scale, cudaStream_t st);
 
-// ---- explicit im2col of a 16-stored-channel tensor (the 3- and 1-channel sides of stem / head / conv0 /
-// conv4), so that their weight gradients become plain tensor-core GEMMs:
-//   dst[n][h][w][t*C + c] = src[n][h*stride + sgn*r + off][w*stride + sgn*s + off][c],  t = r*k + s, c < C
+// ---- explicit im2col of a 16-stored-channel tensor with <= 4 real channels (the 3- and 1-channel sides of
+// stem / head / conv0 / conv4), so that those layers become plain tensor-core GEMMs:
+//   dst[n][h][w][t*4 + c] = src[n][h*stride + sgn*r + off][w*stride + sgn*s + off][c],  t = r*k + s, c < 4
 // (zero outside the valid region; with use_halo the reflect halo of src counts as valid).  dst has
-// dst.C >= k*k*C stored channels; the tail is zero-filled.
-void im2col_small(const TensorDesc& src, int C, int k, int stride, int sgn, int off, bool use_halo,
-                  const TensorDesc& dst, cudaStream_t st);
+// dst.C >= 4*k*k stored channels; columns >= 4*k*k are never written (they must be zero-initialised once).
+void im2col4(const TensorDesc& src, int k, int stride, int sgn, int off, bool use_halo, const TensorDesc& dst,
+             cudaStream_t st);
 
 // ---- CUDA-core convolution passes for the 3-channel / 1-channel layers ------------------------
 // g[Cout][T][Cin] += sum_pixels dy * x   (x may carry a reflect halo == pad; zero padding otherwise)

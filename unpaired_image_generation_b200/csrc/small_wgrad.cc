@@ -4,59 +4,71 @@
 
 namespace cgb {
 
-static int col_width(int n) { return n <= 64 ? 64 : 256; }
+int im2col4_width(int taps) { return taps * 4 <= 64 ? 64 : 256; }
 
 size_t small_wgrad_col_elems(const ConvSpec& s, const TensorDesc& x, const TensorDesc& dy) {
-  const int T = s.taps();
-  if (s.Cin <= 16) return (size_t)dy.N * dy.H * dy.W * col_width(T * s.Cin);
+  const int Kp = im2col4_width(s.taps());
+  if (s.Cin <= 16) return (size_t)dy.N * dy.H * dy.W * Kp;
   const int halo = s.reflect ? x.halo : 0;
-  return (size_t)x.N * (x.H + 2 * halo) * (x.W + 2 * halo) * col_width(T * s.Cout);
+  return (size_t)x.N * (x.H + 2 * halo) * (x.W + 2 * halo) * Kp;
 }
 
 SmallWgradPlan plan_wgrad_small(const ConvSpec& s, const TensorDesc& x, const TensorDesc& dy, float* g, bf16* colbuf,
-                                size_t colbuf_elems, int sm_count) {
+                                size_t colbuf_elems, int sm_count, const TensorDesc* precomputed_col) {
   CGB_CHECK(!s.transposed, "small-channel transposed convs are not part of the model");
-  CGB_CHECK(s.Cin <= 16 || s.Cout <= 16, "plan_wgrad_small is for 3-/1-channel layers");
-  CGB_CHECK(small_wgrad_col_elems(s, x, dy) <= colbuf_elems, "im2col scratch too small");
+  CGB_CHECK(s.Cin <= 4 || s.Cout <= 4, "plan_wgrad_small is for 3-/1-channel layers");
   SmallWgradPlan p;
   const int T = s.taps();
+  const int Kp = im2col4_width(T);
+  CGB_CHECK(T * 4 <= Kp, "im2col row too long");
   p.flops = 2.0 * dy.N * (double)dy.H * dy.W * s.Cout * s.Cin * T;
   ConvSpec s1;
   s1.k = 1;
   s1.stride = 1;
   s1.pad = 0;
   p.k = s.k;
-  p.col.ptr = colbuf;
-  p.col.halo = 0;
-  if (s.Cin <= 16) {
-    // im2col on the input side: g[co][(t, ci)] = sum_px dy[px][co] * col[px][(t, ci)]
-    const int Kp = col_width(T * s.Cin);
-    CGB_CHECK(T * s.Cin <= Kp, "im2col row too long");
-    p.col.N = dy.N; p.col.H = dy.H; p.col.W = dy.W; p.col.C = Kp;
-    p.src = x; p.C = s.Cin; p.stride = s.stride; p.sgn = +1; p.off = -s.pad; p.use_halo = s.reflect;
-    s1.Cin = T * s.Cin; s1.CinS = Kp; s1.Cout = s.Cout; s1.CoutS = s.CoutS;
+  if (s.Cin <= 4) {
+    // im2col on the input side: g[co][(t, ci)] = sum_px dy[px][co] * col[px][t*4 + ci]
+    if (precomputed_col) {
+      p.col = *precomputed_col;
+      p.col_is_precomputed = true;
+      CGB_CHECK(p.col.N == dy.N && p.col.H == dy.H && p.col.W == dy.W && p.col.C == Kp, "precomputed im2col shape");
+    } else {
+      CGB_CHECK(small_wgrad_col_elems(s, x, dy) <= colbuf_elems, "im2col scratch too small");
+      p.col.ptr = colbuf; p.col.halo = 0;
+      p.col.N = dy.N; p.col.H = dy.H; p.col.W = dy.W; p.col.C = Kp;
+    }
+    p.src = x; p.stride = s.stride; p.sgn = +1; p.off = -s.pad; p.use_halo = s.reflect;
+    s1.Cin = Kp; s1.CinS = Kp; s1.Cout = s.Cout; s1.CoutS = s.CoutS;
     p.gemm = plan_wgrad(s1, p.col, dy, g, sm_count);
+    p.gemm.args.Cin = T * s.Cin;  // row length of g
+    p.gemm.args.ncols = Kp;
+    p.col_map.assign(Kp, -1);
+    for (int j = 0; j < T * 4; ++j)
+      if (j % 4 < s.Cin) p.col_map[j] = (j / 4) * s.Cin + j % 4;
   } else {
-    // im2col on the output-gradient side: g[(t, co)][ci] = sum_px col[px][(t, co)] * x[px][ci]
-    const int Kp = col_width(T * s.Cout);
-    CGB_CHECK(T * s.Cout <= Kp && s.stride == 1, "im2col row too long / strided skinny-output conv");
+    // im2col on the output-gradient side: g[(t, co)][ci] = sum_px col[px][t*4 + co] * x[px][ci]
+    CGB_CHECK(s.stride == 1, "strided skinny-output conv");
+    CGB_CHECK(small_wgrad_col_elems(s, x, dy) <= colbuf_elems, "im2col scratch too small");
     TensorDesc x1 = x;  // pixel domain = input pixels as the conv sees them (padded domain for reflect convs)
     if (s.reflect) {
       x1.H = x.H + 2 * x.halo; x1.W = x.W + 2 * x.halo; x1.halo = 0;
     }
+    p.col.ptr = colbuf; p.col.halo = 0;
     p.col.N = x1.N; p.col.H = x1.H; p.col.W = x1.W; p.col.C = Kp;
-    p.src = dy; p.C = s.Cout; p.stride = 1; p.sgn = -1; p.off = s.reflect ? 0 : s.pad; p.use_halo = false;
-    s1.Cin = s.Cin; s1.CinS = s.CinS; s1.Cout = T * s.Cout; s1.CoutS = Kp;
+    p.src = dy; p.stride = 1; p.sgn = -1; p.off = s.reflect ? 0 : s.pad; p.use_halo = false;
+    s1.Cin = s.Cin; s1.CinS = s.CinS; s1.Cout = Kp; s1.CoutS = Kp;
     p.gemm = plan_wgrad(s1, x1, p.col, g, sm_count);
     p.row_map.assign(Kp, -1);
-    for (int j = 0; j < T * s.Cout; ++j) p.row_map[j] = (j % s.Cout) * T + j / s.Cout;
+    for (int j = 0; j < T * 4; ++j)
+      if (j % 4 < s.Cout) p.row_map[j] = (j % 4) * T + j / 4;
   }
   p.gemm.flops = p.flops;
   return p;
 }
 
 void run(const SmallWgradPlan& p, cudaStream_t stream) {
-  im2col_small(p.src, p.C, p.k, p.stride, p.sgn, p.off, p.use_halo, p.col, stream);
+  if (!p.col_is_precomputed) im2col4(p.src, p.k, p.stride, p.sgn, p.off, p.use_halo, p.col, stream);
   run(p.gemm, stream);
 }
 

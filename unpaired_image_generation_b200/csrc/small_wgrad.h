@@ -11,17 +11,21 @@ namespace cgb {
 
 struct SmallWgradPlan {
   WgradPlan gemm;            // gemm.args.taps / row_map must point at device copies before run()
-  std::vector<int> row_map;  // empty when rows map 1:1
+  std::vector<int> row_map;  // (tap*4 + cout) -> row of g   (im2col on the output-gradient side)
+  std::vector<int> col_map;  // (tap*4 + cin)  -> column of g (im2col on the input side)
   // im2col parameters
   TensorDesc src, col;
-  int C = 0, k = 0, stride = 1, sgn = 1, off = 0;
+  int k = 0, stride = 1, sgn = 1, off = 0;
   bool use_halo = false;
+  bool col_is_precomputed = false;  // the caller keeps `col` up to date (shared stem im2col)
   double flops = 0;
 };
 
 size_t small_wgrad_col_elems(const ConvSpec& s, const TensorDesc& x, const TensorDesc& dy);
+// precomputed_col: an im2col4 matrix of x that the caller maintains (input-side layers only), else nullptr
 SmallWgradPlan plan_wgrad_small(const ConvSpec& s, const TensorDesc& x, const TensorDesc& dy, float* g, bf16* colbuf,
-                                size_t colbuf_elems, int sm_count);
+                                size_t colbuf_elems, int sm_count, const TensorDesc* precomputed_col = nullptr);
+int im2col4_width(int taps);  // stored columns of an im2col4 matrix: 64 or 256
 void run(const SmallWgradPlan& p, cudaStream_t stream);
 
 }  // namespace cgb

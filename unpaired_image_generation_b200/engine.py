@@ -214,8 +214,8 @@ class StepEngine:
 
     def timeline(self) -> str:
         """pass-boundary timestamps of one graph-replayed step (development profiling)"""
-        buf = ctypes.create_string_buffer(8192)
-        _lib.check(self.lib.cgb_profile_timeline(self._h, _stream(), buf, 8192))
+        buf = ctypes.create_string_buffer(65536)
+        _lib.check(self.lib.cgb_profile_timeline(self._h, _stream(), buf, 65536))
         return buf.value.decode()
 
     @property
