@@ -241,8 +241,9 @@ int cgb_train_step_host(cgb_engine_t* e, const float* real_A_host, const float* 
 
 long long cgb_launches_per_step(const cgb_engine_t* e) {
   if (!e || !e->bound) return -1;
-  return e->prog_set_inputs.launches + e->prog_cycle.launches + e->prog_G.launches + e->prog_D.launches +
-         e->prog_adam[0].launches + e->prog_adam[1].launches;
+  long long n = 0;
+  for (const Program* p : e->segments[CGB_SEG_STEP].seq) n += p->launches;
+  return n;
 }
 
 int cgb_profile_kind(cgb_engine_t* e, int kind, int reps, void* stream, float* ms_per_step, long long* launches,

@@ -746,6 +746,85 @@ void cgb_engine::record_programs() {
     pr.cur_lane = 0;
     pr.mark("D phase end");
   }
+  {  // ---- the whole step as one schedule.  Lanes 0/1 carry the critical chains
+     //      fwd fake -> fwd rec -> bwd rec -> bwd fake; lanes 2/3 do the identity passes, the frozen-D input
+     //      gradients and then the entire D phase in the shadow of those chains.
+    Program& pr = prog_step;
+    double sink = 0;  // FLOPs are already accounted by prog_cycle / prog_G / prog_D
+    float* gG = G[CGB_GROUP_G];
+    float* gD = G[CGB_GROUP_D];
+    const size_t gGb = (size_t)group_numel[CGB_GROUP_G] * sizeof(float), gDb = (size_t)group_numel[CGB_GROUP_D] * sizeof(float);
+    float* ls = losses;
+    pr.cur_lane = 0;
+    pr.mark("step begin");
+    pr.add([gG, gGb](cudaStream_t s) { CGB_CUDA(cudaMemsetAsync(gG, 0, gGb, s)); }, 0, kOpMemset);
+    pr.add([gD, gDb](cudaStream_t s) { CGB_CUDA(cudaMemsetAsync(gD, 0, gDb, s)); }, 0, kOpMemset);
+    pr.add([ls](cudaStream_t s) { CGB_CUDA(cudaMemsetAsync(ls, 0, 64 * sizeof(float), s)); }, 0, kOpMemset);
+    pr.fork();
+    pr.cur_lane = 0;
+    emit_gen_forward(pr, &sink, gen[0], CGB_NET_G_AB, real_A, img[CGB_IMG_FAKE_B], true, &xcol[0], &xcol[2]);
+    const int ev_fake_B = pr.record(0);
+    pr.mark("fwd fake_B done");
+    pr.cur_lane = 1;
+    emit_gen_forward(pr, &sink, gen[2], CGB_NET_G_BA, real_B, img[CGB_IMG_FAKE_A], true, &xcol[1], &xcol[3]);
+    const int ev_fake_A = pr.record(1);
+    pr.mark("fwd fake_A done");
+    // identity passes: forward and backward back to back
+    pr.cur_lane = 2;
+    emit_gen_forward(pr, &sink, gen[4], CGB_NET_G_AB, real_B, img[CGB_IMG_IDT_A], false, &xcol[1], nullptr);
+    emit_gen_backward(pr, &sink, gen[4], gs[2], &real_B, cfg.lambda_B * cfg.lambda_idt / numel_img, CGB_LOSS_IDT_A, GradSrc(), nullptr);
+    pr.mark("idt_A fwd+bwd done");
+    pr.cur_lane = 3;
+    emit_gen_forward(pr, &sink, gen[5], CGB_NET_G_BA, real_A, img[CGB_IMG_IDT_B], false, &xcol[0], nullptr);
+    emit_gen_backward(pr, &sink, gen[5], gs[3], &real_A, cfg.lambda_A * cfg.lambda_idt / numel_img, CGB_LOSS_IDT_B, GradSrc(), nullptr);
+    pr.mark("idt_B fwd+bwd done");
+    // cycle passes
+    pr.cur_lane = 0;
+    emit_gen_forward(pr, &sink, gen[1], CGB_NET_G_BA, fake_B, img[CGB_IMG_REC_A], false, &xcol[2], nullptr);
+    emit_gen_backward(pr, &sink, gen[1], gs[0], &real_A, cfg.lambda_A / numel_img, CGB_LOSS_CYCLE_A, GradSrc(), &dxp_img[0]);
+    pr.mark("rec_A fwd+bwd done");
+    pr.cur_lane = 1;
+    emit_gen_forward(pr, &sink, gen[3], CGB_NET_G_AB, fake_A, img[CGB_IMG_REC_B], false, &xcol[3], nullptr);
+    emit_gen_backward(pr, &sink, gen[3], gs[1], &real_B, cfg.lambda_B / numel_img, CGB_LOSS_CYCLE_B, GradSrc(), &dxp_img[1]);
+    pr.mark("rec_B fwd+bwd done");
+    // adversarial terms on the fakes (D frozen), then the whole D phase, on lanes 2/3
+    pr.cur_lane = 2;
+    pr.wait(2, ev_fake_B);
+    emit_dis_forward(pr, &sink, dis[0], CGB_NET_D_A, fake_B);
+    emit_dis_backward(pr, &sink, dis[0], ds[0], 1.f, 1.f, CGB_LOSS_G_A, false, &dx_D0[0]);
+    const int ev_dD_A = pr.record(2);
+    emit_dis_forward(pr, &sink, dis[2], CGB_NET_D_A, real_B);
+    emit_dis_backward(pr, &sink, dis[2], ds[0], 1.f, 0.5f, CGB_LOSS_D_A, true, nullptr);
+    emit_dis_backward(pr, &sink, dis[0], ds[0], 0.f, 0.5f, CGB_LOSS_D_A, true, nullptr);
+    pr.mark("D_A all done");
+    pr.cur_lane = 3;
+    pr.wait(3, ev_fake_A);
+    emit_dis_forward(pr, &sink, dis[1], CGB_NET_D_B, fake_A);
+    emit_dis_backward(pr, &sink, dis[1], ds[1], 1.f, 1.f, CGB_LOSS_G_B, false, &dx_D0[1]);
+    const int ev_dD_B = pr.record(3);
+    emit_dis_forward(pr, &sink, dis[3], CGB_NET_D_B, real_A);
+    emit_dis_backward(pr, &sink, dis[3], ds[1], 1.f, 0.5f, CGB_LOSS_D_B, true, nullptr);
+    emit_dis_backward(pr, &sink, dis[1], ds[1], 0.f, 0.5f, CGB_LOSS_D_B, true, nullptr);
+    pr.mark("D_B all done");
+    // the passes that produced the fakes
+    GradSrc g;
+    g.fold = 3;
+    g.g1 = &dx_D0[0];
+    g.g2 = &dxp_img[0];
+    pr.cur_lane = 0;
+    pr.wait(0, ev_dD_A);
+    emit_gen_backward(pr, &sink, gen[0], gs[0], nullptr, 0.f, -1, g, nullptr);
+    pr.mark("bwd fake_B done");
+    g.g1 = &dx_D0[1];
+    g.g2 = &dxp_img[1];
+    pr.cur_lane = 1;
+    pr.wait(1, ev_dD_B);
+    emit_gen_backward(pr, &sink, gen[2], gs[1], nullptr, 0.f, -1, g, nullptr);
+    pr.mark("bwd fake_A done");
+    pr.join();
+    pr.cur_lane = 0;
+    pr.mark("step end (before Adam)");
+  }
   // ---- optimiser + bf16 weight refresh
   for (int g = 0; g < 2; ++g) {
     std::vector<PackEntry> table;
@@ -785,7 +864,18 @@ void cgb_engine::record_programs() {
         2);
     prog_adam[g].add([p, tb, cnt, mx, arena](cudaStream_t s) { pack_weights(p, tb, cnt, mx, arena, s); });
   }
-  segments[CGB_SEG_STEP].seq = {&prog_set_inputs, &prog_cycle, &prog_G, &prog_adam[0], &prog_D, &prog_adam[1]};
+  {  // both optimisers side by side
+    Program& pr = prog_adams;
+    pr.fork(2);
+    for (int g = 0; g < 2; ++g) {
+      pr.cur_lane = g;
+      for (size_t i = 0; i < prog_adam[g].ops.size(); ++i) pr.add(prog_adam[g].ops[i], 0, prog_adam[g].kinds[i]);
+    }
+    pr.launches = prog_adam[0].launches + prog_adam[1].launches;
+    pr.join(2);
+    pr.cur_lane = 0;
+  }
+  segments[CGB_SEG_STEP].seq = {&prog_set_inputs, &prog_step, &prog_adams};
   segments[CGB_SEG_G].seq = {&prog_set_inputs, &prog_cycle, &prog_G};
   segments[CGB_SEG_D].seq = {&prog_D};
   segments[CGB_SEG_ADAM_G].seq = {&prog_adam[0]};

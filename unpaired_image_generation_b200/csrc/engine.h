@@ -26,7 +26,7 @@ struct LayerParam {
 };
 
 typedef std::function<void(cudaStream_t)> Op;
-enum OpKind { kOpOther = 0, kOpIgemm = 1, kOpWgradTc = 2, kOpWgradDirect = 3, kOpNorm = 4, kOpMemset = 5, kOpDep = 6, kOpMarker = 7, kNumOpKinds = 8 };
+enum OpKind { kOpOther = 0, kOpIgemm = 1, kOpWgradTc = 2, kOpWgradDirect = 3, kOpNorm = 4, kOpMemset = 5, kOpDep = 6, kOpMarker = 7, kOpRecord = 8, kOpWait = 9, kNumOpKinds = 10 };
 constexpr int kLanes = 8;  // parallel graph branches: lanes 0-3 carry independent passes, lane l+4 the weight
                            // gradients of the pass on lane l (wgrad runs beside the dgrad of the same layer)
 constexpr int kPassLanes = 4;
@@ -70,6 +70,26 @@ struct Program {
     names.push_back("");
     labels.push_back(label);
   }
+  // split form of dep(): `int e = record(a)` ... later ... `wait(b, e)`: lane b waits only for what lane a had
+  // issued at the record point
+  int n_records = 0;
+  int record(int lane) {
+    ops.push_back(Op());
+    kinds.push_back(kOpRecord);
+    lanes.push_back(lane);
+    dep_from.push_back(n_records);
+    flops.push_back(0.0);
+    names.push_back("");
+    return n_records++;
+  }
+  void wait(int lane, int record_id) {
+    ops.push_back(Op());
+    kinds.push_back(kOpWait);
+    lanes.push_back(lane);
+    dep_from.push_back(record_id);
+    flops.push_back(0.0);
+    names.push_back("");
+  }
   void fork(int n = kLanes) {
     for (int l = 1; l < n; ++l) dep(0, l);
   }
@@ -78,7 +98,7 @@ struct Program {
   }
   void run(cudaStream_t st) const {
     for (size_t i = 0; i < ops.size(); ++i)
-      if (kinds[i] != kOpDep && kinds[i] != kOpMarker) ops[i](st);
+      if (kinds[i] < kOpDep) ops[i](st);
   }
   // lanes[l] are distinct streams (lane 0 = the caller's); events: one per dep op, created by the caller
   struct Mark {
@@ -88,8 +108,21 @@ struct Program {
   };
   void run_lanes(cudaStream_t* lane_streams, std::vector<cudaEvent_t>& events, size_t* next_event,
                  std::vector<Mark>* timeline = nullptr) const {
+    std::vector<cudaEvent_t> rec(n_records, nullptr);
     for (size_t i = 0; i < ops.size(); ++i) {
-      if (kinds[i] == kOpMarker) {
+      if (kinds[i] == kOpRecord || kinds[i] == kOpWait) {
+        if (kinds[i] == kOpRecord) {
+          if (*next_event >= events.size()) {
+            cudaEvent_t ev;
+            CGB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            events.push_back(ev);
+          }
+          rec[dep_from[i]] = events[(*next_event)++];
+          CGB_CUDA(cudaEventRecord(rec[dep_from[i]], lane_streams[lanes[i]]));
+        } else {
+          CGB_CUDA(cudaStreamWaitEvent(lane_streams[lanes[i]], rec[dep_from[i]], 0));
+        }
+      } else if (kinds[i] == kOpMarker) {
         if (timeline) {
           Mark m;
           m.label = labels[dep_from[i]];
@@ -115,7 +148,7 @@ struct Program {
   // replay only the ops of one kind (profiling; data dependencies are ignored on purpose)
   void run_kind(int kind, cudaStream_t st, long long* count, double* fl) const {
     for (size_t i = 0; i < ops.size(); ++i)
-      if (kinds[i] == kind && kind != kOpDep && kind != kOpMarker) {
+      if (kinds[i] == kind && kind < kOpDep) {
         ops[i](st);
         if (count) ++*count;
         if (fl) *fl += flops[i];
@@ -223,6 +256,8 @@ struct cgb_engine {
   std::deque<cgb::WgradPlan> wgrad_plans;
   std::deque<cgb::SmallWgradPlan> small_wgrad_plans;
   cgb::Program prog_set_inputs, prog_cycle, prog_G, prog_D, prog_adam[2], prog_refresh[2];
+  cgb::Program prog_step;   // forward + G phase + D phase as ONE schedule (no joins between the phases)
+  cgb::Program prog_adams;  // both optimisers side by side
   cgb::Program prog_mod_gen[2], prog_mod_dis[2];
   double conv_flops = 0;  // accumulated while recording prog_cycle/prog_G/prog_D
 
