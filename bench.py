@@ -240,6 +240,18 @@ def run_b200(args):
                 e1.record(tr.stream)
                 torch.cuda.synchronize()
                 seg_ms[name] = e0.elapsed_time(e1) / 5
+            # the FLOP-dominant instantiation: residual-block 3x3 convs (108 of the fprop launches, 83 % of FLOPs)
+            res_fprop = res_dgrad = res_wgrad = None
+            try:
+                os.environ["CGB_PROFILE_OPS"] = "1"
+                txt = eng.timeline()
+                os.environ.pop("CGB_PROFILE_OPS", None)
+                def pick(prefix):
+                    vals = [float(l.split()[-2]) for l in txt.splitlines() if l.startswith(prefix)]
+                    return sum(vals) / len(vals) if vals else None
+                res_fprop, res_dgrad, res_wgrad = pick("fprop res."), pick("dgrad res."), pick("wgrad res.")
+            except Exception:
+                os.environ.pop("CGB_PROFILE_OPS", None)
         achieved = fl_ig / (ms_ig * 1e-3) / 1e12
         roofline = {
             "bound": "tensor", "kernel": "igemm_conv_kernel (tcgen05 implicit-GEMM conv fprop/dgrad, all layer shapes)",
@@ -254,6 +266,8 @@ def run_b200(args):
                 "instnorm_pointwise": {"ms_per_step": ms_pw, "launches": n_pw},
             },
             "segments_ms": seg_ms,
+            "res_block_conv_tflops": {"fprop": res_fprop, "dgrad": res_dgrad, "wgrad": res_wgrad,
+                                      "frac_of_peak_fprop": (res_fprop / peaks["tf_sustained"]) if res_fprop else None},
             "step_conv_tflops": eng.conv_flops_per_step / (ms_step * 1e-3) / 1e12,
             "step_conv_frac_of_peak": eng.conv_flops_per_step / (ms_step * 1e-3) / 1e12 / peaks["tf_sustained"],
         }
@@ -317,7 +331,17 @@ def measure_extra(cgb, torch, batch, size, steps, peaks):
         ms = ev0.elapsed_time(ev1) / steps
         ms_ig, n_ig, fl_ig = eng.profile_kind(1, reps=3)
         ms_wg, n_wg, fl_wg = eng.profile_kind(2, reps=3)
-    return {"batch_per_gpu": batch, "value": batch / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+        res = {}
+        try:
+            os.environ["CGB_PROFILE_OPS"] = "1"
+            txt = eng.timeline()
+            for key, prefix in (("fprop", "fprop res."), ("dgrad", "dgrad res."), ("wgrad", "wgrad res.")):
+                vals = [float(l.split()[-2]) for l in txt.splitlines() if l.startswith(prefix)]
+                res[key] = sum(vals) / len(vals) if vals else None
+        finally:
+            os.environ.pop("CGB_PROFILE_OPS", None)
+    return {"batch_per_gpu": batch, "res_block_conv_tflops": res,
+            "res_block_fprop_frac_of_peak": (res.get("fprop") / peaks["tf_sustained"]) if res.get("fprop") else None, "value": batch / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
             "igemm_tflops": fl_ig / (ms_ig * 1e-3) / 1e12, "igemm_frac_of_peak": fl_ig / (ms_ig * 1e-3) / 1e12 / peaks["tf_sustained"],
             "wgrad_tflops": fl_wg / (ms_wg * 1e-3) / 1e12,
             "step_conv_tflops": eng.conv_flops_per_step / (ms * 1e-3) / 1e12,

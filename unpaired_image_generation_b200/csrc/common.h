@@ -70,6 +70,25 @@ struct IgemmArgs {
   long long* prof;                 // optional [ctas][8] clock64 timestamps (development profiling)
 };
 
+// Geometry of the patch-resident implicit GEMM (conv_patch.cu): the halo'd input patch of a 16 x 8 pixel output
+// tile is fetched ONCE per 64-channel chunk and every filter tap reads it through a shifted UMMA descriptor.
+struct PatchArgs {
+  int k;            // filter taps per side
+  int flip;         // 1: weight tap index = k*k-1 - (py*k + px)  (input gradients walk the filter backwards)
+  int ox, oy;       // patch origin relative to the tile's output origin, in the TMA view's coordinates
+  int chunks;       // 64-channel chunks of the contraction
+  int tap_stride;   // K distance between consecutive filter taps in the packed weights (= stored channels)
+  int PH;           // patch rows (16 + k - 1)
+  int nbox;         // TMA boxes per patch: 1 (whole patch, PW = 8 + k - 1 columns) or k column-shifted 8-wide boxes
+  int box_bytes;    // bytes of one box
+  int patch_bytes;  // bytes reserved per patch in shared memory (multiple of 1024)
+  int row_step;     // descriptor start-address step per patch row    (16-byte units)
+  int col_step;     // descriptor start-address step per patch column (16-byte units)
+  int sbo;          // bytes between consecutive 8-pixel row groups of the M tile
+  int base_offset;  // 1: put (start address >> 7) & 7 into the descriptor's base-offset field
+  int b_stages;     // weight-tile ring depth
+};
+
 // One filter tap of the weight-gradient GEMM: offsets for both operands.
 struct WTap {
   int16_t a_c, a_dx, a_par, a_dy;  // dY side (M = Cout)

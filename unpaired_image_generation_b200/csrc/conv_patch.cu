@@ -1,0 +1,278 @@
+// Patch-resident tcgen05 implicit GEMM for stride-1 convolutions and stride-1 input gradients (sm_100a).
+//
+// igemm_conv_kernel (conv_tc.cu) re-fetches the 128-pixel activation box for every filter tap, so a 3x3 conv
+// pulls 9x (a 7x7 conv 49x) the activation bytes through L2 and the kernel runs at the chip-wide L2 -> SM limit
+// (~6.3 KB/clk), not at the tensor pipe.  Here the halo'd input patch of a 16 x 8 pixel output tile
+// ((16 + k - 1) x (8 + k - 1) pixels x 64 channels, SWIZZLE_128B rows of 128 bytes) is fetched ONCE per channel
+// chunk by one TMA box; every filter tap then reads it in place through a UMMA shared-memory descriptor whose
+// start address is shifted by (py * PW + px) rows and whose stride between 8-pixel row groups is the patch pitch.
+// Only the weights stream per tap.  MT = 2 stacks two M tiles on one CTA (two TMEM accumulators) so each weight
+// stage feeds twice the MMAs.
+//
+// Stand-in counterpart: F.conv2d (stride 1, reflection- or zero-padded) and its input gradient in
+// oracle/cyclegan_standin.py (ResnetBlock convs, generator head, discriminator conv3/conv4).
+//
+// Warp roles (224 threads): warp 0 = weight-tile TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue, warp 6 = patch TMA producer.
+#include "common.h"
+#include "conv_epilogue.cuh"
+#include "conv_tc.h"
+#include "ptx.cuh"
+
+namespace cgb {
+
+using namespace ptx;
+
+namespace {
+constexpr int kPatchMisc = 256 /*barriers*/ + 512 /*tap tables*/ + 1024 /*bias*/;
+constexpr int kPatchMaxBStages = 8;
+constexpr int kPatchSmemMax = 232448;
+}  // namespace
+
+template <int BN, int MT, int KPS>
+__global__ void __launch_bounds__(224, 1)
+igemm_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const IgemmArgs args, const PatchArgs pa) {
+  constexpr int kBBytesTx = BN * 128;
+  constexpr int kBBytes = (kBBytesTx + 1023) / 1024 * 1024;
+  constexpr int kStageBytes = KPS * kBBytes;
+  constexpr int kAcc = BN < 32 ? 32 : BN;  // TMEM columns per accumulator
+  constexpr int kTmemCols = MT * kAcc;
+  static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM allocation must be a power of two <= 512");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int ring_bytes = pa.b_stages * kStageBytes;
+  uint8_t* patches = smem + ring_bytes;
+  uint8_t* misc = patches + 2 * MT * pa.patch_bytes;
+  uint64_t* b_full = reinterpret_cast<uint64_t*>(misc);
+  uint64_t* b_empty = b_full + kPatchMaxBStages;
+  uint64_t* a_full = b_empty + kPatchMaxBStages;
+  uint64_t* a_empty = a_full + 2;
+  uint64_t* tmem_full_bar = a_empty + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint32_t* s_aoff = reinterpret_cast<uint32_t*>(misc + 256);  // per tap: descriptor start offset (16 B units)
+  int32_t* s_bk = reinterpret_cast<int32_t*>(misc + 256 + 256);  // per tap: K offset in the packed weights
+  float* s_bias = reinterpret_cast<float*>(misc + 256 + 512);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nblk = blockIdx.y;
+  long long* prof = args.prof ? args.prof + 16 * (blockIdx.x + gridDim.x * blockIdx.y) : nullptr;
+  if (prof && threadIdx.x == 0) prof[0] = clock64();
+
+  const int T = pa.k * pa.k;
+  const int nbs = (T + KPS - 1) / KPS;  // weight stages per channel chunk
+
+  // CTA -> (image, CTA row, tile column); a CTA row is MT stacked tiles of 16 x 8 output pixels
+  int t = blockIdx.x;
+  const int tw = t % args.tiles_w;
+  t /= args.tiles_w;
+  const int th = t % args.tiles_h;
+  const int n = t / args.tiles_h;
+  const int wo0 = tw * 8, ho0 = th * 16 * MT;
+
+  for (int i = threadIdx.x; i < T; i += blockDim.x) {
+    const int py = i / pa.k, px = i - py * pa.k;
+    s_aoff[i] = (uint32_t)(py * pa.row_step + px * pa.col_step);
+    s_bk[i] = (pa.flip ? T - 1 - i : i) * pa.tap_stride;
+  }
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < pa.b_stages; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_mbar_init();
+  } else if (warp == 1) {
+    tmem_alloc(tmem_ptr, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  if (prof && threadIdx.x == 0) prof[1] = clock64();
+
+  // The producer / MMA loops are executed by ONE thread each and their per-stage instruction latency is on the
+  // critical path of narrow tiles: ring positions and phases are tracked incrementally (no runtime div / mod).
+  if (warp == 6) {
+    // ===================== patch producer =====================
+    uint32_t ph = 1;  // parity to wait for on a_empty: the first pass over the two buffers does not block
+    for (int c = 0; c < pa.chunks; ++c) {
+      const int ca = c & 1;
+      mbar_wait(&a_empty[ca], ph);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&a_full[ca], MT * pa.nbox * pa.box_bytes);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          uint8_t* dst = patches + (ca * MT + mt) * pa.patch_bytes;
+          for (int b = 0; b < pa.nbox; ++b)
+            tma_load_5d(dst + b * pa.box_bytes, &tmA, &a_full[ca], c * 64, wo0 + pa.ox + b, 0,
+                        ho0 + mt * 16 + pa.oy, n);
+        }
+        if (prof && c == 0) prof[2] = clock64();
+      }
+      __syncwarp();
+      if (ca == 1) ph ^= 1;
+    }
+  } else if (warp == 0) {
+    // ===================== weight-tile producer =====================
+    int s = 0;
+    uint32_t ph = 1;
+    uint8_t* sb = smem;
+    for (int c = 0; c < pa.chunks; ++c) {
+      for (int bs = 0; bs < nbs; ++bs) {
+        mbar_wait(&b_empty[s], ph);
+        if (elect_one()) {
+          const int nk = min(KPS, T - bs * KPS);
+          mbar_arrive_expect_tx(&b_full[s], nk * kBBytesTx);
+#pragma unroll
+          for (int j = 0; j < KPS; ++j) {
+            if (j < nk) tma_load_2d(sb + j * kBBytes, &tmB, &b_full[s], s_bk[bs * KPS + j] + c * 64, nblk * BN);
+          }
+        }
+        __syncwarp();
+        sb += kStageBytes;
+        if (++s == pa.b_stages) {
+          s = 0;
+          ph ^= 1;
+          sb = smem;
+        }
+      }
+    }
+    if (prof && lane == 0) prof[3] = clock64();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc_bf16(128, BN < 16 ? 16 : BN, 0, 0);
+    constexpr uint32_t desc_hi_b = smem_desc_hi(1024, 2);
+    const uint32_t desc_hi_a = smem_desc_hi((uint32_t)pa.sbo, 2);
+    const uint32_t lo_ring = smem_u32(smem) >> 4;
+    const uint32_t lo_patch = smem_u32(patches) >> 4;
+    const uint32_t patch_units = (uint32_t)pa.patch_bytes >> 4;
+    int s = 0;
+    uint32_t ph = 0, acc = 0;
+    uint32_t b_lo0 = lo_ring;
+    for (int c = 0; c < pa.chunks; ++c) {
+      const int ca = c & 1;
+      mbar_wait(&a_full[ca], (c >> 1) & 1);
+      const uint32_t a_base = lo_patch + (uint32_t)(ca * MT) * patch_units;
+      for (int bs = 0; bs < nbs; ++bs) {
+        mbar_wait(&b_full[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const int nk = min(KPS, T - bs * KPS);
+#pragma unroll
+          for (int j = 0; j < KPS; ++j) {
+            if (j < nk) {
+              const uint32_t b_lo = b_lo0 + j * (kBBytes >> 4);
+              const uint32_t aoff = s_aoff[bs * KPS + j];
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) {
+                const uint32_t a_lo = a_base + mt * patch_units + aoff;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {  // 4 x (K = 16 channels = 32 bytes inside the swizzle atom)
+                  umma_bf16(tmem_base + mt * kAcc, smem_desc_join(a_lo + 2 * kk, desc_hi_a),
+                            smem_desc_join(b_lo + 2 * kk, desc_hi_b), idesc, (kk == 0 && j == 0) ? acc : 1u);
+                }
+              }
+            }
+          }
+          umma_commit(&b_empty[s]);  // weight slot free once these MMAs retire
+          if (bs == nbs - 1) {
+            umma_commit(&a_empty[ca]);  // ... and the patch buffer after the chunk's last tap
+            if (c == pa.chunks - 1) umma_commit(tmem_full_bar);
+          }
+        }
+        __syncwarp();
+        acc = 1;
+        b_lo0 += kStageBytes >> 4;
+        if (++s == pa.b_stages) {
+          s = 0;
+          ph ^= 1;
+          b_lo0 = lo_ring;
+        }
+      }
+    }
+    if (prof && lane == 0) prof[4] = clock64();
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    if (args.bias != nullptr) {
+      for (int j = threadIdx.x - 64; j < BN; j += 128) {
+        const int co = nblk * BN + j;
+        s_bias[j] = co < args.bias_n ? __ldg(args.bias + co) : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
+    }
+    mbar_wait_relaxed(tmem_full_bar, 0);
+    tc_fence_after();
+    if (prof && threadIdx.x == 64) prof[5] = clock64();
+#pragma unroll 1
+    for (int mt = 0; mt < MT; ++mt) {
+      if (ho0 + mt * 16 >= args.Ho) break;  // ragged CTA row: the stacked tile is entirely outside
+      epilogue_tile<BN>(args, tmem_base + mt * kAcc, smem, s_bias, n, ho0 + mt * 16 + (row >> 3), wo0 + (row & 7), nblk,
+                        args.out_off[0], q, lane, prof);
+    }
+  }
+  if (prof && threadIdx.x == 64) prof[6] = clock64();
+  tc_fence_before();
+  __syncthreads();
+  if (prof && threadIdx.x == 0) prof[7] = clock64();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Host launcher
+// ------------------------------------------------------------------------------------------
+int igemm_patch_kps(int BN) { return BN >= 256 ? 1 : BN >= 64 ? 3 : 7; }
+int igemm_patch_smem_budget() { return kPatchSmemMax - 1024 - kPatchMisc; }
+
+template <int BN, int MT, int KPS>
+static void launch_patch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmArgs& args, const PatchArgs& pa,
+                           dim3 grid, cudaStream_t stream) {
+  constexpr int kBBytes = (BN * 128 + 1023) / 1024 * 1024;
+  static bool configured = false;
+  auto kern = igemm_patch_kernel<BN, MT, KPS>;
+  if (!configured) {
+    CGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPatchSmemMax));
+    configured = true;
+  }
+  CGB_CHECK(pa.b_stages >= 2 && pa.b_stages <= kPatchMaxBStages, "patch igemm: weight ring depth out of range");
+  CGB_CHECK(pa.k * pa.k <= 64, "patch igemm: at most 64 filter taps");
+  const int ring = pa.b_stages * KPS * kBBytes;
+  CGB_CHECK(BN < 64 || ring >= 128 * BN * 2, "patch igemm: weight ring smaller than the epilogue staging area");
+  const int smem = 1024 + ring + 2 * MT * pa.patch_bytes + kPatchMisc;
+  CGB_CHECK(smem <= kPatchSmemMax, "patch igemm: shared memory budget exceeded");
+  kern<<<grid, 224, smem, stream>>>(tmA, tmB, args, pa);
+  CGB_CUDA(cudaGetLastError());
+}
+
+void launch_igemm_patch(int BN, int MT, const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmArgs& args,
+                        const PatchArgs& pa, int num_ctas_m, int n_blocks, cudaStream_t stream) {
+  dim3 grid(num_ctas_m, n_blocks, 1);
+  switch (BN * 10 + MT) {
+    case 2562: return launch_patch_t<256, 2, 1>(tmA, tmB, args, pa, grid, stream);
+    case 2561: return launch_patch_t<256, 1, 1>(tmA, tmB, args, pa, grid, stream);
+    case 1282: return launch_patch_t<128, 2, 3>(tmA, tmB, args, pa, grid, stream);
+    case 1281: return launch_patch_t<128, 1, 3>(tmA, tmB, args, pa, grid, stream);
+    case 642: return launch_patch_t<64, 2, 3>(tmA, tmB, args, pa, grid, stream);
+    case 641: return launch_patch_t<64, 1, 3>(tmA, tmB, args, pa, grid, stream);
+    case 162: return launch_patch_t<16, 2, 7>(tmA, tmB, args, pa, grid, stream);
+    case 161: return launch_patch_t<16, 1, 7>(tmA, tmB, args, pa, grid, stream);
+    default: break;
+  }
+  CGB_CHECK(false, "launch_igemm_patch: unsupported config BN=" + std::to_string(BN) + " MT=" + std::to_string(MT));
+}
+
+}  // namespace cgb

@@ -57,7 +57,7 @@ static int choose_bn(int rows, int bk, long long ctas_per_nblock, int sm_count) 
   // The widest N tile that still yields `target` CTAs.  Wide tiles cost the least SM time per FLOP (the MMA
   // issue loop is paid per K block regardless of N), and the step graph keeps several independent convs in
   // flight, so the target is a fraction of the machine rather than all of it.
-  static const double frac = std::getenv("CGB_CTA_FRAC") ? std::atof(std::getenv("CGB_CTA_FRAC")) : 0.55;
+  static const double frac = std::getenv("CGB_CTA_FRAC") ? std::atof(std::getenv("CGB_CTA_FRAC")) : 0.4;
   const long long target = (long long)(sm_count * frac);
   const int cands[3] = {256, 128, 64};
   for (int bn : cands) {
@@ -126,6 +126,112 @@ static void set_tiles(IgemmPlan& p, int N, int Ho, int Wo) {
   p.args.Ho = Ho;
   p.args.Wo = Wo;
   p.num_tiles = N * p.args.tiles_w * p.args.tiles_h;
+}
+
+// Patch-resident kernel (conv_patch.cu) for a stride-1 conv-like pass over `act` (64-channel chunks):
+// output extent Ho x Wo, patch origin (ox, oy) relative to the output pixel, `flip` walks the filter backwards.
+// Returns false (plan untouched) when the geometry does not fit; the tap-table kernel is used instead.
+static int patch_mode() {
+  static const int mode = std::getenv("CGB_PATCH_MODE") ? std::atoi(std::getenv("CGB_PATCH_MODE")) : 1;
+  return mode;
+}
+
+static bool try_patch(IgemmPlan& p, const TensorDesc& act, bool padded_view, const bf16* w, int rows, int Kw, int k,
+                      int chans, int Ho, int Wo, int ox, int oy, bool flip, int sm_count) {
+  const int mode = patch_mode();
+  if (mode <= 0 || k < 2 || k > 8 || chans % 64 != 0) return false;
+  PatchArgs pa;
+  std::memset(&pa, 0, sizeof(pa));
+  pa.k = k;
+  pa.flip = flip ? 1 : 0;
+  pa.ox = ox;
+  pa.oy = oy;
+  pa.chunks = chans / 64;
+  pa.tap_stride = chans;
+  pa.PH = 16 + k - 1;
+  int box_w;
+  if (mode == 3) {         // k column-shifted 8-wide boxes: every descriptor start is 1024-byte aligned
+    box_w = 8;
+    pa.nbox = k;
+    pa.box_bytes = pa.PH * 8 * 128;
+    pa.patch_bytes = k * pa.box_bytes;
+    pa.row_step = 64;
+    pa.col_step = pa.PH * 64;
+    pa.sbo = 1024;
+  } else {                 // one box; taps start at arbitrary 128-byte rows of it
+    box_w = (mode == 5) ? 16 : 8 + k - 1;  // mode 5: 2048-byte pitch, so SBO is a multiple of the 1024-byte swizzle atom
+    pa.nbox = 1;
+    pa.box_bytes = pa.PH * box_w * 128;
+    pa.patch_bytes = (pa.box_bytes + 1023) / 1024 * 1024;
+    pa.row_step = box_w * 8;
+    pa.col_step = 8;
+    pa.sbo = box_w * 128;
+    pa.base_offset = 0;  // measured on B200: the swizzle XOR uses absolute smem address bits; the base-offset field must stay 0
+  }
+  const int tiles_w = (Wo + 7) / 8, tile_rows = (Ho + 15) / 16;
+  const int prow = padded_rows(rows);
+  static const double frac = std::getenv("CGB_CTA_FRAC") ? std::atof(std::getenv("CGB_CTA_FRAC")) : 0.4;
+  const long long target = (long long)(sm_count * frac);
+  int forced_bn = 0, forced_mt = 0;
+  if (const char* f = std::getenv("CGB_FORCE_BN")) forced_bn = std::atoi(f);
+  if (const char* f = std::getenv("CGB_FORCE_MT")) forced_mt = std::atoi(f);
+  const int bn_cands[3] = {256, 128, 64};
+  int best_bn = 0, best_mt = 0, best_stages = 0;
+  auto fits = [&](int bn, int mt, int* stages) {
+    const int kps = igemm_patch_kps(bn);
+    const int stage = kps * ((bn * 128 + 1023) / 1024 * 1024);
+    const int budget = igemm_patch_smem_budget() - 2 * mt * pa.patch_bytes;
+    int st = budget / stage;
+    if (st > 8) st = 8;
+    if (st < 2) return false;
+    if (bn >= 64 && st * stage < 128 * bn * 2) return false;
+    *stages = st;
+    return true;
+  };
+  if (prow <= 16) {
+    for (int mt : {2, 1}) {
+      int st;
+      if (forced_mt && mt != forced_mt) continue;
+      if (!fits(16, mt, &st)) continue;
+      const long long ctas = (long long)act.N * tiles_w * ((tile_rows + mt - 1) / mt);
+      best_bn = 16, best_mt = mt, best_stages = st;
+      if (ctas >= 4 * target) break;  // short per-tile work: only stack tiles when there are plenty of them
+    }
+  } else {
+    bool done = false;
+    for (int bn : bn_cands) {
+      if (done || prow % bn != 0 || (forced_bn && bn != forced_bn)) continue;
+      for (int mt : {2, 1}) {
+        int st;
+        if (done || (forced_mt && mt != forced_mt)) continue;
+        // stacking wastes a whole tile when the tile-row count is odd (the 66-row padded-domain gradients: 5 rows)
+        if (mt == 2 && !forced_mt && tile_rows % 2 != 0 && tile_rows < 9) continue;
+        if (!fits(bn, mt, &st)) continue;
+        const long long ctas = (long long)act.N * tiles_w * ((tile_rows + mt - 1) / mt) * (prow / bn);
+        best_bn = bn, best_mt = mt, best_stages = st;  // the last (smallest) candidate wins if none reaches the target
+        if (ctas >= target) done = true;
+      }
+    }
+  }
+  if (best_bn == 0) return false;
+  pa.b_stages = best_stages;
+  p.patch = true;
+  p.pargs = pa;
+  p.BN = best_bn;
+  p.MT = best_mt;
+  p.CM = p.CN = 1;
+  p.n_blocks = (prow + p.BN - 1) / p.BN;
+  p.n_classes = 1;
+  p.args.tw_shift = 3;
+  p.args.tiles_w = tiles_w;
+  p.args.tiles_h = (tile_rows + p.MT - 1) / p.MT;  // CTA rows
+  p.args.Ho = Ho;
+  p.args.Wo = Wo;
+  p.num_ctas_m = act.N * tiles_w * p.args.tiles_h;
+  p.num_tiles = p.num_ctas_m;
+  p.tmA = view_s1(act, padded_view, 64, box_w, pa.PH);
+  p.tmB = make_tmap_2d(w, prow, Kw, Kw, 64, p.BN, 128);
+  return true;
 }
 
 IgemmPlan plan_fprop(const ConvSpec& s, const TensorDesc& x, const bf16* wf, const TensorDesc& y, const float* bias,
@@ -221,7 +327,11 @@ IgemmPlan plan_fprop(const ConvSpec& s, const TensorDesc& x, const bf16* wf, con
         p.args.k_count[z] = (int)p.kiters.size() - p.args.k_begin[z];
       }
   }
-  finalize(p, vk, x, wf, s.CoutS, Kw, sm_count);
+  bool patched = false;
+  if (!s.transposed && s.stride == 1 && BK == 64)
+    patched = try_patch(p, x, s.reflect, wf, s.CoutS, Kw, k, s.CinS, Ho, Wo, s.reflect ? 0 : -s.pad,
+                        s.reflect ? 0 : -s.pad, false, sm_count);
+  if (!patched) finalize(p, vk, x, wf, s.CoutS, Kw, sm_count);
   p.flops = 2.0 * x.N * (s.transposed ? (double)x.H * x.W : (double)Ho * Wo) * s.Cout * s.Cin * T;
   return p;
 }
@@ -323,7 +433,14 @@ IgemmPlan plan_dgrad(const ConvSpec& s, const TensorDesc& dy, const bf16* wt, co
     p.args.k_begin[0] = 0;
     p.args.k_count[0] = (int)p.kiters.size();
   }
-  finalize(p, vk, dy, wt, s.CinS, Kw, sm_count);
+  bool patched = false;
+  if (!s.transposed && s.stride == 1 && BK == 64) {
+    // dx[h] = sum_r dy[h + off - r] w[r]: the patch starts at off - (k - 1) and the filter is walked backwards
+    const int off = s.reflect ? 0 : s.pad;
+    patched = try_patch(p, dy, false, wt, s.CinS, Kw, k, s.CoutS, dx.H, dx.W, off - (k - 1), off - (k - 1), true,
+                        sm_count);
+  }
+  if (!patched) finalize(p, vk, dy, wt, s.CinS, Kw, sm_count);
   const double out_px = s.transposed ? (double)dx.H * dx.W : (double)dy.H * dy.W;
   p.flops = 2.0 * dy.N * out_px * s.Cout * s.Cin * T;
   return p;
@@ -400,9 +517,13 @@ WgradPlan plan_wgrad(const ConvSpec& s, const TensorDesc& x, const TensorDesc& d
   const long long base_ctas = (long long)p.m_blocks * ((s.CinS + p.BNW - 1) / p.BNW) * T;
   // split-K so that the launch has about `frac` of a wave of CTAs: long K per CTA amortises the prologue and
   // the fp32 reduction epilogue, and leaves room for the other lanes of the step graph
-  static const double frac = std::getenv("CGB_CTA_FRAC") ? std::atof(std::getenv("CGB_CTA_FRAC")) : 0.85;
+  static const double frac = std::getenv("CGB_WGRAD_FRAC") ? std::atof(std::getenv("CGB_WGRAD_FRAC")) : 0.85;
+  // ... but never shorter than `min_chunks` 64-pixel chunks per CTA: below that the prologue and the fp32
+  // reduction of the 128 x BNW tile dominate (measured at batch 1: split 6 -> 2 on the residual layers is
+  // 7 % faster end to end although the isolated kernel is slower)
+  static const long long min_chunks = std::getenv("CGB_WGRAD_MIN_CHUNKS") ? std::atoll(std::getenv("CGB_WGRAD_MIN_CHUNKS")) : 32;
   long long split = (long long)(sm_count * frac) / base_ctas;
-  split = std::max(1LL, std::min(split, std::max(1LL, total_chunks / 4)));
+  split = std::max(1LL, std::min(split, std::max(1LL, total_chunks / min_chunks)));
   p.args.split_k = (int)split;
   p.flops = 2.0 * x.N * (double)PH * PW * s.Cout * s.Cin * T;
   return p;
@@ -410,6 +531,10 @@ WgradPlan plan_wgrad(const ConvSpec& s, const TensorDesc& x, const TensorDesc& d
 
 void run(const IgemmPlan& p, cudaStream_t stream) {
   CGB_CHECK(p.args.kiters != nullptr, "igemm plan has no device K-iteration table");
+  if (p.patch) {
+    launch_igemm_patch(p.BN, p.MT, p.tmA, p.tmB, p.args, p.pargs, p.num_ctas_m, p.n_blocks, stream);
+    return;
+  }
   for (int z = 0; z < p.n_classes; ++z) CGB_CHECK(p.args.k_count[z] <= 192, "K-iteration table exceeds the smem staging area");
   launch_igemm(p.BN, p.BK, p.CM, p.CN, p.tmA, p.tmB, p.args, p.num_tiles, p.n_blocks, p.n_classes, stream);
 }

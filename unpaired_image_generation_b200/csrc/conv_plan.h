@@ -49,6 +49,11 @@ struct IgemmPlan {
   int CM = 1, CN = 1;         // thread-block cluster (M tiles x N blocks) sharing operands by TMA multicast
   std::vector<KIter> kiters;  // host copy; args.kiters must point at a device copy
   double flops = 0;           // algorithmic 2*MACs (for roofline accounting)
+  // patch-resident variant (conv_patch.cu): stride-1 convs / input gradients with 64-channel chunks
+  bool patch = false;
+  PatchArgs pargs;
+  int MT = 1;                 // stacked 16 x 8 M tiles per CTA
+  int num_ctas_m = 0;
 };
 
 struct WgradPlan {

@@ -190,6 +190,9 @@ static double compare(const char* what, const std::vector<float>& ref, const std
 }
 
 static int run_case(const std::string& name, ConvSpec s, int N, int H, int W, int act, int passes, int force_bn) {
+  // CGB_PASSES: bit mask (1 fprop, 2 dgrad, 4 wgrad) restricting the passes; CGB_TIMING_ONLY: skip the CPU loops
+  if (getenv("CGB_PASSES")) passes &= atoi(getenv("CGB_PASSES"));
+  const bool timing_only = getenv("CGB_TIMING_ONLY") != nullptr;
   printf("case %s: N=%d H=%d W=%d Cin=%d(%d) Cout=%d(%d) k=%d s=%d p=%d reflect=%d transposed=%d\n", name.c_str(), N,
          H, W, s.Cin, s.CinS, s.Cout, s.CoutS, s.k, s.stride, s.pad, (int)s.reflect, (int)s.transposed);
   Host h;
@@ -247,14 +250,16 @@ static int run_case(const std::string& name, ConvSpec s, int N, int H, int W, in
     IgemmPlan p = plan_fprop(s, x, d_wf, y, d_bias, act, sm_count);
     (void)force_bn;
     p.args.kiters = dev_upload(p.kiters);
-    printf("  fprop: BN=%d BK=%d cluster %dx%d tiles=%d nblk=%d classes=%d kiters=%zu\n", p.BN, p.BK, p.CM, p.CN,
-           p.num_tiles, p.n_blocks, p.n_classes, p.kiters.size());
+    printf("  fprop: BN=%d BK=%d cluster %dx%d tiles=%d nblk=%d classes=%d kiters=%zu patch=%d MT=%d bstages=%d\n", p.BN,
+           p.BK, p.CM, p.CN, p.num_tiles, p.n_blocks, p.n_classes, p.kiters.size(), (int)p.patch, p.MT,
+           p.patch ? p.pargs.b_stages : 0);
     run(p, 0);
     CGB_CUDA(cudaDeviceSynchronize());
     std::vector<bf16> yb((size_t)y.elems());
     CGB_CUDA(cudaMemcpy(yb.data(), y.ptr, yb.size() * sizeof(bf16), cudaMemcpyDeviceToHost));
     std::vector<float> ref, got;
-    ref_fprop(h, ref);
+    if (!timing_only) ref_fprop(h, ref);
+    else ref.assign((size_t)N * h.Ho * h.Wo * s.Cout, 0.f);
     for (auto& v : ref) {
       if (act == kActLeaky) v = v > 0 ? v : 0.2f * v;
       if (act == kActTanh) v = std::tanh(v);
@@ -269,7 +274,7 @@ static int run_case(const std::string& name, ConvSpec s, int N, int H, int W, in
         else if (v != 0.f)
           pad_zero = false;
       }
-    if (compare("fprop", ref, got) >= 1e-2 || !pad_zero) ++fails;
+    if (!timing_only && (compare("fprop", ref, got) >= 1e-2 || !pad_zero)) ++fails;
     if (!pad_zero) printf("  fprop: padded channels are not zero -> FAIL\n");
     // timing
     for (int i = 0; i < 3; ++i) run(p, 0);
@@ -305,14 +310,20 @@ static int run_case(const std::string& name, ConvSpec s, int N, int H, int W, in
   if (passes & 2) {
     int DH, DW;
     std::vector<float> ref;
-    ref_dgrad(h, ref, &DH, &DW);
+    if (!timing_only) ref_dgrad(h, ref, &DH, &DW);
+    else {
+      DH = H + 2 * (s.reflect ? s.pad : 0);
+      DW = W + 2 * (s.reflect ? s.pad : 0);
+      ref.assign((size_t)N * DH * DW * s.Cin, 0.f);
+    }
     TensorDesc dx{nullptr, N, DH, DW, s.CinS, 0};
     CGB_CUDA(cudaMalloc(&dx.ptr, dx.elems() * sizeof(bf16)));
     CGB_CUDA(cudaMemset(dx.ptr, 0xFF, dx.elems() * sizeof(bf16)));
     IgemmPlan p = plan_dgrad(s, dy, d_wt, dx, sm_count);
     p.args.kiters = dev_upload(p.kiters);
-    printf("  dgrad: BN=%d BK=%d cluster %dx%d tiles=%d nblk=%d classes=%d kiters=%zu out %dx%d\n", p.BN, p.BK, p.CM,
-           p.CN, p.num_tiles, p.n_blocks, p.n_classes, p.kiters.size(), DH, DW);
+    printf("  dgrad: BN=%d BK=%d cluster %dx%d tiles=%d nblk=%d classes=%d kiters=%zu out %dx%d patch=%d MT=%d bstages=%d\n",
+           p.BN, p.BK, p.CM, p.CN, p.num_tiles, p.n_blocks, p.n_classes, p.kiters.size(), DH, DW, (int)p.patch, p.MT,
+           p.patch ? p.pargs.b_stages : 0);
     run(p, 0);
     CGB_CUDA(cudaDeviceSynchronize());
     std::vector<bf16> db((size_t)dx.elems());
@@ -320,7 +331,7 @@ static int run_case(const std::string& name, ConvSpec s, int N, int H, int W, in
     std::vector<float> got(ref.size());
     for (size_t px = 0; px < (size_t)N * DH * DW; ++px)
       for (int c = 0; c < s.Cin; ++c) got[px * s.Cin + c] = __bfloat162float(db[px * s.CinS + c]);
-    if (compare("dgrad", ref, got) >= 1e-2) ++fails;
+    if (!timing_only && compare("dgrad", ref, got) >= 1e-2) ++fails;
     for (int i = 0; i < 3; ++i) run(p, 0);
     cudaEventRecord(e0);
     const int reps = 20;
@@ -333,7 +344,8 @@ static int run_case(const std::string& name, ConvSpec s, int N, int H, int W, in
   }
   if (passes & 4) {
     std::vector<float> ref;
-    ref_wgrad(h, ref);
+    if (!timing_only) ref_wgrad(h, ref);
+    else ref.assign((size_t)s.Cout * T * s.Cin, 0.f);
     float* d_g = nullptr;
     CGB_CUDA(cudaMalloc(&d_g, ref.size() * sizeof(float)));
     CGB_CUDA(cudaMemset(d_g, 0, ref.size() * sizeof(float)));
@@ -345,7 +357,7 @@ static int run_case(const std::string& name, ConvSpec s, int N, int H, int W, in
     CGB_CUDA(cudaDeviceSynchronize());
     std::vector<float> got(ref.size());
     CGB_CUDA(cudaMemcpy(got.data(), d_g, got.size() * sizeof(float), cudaMemcpyDeviceToHost));
-    if (compare("wgrad", ref, got) >= 1e-2) ++fails;
+    if (!timing_only && compare("wgrad", ref, got) >= 1e-2) ++fails;
     for (int i = 0; i < 3; ++i) run(p, 0);
     cudaEventRecord(e0);
     const int reps = 20;
@@ -379,19 +391,21 @@ int main(int argc, char** argv) {
   const std::string name = argc > 1 ? argv[1] : "res_small";
   const int N = argc > 2 ? atoi(argv[2]) : 1;
   const int force_bn = argc > 3 ? atoi(argv[3]) : 0;
+  const int Hov = argc > 4 ? atoi(argv[4]) : 0;  // spatial extent override (0: the case's default)
+  auto HH = [&](int d) { return Hov ? Hov : d; };
   try {
-    if (name == "res_small") return run_case(name, spec(64, 64, 3, 1, 1, true, false), N, 16, 16, 0, 7, force_bn);
-    if (name == "res") return run_case(name, spec(256, 256, 3, 1, 1, true, false), N, 64, 64, 0, 7, force_bn);
-    if (name == "dconv3") return run_case(name, spec(256, 512, 4, 1, 1, false, false), N, 32, 32, 0, 7, force_bn);
-    if (name == "down") return run_case(name, spec(64, 128, 3, 2, 1, false, false), N, 32, 32, 0, 7, force_bn);
-    if (name == "down2") return run_case(name, spec(128, 256, 3, 2, 1, false, false), N, 128, 128, 0, 7, force_bn);
-    if (name == "dconv1") return run_case(name, spec(64, 128, 4, 2, 1, false, false), N, 32, 32, 0, 7, force_bn);
-    if (name == "up") return run_case(name, spec(256, 128, 3, 2, 1, false, true), N, 16, 16, 0, 7, force_bn);
-    if (name == "up2") return run_case(name, spec(128, 64, 3, 2, 1, false, true), N, 32, 32, 0, 7, force_bn);
-    if (name == "stem") return run_case(name, spec(3, 64, 7, 1, 3, true, false), N, 32, 32, 0, 3, force_bn);
-    if (name == "head") return run_case(name, spec(64, 3, 7, 1, 3, true, false), N, 32, 32, kActTanh, 3, force_bn);
-    if (name == "dconv0") return run_case(name, spec(3, 64, 4, 2, 1, false, false), N, 32, 32, kActLeaky, 3, force_bn);
-    if (name == "dconv4") return run_case(name, spec(512, 1, 4, 1, 1, false, false), N, 31, 31, 0, 3, force_bn);
+    if (name == "res_small") return run_case(name, spec(64, 64, 3, 1, 1, true, false), N, HH(16), HH(16), 0, 7, force_bn);
+    if (name == "res") return run_case(name, spec(256, 256, 3, 1, 1, true, false), N, HH(64), HH(64), 0, 7, force_bn);
+    if (name == "dconv3") return run_case(name, spec(256, 512, 4, 1, 1, false, false), N, HH(32), HH(32), 0, 7, force_bn);
+    if (name == "down") return run_case(name, spec(64, 128, 3, 2, 1, false, false), N, HH(32), HH(32), 0, 7, force_bn);
+    if (name == "down2") return run_case(name, spec(128, 256, 3, 2, 1, false, false), N, HH(128), HH(128), 0, 7, force_bn);
+    if (name == "dconv1") return run_case(name, spec(64, 128, 4, 2, 1, false, false), N, HH(32), HH(32), 0, 7, force_bn);
+    if (name == "up") return run_case(name, spec(256, 128, 3, 2, 1, false, true), N, HH(16), HH(16), 0, 7, force_bn);
+    if (name == "up2") return run_case(name, spec(128, 64, 3, 2, 1, false, true), N, HH(32), HH(32), 0, 7, force_bn);
+    if (name == "stem") return run_case(name, spec(3, 64, 7, 1, 3, true, false), N, HH(32), HH(32), 0, 3, force_bn);
+    if (name == "head") return run_case(name, spec(64, 3, 7, 1, 3, true, false), N, HH(32), HH(32), kActTanh, 3, force_bn);
+    if (name == "dconv0") return run_case(name, spec(3, 64, 4, 2, 1, false, false), N, HH(32), HH(32), kActLeaky, 3, force_bn);
+    if (name == "dconv4") return run_case(name, spec(512, 1, 4, 1, 1, false, false), N, HH(31), HH(31), 0, 3, force_bn);
     printf("unknown case %s\n", name.c_str());
     return 2;
   } catch (const std::exception& e) {
