@@ -397,18 +397,26 @@ void cgb_engine::record_programs() {
   auto add_norm = [](Program& pr, const TensorDesc& y, float2* stats, int act, const TensorDesc* residual,
                      const TensorDesc& out) {
     // statistics were accumulated by the producing conv's epilogue
+    pr.cur_name = "in_apply C" + std::to_string(y.C) + " " + std::to_string(y.H) + "x" + std::to_string(y.W) +
+                  " halo" + std::to_string(out.halo) + (residual ? " +res" : "");
     if (residual) {
       const TensorDesc r = *residual;
       pr.add([y, stats, act, r, out](cudaStream_t st) { in_apply(y, stats, act, &r, out, st); }, 1, kOpNorm);
     } else {
       pr.add([y, stats, act, out](cudaStream_t st) { in_apply(y, stats, act, nullptr, out, st); }, 1, kOpNorm);
     }
+    pr.cur_name.clear();
   };
   // InstanceNorm + activation backward; da_store (engine-owned tensor) receives the assembled gradient
   auto add_in_bwd_raw = [](Program& pr, const TensorDesc& y, const float2* stats, float2* bstats, GradSrc g, int act,
                            const TensorDesc* da_store, const TensorDesc& dy) {
+    const std::string shape = " C" + std::to_string(y.C) + " " + std::to_string(y.H) + "x" + std::to_string(y.W) +
+                              (g.g1 ? " g1" : "") + (g.g2 ? " g2fold" + std::to_string(g.fold) : "") +
+                              (da_store ? " +da" : "");
+    pr.cur_name = "in_bwd_reduce" + shape;
     pr.add([y, stats, bstats, g, act, da_store](cudaStream_t st) { in_bwd_reduce(y, stats, g, act, da_store, bstats, st); },
            1, kOpNorm);
+    pr.cur_name = "in_bwd_apply" + shape;
     GradSrc g2 = g;
     if (da_store) {
       g2 = GradSrc();
@@ -416,6 +424,7 @@ void cgb_engine::record_programs() {
     }
     pr.add([y, stats, bstats, g2, act, dy](cudaStream_t st) { in_bwd_apply(y, stats, bstats, g2, act, dy, st); }, 1,
            kOpNorm);
+    pr.cur_name.clear();
   };
 
   // ---------------------------------------------------------------- generator forward

@@ -61,6 +61,15 @@ __device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
     v[2 * i + 1] = f.y;
   }
 }
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
 __device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
   uint4 u;
   __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
@@ -235,9 +244,39 @@ int pick_pix_per_block(int HW) {
 
 // ------------------------------------------------------------------------------------------ IN apply
 // Block = 256 threads = (C/8 channel lanes) x (pixel rows); a thread keeps ONE 8-channel chunk, so mean / rstd
-// are computed once and reused over `ppt` pixels (grid.x * rows * ppt covers the padded output pixels).
-__global__ void in_apply_kernel(DevTensor y, const float2* __restrict__ stats, int act, DevTensor res, DevTensor out,
-                                int ppt) {
+// are computed once and reused over PPT consecutive pixels.  All PPT loads are issued before the first use
+// (these kernels are latency-bound on small maps and bandwidth-bound on large ones: either way the number of
+// 16-byte loads in flight per thread is what matters).
+struct PixIter {  // walks consecutive pixels of a WP-wide raster without a division per pixel
+  int hp, wp;
+  __device__ __forceinline__ PixIter(int p, int WP) : hp(p / WP), wp(p - (p / WP) * WP) {}
+  __device__ __forceinline__ void next(int WP) {
+    if (++wp == WP) {
+      wp = 0;
+      ++hp;
+    }
+  }
+};
+
+// per-channel affine form of the normalisation: xhat = x * a + b with a = rstd, b = -mean * rstd
+__device__ __forceinline__ void load_norm8(const float2* __restrict__ stats, long long idx, float inv, float (&a)[8],
+                                           float (&b)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; i += 2) {
+    const float4 st = __ldg(reinterpret_cast<const float4*>(stats + idx + i));
+    const float m0 = st.x * inv, m1 = st.z * inv;
+    a[i] = rsqrtf(fmaxf(st.y * inv - m0 * m0, 0.f) + 1e-5f);
+    a[i + 1] = rsqrtf(fmaxf(st.w * inv - m1 * m1, 0.f) + 1e-5f);
+    b[i] = -m0 * a[i];
+    b[i + 1] = -m1 * a[i + 1];
+  }
+}
+
+// Each block walks `ppb` consecutive pixels of one image: per iteration a thread issues PPT loads (x and, when
+// present, the residual) before using any of them.
+template <int PPT>
+__global__ void __launch_bounds__(256)
+in_apply_kernel(DevTensor y, const float2* __restrict__ stats, int act, DevTensor res, DevTensor out, int ppb) {
   const int C8 = out.C / 8;
   const int lanes = C8 < 256 ? C8 : 256;
   const int rows = 256 / lanes;
@@ -246,79 +285,171 @@ __global__ void in_apply_kernel(DevTensor y, const float2* __restrict__ stats, i
   const int HP = out.H + 2 * out.halo, WP = out.W + 2 * out.halo;
   const int total = HP * WP;
   const float inv = 1.f / (float)(y.H * y.W);
+  const int p0 = blockIdx.x * ppb, p1 = min(total, p0 + ppb);
+  if (pr >= rows) return;
   for (int cb = cl; cb < C8; cb += lanes) {
     const int c0 = cb * 8;
-    float mean[8], rstd[8];
+    float a[8], b[8];
+    load_norm8(stats, (long long)n * y.C + c0, inv, a, b);
+#pragma unroll 1
+    for (int pb = p0 + pr * PPT; pb < p1; pb += rows * PPT) {
+      uint4 raw[PPT], rraw[PPT];
+      long long ooff[PPT];
+      bool ok[PPT];
+      PixIter it(pb, WP);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float2 st = __ldg(stats + (long long)n * y.C + c0 + i);
-      mean[i] = st.x * inv;
-      rstd[i] = rsqrtf(fmaxf(st.y * inv - mean[i] * mean[i], 0.f) + 1e-5f);
-    }
-    const int p_begin = (blockIdx.x * rows + pr) * ppt;
-#pragma unroll 4
-    for (int k = 0; k < ppt; ++k) {
-      const int p = p_begin + k;
-      if (p >= total) break;
-      const int hp = p / WP, wp = p - hp * WP;
-      const int h = reflect_idx(hp - out.halo, out.H), w = reflect_idx(wp - out.halo, out.W);
-      float v[8];
-      load8(y.p + n * y.sN + h * y.sH + w * y.sW + c0, v);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = act_fwd((v[i] - mean[i]) * rstd[i], act);
-      if (res.p != nullptr) {
-        float rv[8];
-        load8(res.p + n * res.sN + h * res.sH + w * res.sW + c0, rv);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] += rv[i];
+      for (int k = 0; k < PPT; ++k) {
+        ok[k] = pb + k < p1;
+        const int h = reflect_idx(it.hp - out.halo, out.H), w = reflect_idx(it.wp - out.halo, out.W);
+        ooff[k] = n * out.sN + (long long)(it.hp - out.halo) * out.sH + (long long)(it.wp - out.halo) * out.sW + c0;
+        if (ok[k]) {
+          raw[k] = *reinterpret_cast<const uint4*>(y.p + n * y.sN + h * y.sH + w * y.sW + c0);
+          if (res.p != nullptr)
+            rraw[k] = *reinterpret_cast<const uint4*>(res.p + n * res.sN + h * res.sH + w * res.sW + c0);
+        }
+        it.next(WP);
       }
-      store8(out.p + n * out.sN + (hp - out.halo) * out.sH + (wp - out.halo) * out.sW + c0, v);
+#pragma unroll
+      for (int k = 0; k < PPT; ++k) {
+        if (!ok[k]) continue;
+        float v[8];
+        unpack8(raw[k], v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = act_fwd(fmaf(v[i], a[i], b[i]), act);
+        if (res.p != nullptr) {
+          float rv[8];
+          unpack8(rraw[k], rv);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] += rv[i];
+        }
+        store8(out.p + ooff[k], v);
+      }
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------ IN backward
-__global__ void in_bwd_reduce_kernel(DevTensor y, const float2* __restrict__ stats, DevGrad g, int act, DevTensor da,
-                                     float* __restrict__ bstats, int pix_per_block) {
+// Gradient gather shared by both backward kernels: the main source pixels are loaded for all PPT pixels first;
+// the (rare) mirrored border contributions of a padded-domain gradient are added afterwards.
+template <int PPT>
+struct BwdLoads {
+  uint4 yraw[PPT], g1raw[PPT], g2raw[PPT];
+  int h[PPT], w[PPT];
+  bool ok[PPT];
+};
+
+template <int PPT>
+__device__ __forceinline__ void bwd_issue_loads(const DevTensor& y, const DevGrad& g, int n, int p_begin, int total,
+                                                int c0, BwdLoads<PPT>& L) {
+  PixIter it(p_begin, y.W);
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    L.ok[k] = p_begin + k < total;
+    L.h[k] = it.hp;
+    L.w[k] = it.wp;
+    if (L.ok[k]) {
+      L.yraw[k] = *reinterpret_cast<const uint4*>(y.p + n * y.sN + it.hp * y.sH + it.wp * y.sW + c0);
+      if (g.g1.p != nullptr)
+        L.g1raw[k] = *reinterpret_cast<const uint4*>(g.g1.p + n * g.g1.sN + it.hp * g.g1.sH + it.wp * g.g1.sW + c0);
+      if (g.g2.p != nullptr)
+        L.g2raw[k] = *reinterpret_cast<const uint4*>(g.g2.p + n * g.g2.sN + (it.hp + g.fold) * g.g2.sH +
+                                                      (it.wp + g.fold) * g.g2.sW + c0);
+    }
+    it.next(y.W);
+  }
+}
+
+// gradient w.r.t. the activation for pixel k (fp32), including the folded reflection-halo contributions
+template <int PPT>
+__device__ __forceinline__ void bwd_grad(const DevTensor& y, const DevGrad& g, int n, int c0, const BwdLoads<PPT>& L,
+                                         int k, float (&out)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) out[i] = 0.f;
+  if (g.g1.p != nullptr) {
+    float v[8];
+    unpack8(L.g1raw[k], v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[i] += v[i];
+  }
+  if (g.g2.p != nullptr) {
+    float v[8];
+    unpack8(L.g2raw[k], v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[i] += v[i];
+    const int p = g.fold, h = L.h[k], w = L.w[k], H = y.H, W = y.W;
+    const bool hb = (h >= 1 && h <= p) || (h >= H - 1 - p && h <= H - 2);
+    const bool wb = (w >= 1 && w <= p) || (w >= W - 1 - p && w <= W - 2);
+    if (hb || wb) {  // this pixel is the mirror image of one or three halo pixels
+      const int hm = (h >= 1 && h <= p) ? p - h : 2 * (H - 1) - h + p;
+      const int wm = (w >= 1 && w <= p) ? p - w : 2 * (W - 1) - w + p;
+      const bf16* base = g.g2.p + n * g.g2.sN + c0;
+      if (hb) {
+        load8(base + hm * g.g2.sH + (w + p) * g.g2.sW, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) out[i] += v[i];
+      }
+      if (wb) {
+        load8(base + (h + p) * g.g2.sH + wm * g.g2.sW, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) out[i] += v[i];
+      }
+      if (hb && wb) {
+        load8(base + hm * g.g2.sH + wm * g.g2.sW, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) out[i] += v[i];
+      }
+    }
+  }
+}
+
+template <int PPT>
+__global__ void __launch_bounds__(256)
+in_bwd_reduce_kernel(DevTensor y, const float2* __restrict__ stats, DevGrad g, int act, DevTensor da,
+                     float* __restrict__ bstats, int ppb) {
   const int C8 = y.C / 8;
   const int lanes = C8 < 256 ? C8 : 256;
   const int rows = 256 / lanes;
   const int cl = threadIdx.x % lanes, pr = threadIdx.x / lanes;
   const int n = blockIdx.y;
   const int HW = y.H * y.W;
-  const int p0 = blockIdx.x * pix_per_block;
-  const int p1 = min(HW, p0 + pix_per_block);
   const float inv = 1.f / (float)HW;
+  const int p0 = blockIdx.x * ppb, p1 = min(HW, p0 + ppb);
   __shared__ float red[256 * 16];
   for (int cb = cl; cb < C8; cb += lanes) {
-    float mean[8], rstd[8], s1[8], s2[8];
+    const int c0 = cb * 8;
+    float s1[8], s2[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float2 st = __ldg(stats + (long long)n * y.C + cb * 8 + i);
-      mean[i] = st.x * inv;
-      rstd[i] = rsqrtf(fmaxf(st.y * inv - mean[i] * mean[i], 0.f) + 1e-5f);
-      s1[i] = s2[i] = 0.f;
-    }
+    for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
     if (pr < rows) {
-      for (int p = p0 + pr; p < p1; p += rows) {
-        const int h = p / y.W, w = p % y.W;
-        float v[8], gr[8];
-        load8(y.p + n * y.sN + h * y.sH + w * y.sW + cb * 8, v);
-        load_grad8(g, n, h, w, cb * 8, y.H, y.W, gr);
-        if (da.p != nullptr) {
+      float a[8], b[8];
+      load_norm8(stats, (long long)n * y.C + c0, inv, a, b);
+#pragma unroll 1
+      for (int pb = p0 + pr * PPT; pb < p1; pb += rows * PPT) {
+        BwdLoads<PPT> L;
+        bwd_issue_loads<PPT>(y, g, n, pb, p1, c0, L);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) gr[i] = round_bf16(gr[i]);
-          store8(da.p + n * da.sN + h * da.sH + w * da.sW + cb * 8, gr);
-        }
+        for (int k = 0; k < PPT; ++k) {
+          if (!L.ok[k]) continue;
+          float v[8], gr[8];
+          unpack8(L.yraw[k], v);
+          bwd_grad<PPT>(y, g, n, c0, L, k, gr);
+          if (da.p != nullptr) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float xh = (v[i] - mean[i]) * rstd[i];
-          const float dz = gr[i] * act_grad(xh, act);
-          s1[i] += dz;
-          s2[i] += dz * xh;
+            for (int i = 0; i < 8; ++i) gr[i] = round_bf16(gr[i]);
+            store8(da.p + n * da.sN + L.h[k] * da.sH + L.w[k] * da.sW + c0, gr);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float xh = fmaf(v[i], a[i], b[i]);
+            const float dz = gr[i] * act_grad(xh, act);
+            s1[i] += dz;
+            s2[i] = fmaf(dz, xh, s2[i]);
+          }
         }
       }
     }
+    // reduce across the block's pixel rows through shared memory, then one vector atomic per channel pair
+    // (the launcher keeps the number of blocks per image small: same-address atomics serialise in L2)
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       red[threadIdx.x * 16 + i] = s1[i];
@@ -343,8 +474,10 @@ __global__ void in_bwd_reduce_kernel(DevTensor y, const float2* __restrict__ sta
   }
 }
 
-__global__ void in_bwd_apply_kernel(DevTensor y, const float2* __restrict__ stats, const float2* __restrict__ bstats,
-                                    DevGrad g, int act, DevTensor dy, int ppt) {
+template <int PPT>
+__global__ void __launch_bounds__(256)
+in_bwd_apply_kernel(DevTensor y, const float2* __restrict__ stats, const float2* __restrict__ bstats, DevGrad g,
+                    int act, DevTensor dy, int ppb) {
   const int C8 = y.C / 8;
   const int lanes = C8 < 256 ? C8 : 256;
   const int rows = 256 / lanes;
@@ -352,34 +485,39 @@ __global__ void in_bwd_apply_kernel(DevTensor y, const float2* __restrict__ stat
   const int n = blockIdx.y;
   const int total = y.H * y.W;
   const float inv = 1.f / (float)total;
+  const int p0 = blockIdx.x * ppb, p1 = min(total, p0 + ppb);
+  if (pr >= rows) return;
   for (int cb = cl; cb < C8; cb += lanes) {
     const int c0 = cb * 8;
-    float mean[8], rstd[8], m1[8], m2[8];
+    // dy = rstd * (dz - mean(dz) - xhat * mean(dz * xhat)) = a * dz - c - d * xhat
+    float a[8], b[8], c[8], d[8];
+    load_norm8(stats, (long long)n * y.C + c0, inv, a, b);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float2 st = __ldg(stats + (long long)n * y.C + c0 + i);
-      const float2 bs = __ldg(bstats + (long long)n * y.C + c0 + i);
-      mean[i] = st.x * inv;
-      rstd[i] = rsqrtf(fmaxf(st.y * inv - mean[i] * mean[i], 0.f) + 1e-5f);
-      m1[i] = bs.x * inv;
-      m2[i] = bs.y * inv;
+    for (int i = 0; i < 8; i += 2) {
+      const float4 bs = __ldg(reinterpret_cast<const float4*>(bstats + (long long)n * y.C + c0 + i));
+      c[i] = a[i] * bs.x * inv;
+      d[i] = a[i] * bs.y * inv;
+      c[i + 1] = a[i + 1] * bs.z * inv;
+      d[i + 1] = a[i + 1] * bs.w * inv;
     }
-    const int p_begin = (blockIdx.x * rows + pr) * ppt;
-#pragma unroll 4
-    for (int k = 0; k < ppt; ++k) {
-      const int p = p_begin + k;
-      if (p >= total) break;
-      const int h = p / y.W, w = p - h * y.W;
-      float v[8], gr[8];
-      load8(y.p + n * y.sN + h * y.sH + w * y.sW + c0, v);
-      load_grad8(g, n, h, w, c0, y.H, y.W, gr);
+#pragma unroll 1
+    for (int pb = p0 + pr * PPT; pb < p1; pb += rows * PPT) {
+      BwdLoads<PPT> L;
+      bwd_issue_loads<PPT>(y, g, n, pb, p1, c0, L);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float xh = (v[i] - mean[i]) * rstd[i];
-        const float dz = gr[i] * act_grad(xh, act);
-        v[i] = rstd[i] * (dz - m1[i] - xh * m2[i]);
+      for (int k = 0; k < PPT; ++k) {
+        if (!L.ok[k]) continue;
+        float v[8], gr[8];
+        unpack8(L.yraw[k], v);
+        bwd_grad<PPT>(y, g, n, c0, L, k, gr);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xh = fmaf(v[i], a[i], b[i]);
+          const float dz = gr[i] * act_grad(xh, act);
+          v[i] = fmaf(a[i], dz, -c[i]) - d[i] * xh;
+        }
+        store8(dy.p + n * dy.sN + L.h[k] * dy.sH + L.w[k] * dy.sW + c0, v);
       }
-      store8(dy.p + n * dy.sN + h * dy.sH + w * dy.sW + c0, v);
     }
   }
 }
@@ -649,14 +787,24 @@ void bias_grad(const TensorDesc& dy, int C, float* gbias, cudaStream_t st) {
   CGB_CUDA(cudaGetLastError());
 }
 
+// Streaming kernels: blocks of `ppb` pixels sized for ~8 CTAs per SM over the whole batch (but at least one
+// PPT-batch per pixel row of the block, so small maps still spread over the machine).
+static int stream_ppb(long long pixels, int rows, int ppt, int images) {
+  const int unit = rows * ppt;
+  const long long want_blocks = std::max(1LL, 8LL * 148 / images);
+  long long ppb = (pixels + want_blocks - 1) / want_blocks;
+  ppb = (ppb + unit - 1) / unit * unit;
+  return (int)std::max<long long>(ppb, unit);
+}
+
 void in_apply(const TensorDesc& y, const float2* stats, int act, const TensorDesc* residual, const TensorDesc& out,
               cudaStream_t st) {
   CGB_CHECK(y.C == out.C && y.H == out.H && y.W == out.W && y.N == out.N, "in_apply: shape mismatch");
   const int total = (out.H + 2 * out.halo) * (out.W + 2 * out.halo);
   const int lanes = std::min(256, out.C / 8), rows = 256 / lanes;
-  const int ppt = total >= 16384 ? 8 : 4;  // pixels per thread
-  dim3 grid((total + rows * ppt - 1) / (rows * ppt), out.N);
-  in_apply_kernel<<<grid, 256, 0, st>>>(dev(y), stats, act, residual ? dev(*residual) : dev_null(), dev(out), ppt);
+  const int ppb = stream_ppb(total, rows, 2, out.N);
+  dim3 grid((total + ppb - 1) / ppb, out.N);
+  in_apply_kernel<2><<<grid, 256, 0, st>>>(dev(y), stats, act, residual ? dev(*residual) : dev_null(), dev(out), ppb);
   CGB_CUDA(cudaGetLastError());
 }
 
@@ -672,12 +820,16 @@ void in_bwd_reduce(const TensorDesc& y, const float2* stats, const GradSrc& g, i
                    float2* bstats, cudaStream_t st) {
   check_grad(y, g);
   const int HW = y.H * y.W;
-  // two pixels per thread: enough CTAs to cover the latency of the gather even at batch 1
-  const int lanes = std::min(256, y.C / 8);
-  const int ppb = std::max(4 * (256 / lanes), 16);  // four pixels per thread
+  const int lanes = std::min(256, y.C / 8), rows = 256 / lanes;
+  // every block ends with one atomic per channel on the image's (sum dz, sum dz*xhat) pair: at most 64 blocks
+  // per image (measured: 512 blocks per image made this kernel 19 us on a 2 MB tensor, all of it atomics)
+  const int blocks_per_image = std::min(64, std::max(16, (2 * 148 + y.N - 1) / y.N));
+  const int unit = rows * 2;
+  int ppb = (HW + blocks_per_image - 1) / blocks_per_image;
+  ppb = std::max(unit, (ppb + unit - 1) / unit * unit);
   dim3 grid((HW + ppb - 1) / ppb, y.N);
-  in_bwd_reduce_kernel<<<grid, 256, 0, st>>>(dev(y), stats, dev(g), act, da_out ? dev(*da_out) : dev_null(),
-                                             reinterpret_cast<float*>(bstats), ppb);
+  in_bwd_reduce_kernel<2><<<grid, 256, 0, st>>>(dev(y), stats, dev(g), act, da_out ? dev(*da_out) : dev_null(),
+                                                reinterpret_cast<float*>(bstats), ppb);
   CGB_CUDA(cudaGetLastError());
 }
 
@@ -686,9 +838,9 @@ void in_bwd_apply(const TensorDesc& y, const float2* stats, const float2* bstats
   check_grad(y, g);
   const int total = y.H * y.W;
   const int lanes = std::min(256, y.C / 8), rows = 256 / lanes;
-  const int ppt = total >= 16384 ? 8 : 4;
-  dim3 grid((total + rows * ppt - 1) / (rows * ppt), y.N);
-  in_bwd_apply_kernel<<<grid, 256, 0, st>>>(dev(y), stats, bstats, dev(g), act, dev(dy), ppt);
+  const int ppb = stream_ppb(total, rows, 2, y.N);
+  dim3 grid((total + ppb - 1) / ppb, y.N);
+  in_bwd_apply_kernel<2><<<grid, 256, 0, st>>>(dev(y), stats, bstats, dev(g), act, dev(dy), ppb);
   CGB_CUDA(cudaGetLastError());
 }
 
