@@ -19,6 +19,8 @@
 #include "conv_tc.h"
 #include "ptx.cuh"
 
+#include <cstdlib>
+
 namespace cgb {
 
 using namespace ptx;
@@ -235,8 +237,18 @@ igemm_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 // ------------------------------------------------------------------------------------------
 // Host launcher
 // ------------------------------------------------------------------------------------------
-int igemm_patch_kps(int BN) { return BN >= 256 ? 1 : BN >= 64 ? 3 : 7; }
-int igemm_patch_smem_budget() { return kPatchSmemMax - 1024 - kPatchMisc; }
+// CGB_PATCH_SMEM_KB caps the dynamic shared memory of one CTA (default: all of it); at <= 112 KB two CTAs share an
+// SM, so one CTA's prologue / epilogue overlaps the other's main loop when several convs are in flight.
+static int patch_smem_cap() {
+  static const int cap = std::getenv("CGB_PATCH_SMEM_KB") ? std::atoi(std::getenv("CGB_PATCH_SMEM_KB")) * 1024 : kPatchSmemMax;
+  return cap < kPatchSmemMax ? cap : kPatchSmemMax;
+}
+static bool patch_kps1() {
+  static const bool v = std::getenv("CGB_PATCH_KPS1") != nullptr;
+  return v;
+}
+int igemm_patch_kps(int BN) { return BN >= 256 ? 1 : BN >= 64 ? (patch_kps1() ? 1 : 3) : 7; }
+int igemm_patch_smem_budget() { return patch_smem_cap() - 1024 - kPatchMisc; }
 
 template <int BN, int MT, int KPS>
 static void launch_patch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmArgs& args, const PatchArgs& pa,
@@ -264,10 +276,14 @@ void launch_igemm_patch(int BN, int MT, const CUtensorMap& tmA, const CUtensorMa
   switch (BN * 10 + MT) {
     case 2562: return launch_patch_t<256, 2, 1>(tmA, tmB, args, pa, grid, stream);
     case 2561: return launch_patch_t<256, 1, 1>(tmA, tmB, args, pa, grid, stream);
-    case 1282: return launch_patch_t<128, 2, 3>(tmA, tmB, args, pa, grid, stream);
-    case 1281: return launch_patch_t<128, 1, 3>(tmA, tmB, args, pa, grid, stream);
-    case 642: return launch_patch_t<64, 2, 3>(tmA, tmB, args, pa, grid, stream);
-    case 641: return launch_patch_t<64, 1, 3>(tmA, tmB, args, pa, grid, stream);
+    case 1282: return patch_kps1() ? launch_patch_t<128, 2, 1>(tmA, tmB, args, pa, grid, stream)
+                                   : launch_patch_t<128, 2, 3>(tmA, tmB, args, pa, grid, stream);
+    case 1281: return patch_kps1() ? launch_patch_t<128, 1, 1>(tmA, tmB, args, pa, grid, stream)
+                                   : launch_patch_t<128, 1, 3>(tmA, tmB, args, pa, grid, stream);
+    case 642: return patch_kps1() ? launch_patch_t<64, 2, 1>(tmA, tmB, args, pa, grid, stream)
+                                  : launch_patch_t<64, 2, 3>(tmA, tmB, args, pa, grid, stream);
+    case 641: return patch_kps1() ? launch_patch_t<64, 1, 1>(tmA, tmB, args, pa, grid, stream)
+                                  : launch_patch_t<64, 1, 3>(tmA, tmB, args, pa, grid, stream);
     case 162: return launch_patch_t<16, 2, 7>(tmA, tmB, args, pa, grid, stream);
     case 161: return launch_patch_t<16, 1, 7>(tmA, tmB, args, pa, grid, stream);
     default: break;

@@ -57,7 +57,7 @@ static int choose_bn(int rows, int bk, long long ctas_per_nblock, int sm_count) 
   // The widest N tile that still yields `target` CTAs.  Wide tiles cost the least SM time per FLOP (the MMA
   // issue loop is paid per K block regardless of N), and the step graph keeps several independent convs in
   // flight, so the target is a fraction of the machine rather than all of it.
-  static const double frac = std::getenv("CGB_CTA_FRAC") ? std::atof(std::getenv("CGB_CTA_FRAC")) : 0.4;
+  static const double frac = std::getenv("CGB_CTA_FRAC") ? std::atof(std::getenv("CGB_CTA_FRAC")) : 0.3;
   const long long target = (long long)(sm_count * frac);
   const int cands[3] = {256, 128, 64};
   for (int bn : cands) {
@@ -170,7 +170,7 @@ static bool try_patch(IgemmPlan& p, const TensorDesc& act, bool padded_view, con
   }
   const int tiles_w = (Wo + 7) / 8, tile_rows = (Ho + 15) / 16;
   const int prow = padded_rows(rows);
-  static const double frac = std::getenv("CGB_CTA_FRAC") ? std::atof(std::getenv("CGB_CTA_FRAC")) : 0.4;
+  static const double frac = std::getenv("CGB_CTA_FRAC") ? std::atof(std::getenv("CGB_CTA_FRAC")) : 0.3;
   const long long target = (long long)(sm_count * frac);
   int forced_bn = 0, forced_mt = 0;
   if (const char* f = std::getenv("CGB_FORCE_BN")) forced_bn = std::atoi(f);

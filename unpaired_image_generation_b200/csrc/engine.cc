@@ -104,7 +104,32 @@ void cgb_engine::layout(Arena& A) {
   const int N = cfg.batch, S = cfg.size, nb = cfg.n_blocks;
   const int H2 = S / 2, H4 = S / 4, H8 = S / 8;
   for (int g = 0; g < 2; ++g) pack[g] = static_cast<bf16*>(A.alloc((size_t)pack_elems[g] * sizeof(bf16)));
-  for (int i = 0; i < 8; ++i) img[i] = A.tensor(N, S, S, 16, 3);
+  auto images = [](const TensorDesc& t, int first, int n) {  // view of n consecutive images
+    TensorDesc v = t;
+    v.ptr = t.ptr + (long long)first * t.sN();
+    v.N = n;
+    return v;
+  };
+  // measured on B200 (batch 1: 5.39 ms unpaired vs 5.68 ms paired; batch 8: equal): the paired schedule does 20 %
+  // less kernel work but puts the identity passes on the critical chain, so it is opt-in (CGB_PAIR=1)
+  pair = std::getenv("CGB_PAIR") && std::atoi(std::getenv("CGB_PAIR")) != 0;
+  if (pair) {
+    reals3 = A.tensor(3 * N, S, S, 16, 3);
+    pair_out[0] = A.tensor(2 * N, S, S, 16, 3);  // [fake_B; idt_A]
+    pair_out[1] = A.tensor(2 * N, S, S, 16, 3);  // [fake_A; idt_B]
+    img[CGB_IMG_REAL_A] = images(reals3, 0, N);
+    img[CGB_IMG_REAL_B] = images(reals3, N, N);
+    pair_in[0] = images(reals3, 0, 2 * N);       // [real_A; real_B] -> G_AB
+    pair_in[1] = images(reals3, N, 2 * N);       // [real_B; real_A] -> G_BA
+    img[CGB_IMG_FAKE_B] = images(pair_out[0], 0, N);
+    img[CGB_IMG_IDT_A] = images(pair_out[0], N, N);
+    img[CGB_IMG_FAKE_A] = images(pair_out[1], 0, N);
+    img[CGB_IMG_IDT_B] = images(pair_out[1], N, N);
+    img[CGB_IMG_REC_A] = A.tensor(N, S, S, 16, 3);
+    img[CGB_IMG_REC_B] = A.tensor(N, S, S, 16, 3);
+  } else {
+    for (int i = 0; i < 8; ++i) img[i] = A.tensor(N, S, S, 16, 3);
+  }
   mod_in = A.tensor(N, S, S, 16, 3);
   mod_out = A.tensor(N, S, S, 16, 3);
   for (int i = 0; i < 2; ++i) staging[i] = static_cast<float*>(A.alloc((size_t)N * 3 * S * S * sizeof(float)));
@@ -115,7 +140,10 @@ void cgb_engine::layout(Arena& A) {
   }
 
   gen.resize(7);
-  for (GenPass& P : gen) {
+  for (size_t gi = 0; gi < gen.size(); ++gi) {
+    GenPass& P = gen[gi];
+    // paired schedule: passes 0 / 2 carry 2N images, the identity passes 4 / 5 do not exist
+    const int N = !pair ? cfg.batch : (gi == 0 || gi == 2) ? 2 * cfg.batch : (gi == 4 || gi == 5) ? 0 : cfg.batch;
     P.y_stem = A.tensor(N, S, S, 64, 0);
     P.a_stem = A.tensor(N, S, S, 64, 0);
     P.y_d1 = A.tensor(N, H2, H2, 128, 0);
@@ -164,7 +192,10 @@ void cgb_engine::layout(Arena& A) {
     D.stats = static_cast<float2*>(A.alloc(D.stats_bytes));
     D.bstats = static_cast<float2*>(A.alloc(D.stats_bytes));
   }
-  for (GenScratch& g : gs) {  // one backward scratch set per lane
+  for (int gi = 0; gi < kPassLanes; ++gi) {  // one backward scratch set per lane
+    GenScratch& g = gs[gi];
+    // paired schedule: sets 0 / 1 serve the cycle passes (N images), sets 2 / 3 the paired passes (2N)
+    const int N = (pair && gi >= 2) ? 2 * cfg.batch : cfg.batch;
     g.dpre_head = A.tensor(N, S, S, 16, 0);
     g.dxp_head = A.tensor(N, S + 6, S + 6, 64, 0);
     g.dyF = A.tensor(N, S, S, 64, 0);
@@ -183,7 +214,16 @@ void cgb_engine::layout(Arena& A) {
     dxp_img[i] = A.tensor(N, S + 6, S + 6, 16, 0);
     dx_D0[i] = A.tensor(N, S, S, 16, 0);
   }
-  for (int i = 0; i < 4; ++i) xcol[i] = A.tensor(N, S, S, 256, 0);
+  if (pair) {
+    xcol3 = A.tensor(3 * N, S, S, 256, 0);
+    xcol[0] = images(xcol3, 0, N);
+    xcol[1] = images(xcol3, N, N);
+    pair_xcol[0] = images(xcol3, 0, 2 * N);
+    pair_xcol[1] = images(xcol3, N, 2 * N);
+    for (int i = 2; i < 4; ++i) xcol[i] = A.tensor(N, S, S, 256, 0);
+  } else {
+    for (int i = 0; i < 4; ++i) xcol[i] = A.tensor(N, S, S, 256, 0);
+  }
   for (DisScratch& d : ds) {
     d.dlogits = A.tensor(N, H8 - 2, H8 - 2, 16, 0);
     d.dx3 = A.tensor(N, H8 - 1, H8 - 1, 512, 0);
@@ -474,8 +514,12 @@ void cgb_engine::record_programs() {
   };
 
   // ---------------------------------------------------------------- generator backward
+  // Seeds of the head gradient: L1 against `target` (value into `loss_slot`) and / or the external gradient
+  // `gsrc`.  Paired pass (target2 != nullptr): the first half of the batch is seeded by (target, gsrc), the
+  // second half by the L1 term against target2.
   auto emit_gen_backward = [&](Program& pr, double* fl, GenPass& P, GenScratch& S, const TensorDesc* target,
-                               float l1_scale, int loss_slot, GradSrc gsrc, const TensorDesc* dxp_img_out) {
+                               float l1_scale, int loss_slot, GradSrc gsrc, const TensorDesc* dxp_img_out,
+                               const TensorDesc* target2 = nullptr, float l1_scale2 = 0.f, int loss_slot2 = -1) {
     const std::vector<LayerParam>& L = E->layers[P.net];
     float* Gg = E->G[CGB_GROUP_G];
     float2* st = P.stats;
@@ -497,7 +541,25 @@ void cgb_engine::record_programs() {
     };
     pr.add([bs, bytes = P.stats_bytes](cudaStream_t s) { CGB_CUDA(cudaMemsetAsync(bs, 0, bytes, s)); }, 0, kOpMemset);
     const LayerParam& head = L[5 + 2 * nb];
-    {
+    if (target2) {
+      const int half = P.out.N / 2;
+      auto images = [](const TensorDesc& t, int first, int n) {
+        TensorDesc v = t;
+        v.ptr = t.ptr + (long long)first * t.sN();
+        v.N = n;
+        return v;
+      };
+      const TensorDesc outA = images(P.out, 0, half), outB = images(P.out, half, half);
+      const TensorDesc dpreA = images(S.dpre_head, 0, half), dpreB = images(S.dpre_head, half, half);
+      const TensorDesc tg2 = *target2;
+      float* slot2 = loss_slot2 >= 0 ? E->losses + loss_slot2 : nullptr;
+      CGB_CHECK(target == nullptr, "paired backward: the first half is seeded by an external gradient only");
+      pr.add([outA, gsrc, dpreA](cudaStream_t s) { tanh_bwd(outA, nullptr, 0.f, gsrc, 3, dpreA, nullptr, s); });
+      pr.add([outB, tg2, l1_scale2, dpreB, slot2](cudaStream_t s) { tanh_bwd(outB, &tg2, l1_scale2, GradSrc(), 3, dpreB, slot2, s); });
+      const TensorDesc dpre = S.dpre_head;
+      float* gb = Gg + head.b_off;
+      pr.add([dpre, gb](cudaStream_t s) { bias_grad(dpre, 3, gb, s); });
+    } else {
       const TensorDesc out = P.out, dpre = S.dpre_head;
       float* slot = loss_slot >= 0 ? E->losses + loss_slot : nullptr;
       if (target) {
@@ -652,11 +714,25 @@ void cgb_engine::record_programs() {
     const TensorDesc ra = real_A, rb = real_B;
     prog_set_inputs.add([sa, ra](cudaStream_t s) { nchw_to_nhwc(sa, 3, ra, s); });
     prog_set_inputs.add([sb, rb](cudaStream_t s) { nchw_to_nhwc(sb, 3, rb, s); });
-    // one im2col per distinct input image serves the stem forward and the stem weight gradient of every pass
-    const TensorDesc xa = xcol[0], xb = xcol[1];
-    prog_set_inputs.add([ra, xa](cudaStream_t s) { im2col4(ra, 7, 1, +1, -3, true, xa, s); }, 1, kOpNorm);
-    prog_set_inputs.add([rb, xb](cudaStream_t s) { im2col4(rb, 7, 1, +1, -3, true, xb, s); }, 1, kOpNorm);
+    if (pair) {
+      // [real_A; real_B; real_A]: images 0..2N feed G_AB, images N..3N feed G_BA; one im2col over all three
+      TensorDesc ra2 = reals3;
+      ra2.ptr = reals3.ptr + (long long)2 * N * reals3.sN();
+      ra2.N = N;
+      prog_set_inputs.add([sa, ra2](cudaStream_t s) { nchw_to_nhwc(sa, 3, ra2, s); });
+      const TensorDesc r3 = reals3, x3 = xcol3;
+      prog_set_inputs.add([r3, x3](cudaStream_t s) { im2col4(r3, 7, 1, +1, -3, true, x3, s); }, 1, kOpNorm);
+    } else {
+      // one im2col per distinct input image serves the stem forward and the stem weight gradient of every pass
+      const TensorDesc xa = xcol[0], xb = xcol[1];
+      prog_set_inputs.add([ra, xa](cudaStream_t s) { im2col4(ra, 7, 1, +1, -3, true, xa, s); }, 1, kOpNorm);
+      prog_set_inputs.add([rb, xb](cudaStream_t s) { im2col4(rb, 7, 1, +1, -3, true, xb, s); }, 1, kOpNorm);
+    }
   }
+  // im2col4 of a generated image for the pass that consumes it (paired schedule: the fake half of the pair output)
+  auto add_xcol = [](Program& pr, const TensorDesc& image, const TensorDesc& xc) {
+    pr.add([image, xc](cudaStream_t s) { im2col4(image, 7, 1, +1, -3, true, xc, s); }, 1, kOpNorm);
+  };
   // pass order: 0 fake_B = G_AB(real_A), 1 rec_A = G_BA(fake_B), 2 fake_A = G_BA(real_B),
   //             3 rec_B = G_AB(fake_A), 4 idt_A = G_AB(real_B), 5 idt_B = G_BA(real_A)
   // Independent passes are recorded on different lanes (parallel branches of the step graph).
@@ -664,6 +740,16 @@ void cgb_engine::record_programs() {
     Program& pr = prog_cycle;
     pr.mark("cycle begin");
     pr.fork();
+    if (pair) {
+      pr.cur_lane = 0;
+      emit_gen_forward(pr, flops, gen[0], CGB_NET_G_AB, pair_in[0], pair_out[0], true, &pair_xcol[0], nullptr);
+      add_xcol(pr, fake_B, xcol[2]);
+      pr.mark("fwd fake_B + idt_A done");
+      pr.cur_lane = 1;
+      emit_gen_forward(pr, flops, gen[2], CGB_NET_G_BA, pair_in[1], pair_out[1], true, &pair_xcol[1], nullptr);
+      add_xcol(pr, fake_A, xcol[3]);
+      pr.mark("fwd fake_A + idt_B done");
+    } else {
     pr.cur_lane = 0;
     emit_gen_forward(pr, flops, gen[0], CGB_NET_G_AB, real_A, img[CGB_IMG_FAKE_B], true, &xcol[0], &xcol[2]);
     pr.mark("fwd fake_B done");
@@ -676,6 +762,7 @@ void cgb_engine::record_programs() {
     pr.cur_lane = 3;
     emit_gen_forward(pr, flops, gen[5], CGB_NET_G_BA, real_A, img[CGB_IMG_IDT_B], false, &xcol[0], nullptr);
     pr.mark("fwd idt_B done");
+    }
     pr.cur_lane = 0;
     emit_gen_forward(pr, flops, gen[1], CGB_NET_G_BA, fake_B, img[CGB_IMG_REC_A], false, &xcol[2], nullptr);
     pr.mark("fwd rec_A done");
@@ -699,14 +786,18 @@ void cgb_engine::record_programs() {
     pr.fork();
     // identity passes (L1 seeds), then the adversarial terms (D frozen: input gradients only)
     pr.cur_lane = 2;
-    emit_gen_backward(pr, flops, gen[4], gs[2], &real_B, cfg.lambda_B * cfg.lambda_idt / numel_img, CGB_LOSS_IDT_A, GradSrc(), nullptr);
-    pr.mark("bwd idt_A done");
+    if (!pair) {
+      emit_gen_backward(pr, flops, gen[4], gs[2], &real_B, cfg.lambda_B * cfg.lambda_idt / numel_img, CGB_LOSS_IDT_A, GradSrc(), nullptr);
+      pr.mark("bwd idt_A done");
+    }
     emit_dis_forward(pr, flops, dis[0], CGB_NET_D_A, fake_B);
     emit_dis_backward(pr, flops, dis[0], ds[0], 1.f, 1.f, CGB_LOSS_G_A, false, &dx_D0[0]);
     pr.mark("D_A(fake_B) fwd+dgrad done");
     pr.cur_lane = 3;
-    emit_gen_backward(pr, flops, gen[5], gs[3], &real_A, cfg.lambda_A * cfg.lambda_idt / numel_img, CGB_LOSS_IDT_B, GradSrc(), nullptr);
-    pr.mark("bwd idt_B done");
+    if (!pair) {
+      emit_gen_backward(pr, flops, gen[5], gs[3], &real_A, cfg.lambda_A * cfg.lambda_idt / numel_img, CGB_LOSS_IDT_B, GradSrc(), nullptr);
+      pr.mark("bwd idt_B done");
+    }
     emit_dis_forward(pr, flops, dis[1], CGB_NET_D_B, fake_A);
     emit_dis_backward(pr, flops, dis[1], ds[1], 1.f, 1.f, CGB_LOSS_G_B, false, &dx_D0[1]);
     pr.mark("D_B(fake_A) fwd+dgrad done");
@@ -725,12 +816,20 @@ void cgb_engine::record_programs() {
     g.g2 = &dxp_img[0];
     g.fold = 3;
     pr.cur_lane = 0;
-    emit_gen_backward(pr, flops, gen[0], gs[0], nullptr, 0.f, -1, g, nullptr);
+    if (pair)
+      emit_gen_backward(pr, flops, gen[0], gs[2], nullptr, 0.f, -1, g, nullptr, &real_B,
+                        cfg.lambda_B * cfg.lambda_idt / numel_img, CGB_LOSS_IDT_A);
+    else
+      emit_gen_backward(pr, flops, gen[0], gs[0], nullptr, 0.f, -1, g, nullptr);
     pr.mark("bwd fake_B done");
     g.g1 = &dx_D0[1];
     g.g2 = &dxp_img[1];
     pr.cur_lane = 1;
-    emit_gen_backward(pr, flops, gen[2], gs[1], nullptr, 0.f, -1, g, nullptr);
+    if (pair)
+      emit_gen_backward(pr, flops, gen[2], gs[3], nullptr, 0.f, -1, g, nullptr, &real_A,
+                        cfg.lambda_A * cfg.lambda_idt / numel_img, CGB_LOSS_IDT_B);
+    else
+      emit_gen_backward(pr, flops, gen[2], gs[1], nullptr, 0.f, -1, g, nullptr);
     pr.mark("bwd fake_A done");
     pr.join();
     pr.cur_lane = 0;
@@ -770,13 +869,26 @@ void cgb_engine::record_programs() {
     pr.add([gD, gDb](cudaStream_t s) { CGB_CUDA(cudaMemsetAsync(gD, 0, gDb, s)); }, 0, kOpMemset);
     pr.add([ls](cudaStream_t s) { CGB_CUDA(cudaMemsetAsync(ls, 0, 64 * sizeof(float), s)); }, 0, kOpMemset);
     pr.fork();
+    int ev_fake_B, ev_fake_A;
+    if (pair) {
+      pr.cur_lane = 0;
+      emit_gen_forward(pr, &sink, gen[0], CGB_NET_G_AB, pair_in[0], pair_out[0], true, &pair_xcol[0], nullptr);
+      ev_fake_B = pr.record(0);
+      add_xcol(pr, fake_B, xcol[2]);
+      pr.mark("fwd fake_B + idt_A done");
+      pr.cur_lane = 1;
+      emit_gen_forward(pr, &sink, gen[2], CGB_NET_G_BA, pair_in[1], pair_out[1], true, &pair_xcol[1], nullptr);
+      ev_fake_A = pr.record(1);
+      add_xcol(pr, fake_A, xcol[3]);
+      pr.mark("fwd fake_A + idt_B done");
+    } else {
     pr.cur_lane = 0;
     emit_gen_forward(pr, &sink, gen[0], CGB_NET_G_AB, real_A, img[CGB_IMG_FAKE_B], true, &xcol[0], &xcol[2]);
-    const int ev_fake_B = pr.record(0);
+    ev_fake_B = pr.record(0);
     pr.mark("fwd fake_B done");
     pr.cur_lane = 1;
     emit_gen_forward(pr, &sink, gen[2], CGB_NET_G_BA, real_B, img[CGB_IMG_FAKE_A], true, &xcol[1], &xcol[3]);
-    const int ev_fake_A = pr.record(1);
+    ev_fake_A = pr.record(1);
     pr.mark("fwd fake_A done");
     // identity passes: forward and backward back to back
     pr.cur_lane = 2;
@@ -787,6 +899,7 @@ void cgb_engine::record_programs() {
     emit_gen_forward(pr, &sink, gen[5], CGB_NET_G_BA, real_A, img[CGB_IMG_IDT_B], false, &xcol[0], nullptr);
     emit_gen_backward(pr, &sink, gen[5], gs[3], &real_A, cfg.lambda_A * cfg.lambda_idt / numel_img, CGB_LOSS_IDT_B, GradSrc(), nullptr);
     pr.mark("idt_B fwd+bwd done");
+    }
     // cycle passes
     pr.cur_lane = 0;
     emit_gen_forward(pr, &sink, gen[1], CGB_NET_G_BA, fake_B, img[CGB_IMG_REC_A], false, &xcol[2], nullptr);
@@ -822,13 +935,21 @@ void cgb_engine::record_programs() {
     g.g2 = &dxp_img[0];
     pr.cur_lane = 0;
     pr.wait(0, ev_dD_A);
-    emit_gen_backward(pr, &sink, gen[0], gs[0], nullptr, 0.f, -1, g, nullptr);
+    if (pair)
+      emit_gen_backward(pr, &sink, gen[0], gs[2], nullptr, 0.f, -1, g, nullptr, &real_B,
+                        cfg.lambda_B * cfg.lambda_idt / numel_img, CGB_LOSS_IDT_A);
+    else
+      emit_gen_backward(pr, &sink, gen[0], gs[0], nullptr, 0.f, -1, g, nullptr);
     pr.mark("bwd fake_B done");
     g.g1 = &dx_D0[1];
     g.g2 = &dxp_img[1];
     pr.cur_lane = 1;
     pr.wait(1, ev_dD_B);
-    emit_gen_backward(pr, &sink, gen[2], gs[1], nullptr, 0.f, -1, g, nullptr);
+    if (pair)
+      emit_gen_backward(pr, &sink, gen[2], gs[3], nullptr, 0.f, -1, g, nullptr, &real_A,
+                        cfg.lambda_A * cfg.lambda_idt / numel_img, CGB_LOSS_IDT_B);
+    else
+      emit_gen_backward(pr, &sink, gen[2], gs[1], nullptr, 0.f, -1, g, nullptr);
     pr.mark("bwd fake_A done");
     pr.join();
     pr.cur_lane = 0;
