@@ -63,6 +63,11 @@ int cgb_version(void);
 
 /* ---- construction (host only; works without a GPU) -------------------------------------------------- */
 int cgb_engine_create(const cgb_config_t* cfg, cgb_engine_t** out);
+/* flags: CGB_FLAG_INFERENCE = engine for Generator.forward / Discriminator.forward only (BASELINE.json configs[4],
+ * the generator-only inference sweep): the workspace holds the packed weights and ONE forward pass, none of
+ * the training passes; every training entry point fails with "inference-only engine". */
+enum { CGB_FLAG_INFERENCE = 1 };
+int cgb_engine_create_ex(const cgb_config_t* cfg, int flags, cgb_engine_t** out);
 void cgb_engine_destroy(cgb_engine_t* e);
 int cgb_num_params(const cgb_engine_t* e, int net);                       /* tensors in a network */
 int cgb_param_info(const cgb_engine_t* e, int net, int index, cgb_param_info_t* out);

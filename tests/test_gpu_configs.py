@@ -1,0 +1,149 @@
+"""GPU parity tests for the larger BASELINE.json configurations (run on a B200 via `pytest -m gpu`):
+configs[3] (512x512 training step), configs[2] geometry (batch > 1), configs[4] (generator-only inference,
+256..1024 px, batch 1..64) and the opt-in paired-pass schedule.  Golden vectors: tests/golden/
+standin_golden_large.json / standin_samples_large.npz, made by oracle/make_golden_large.py from the stand-in.
+
+Tolerances follow tests/test_gpu_parity.py: losses <= 1e-2 relative (north_star), LSGAN terms on few logits
+<= 5e-2, images against strided golden samples <= 6e-2 (bf16 noise amplified by the InstanceNorm stack; the
+observed values are printed by -s).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+cgb = pytest.importorskip("unpaired_image_generation_b200")
+from oracle import cyclegan_standin as ref  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+@pytest.fixture(scope="module")
+def large():
+    with open(os.path.join(GOLD, "standin_golden_large.json")) as f:
+        g = json.load(f)
+    return g, np.load(os.path.join(GOLD, "standin_samples_large.npz"))
+
+
+def _trainer(**kw):
+    onets = ref.build_models(seed=0)
+    mods = (cgb.Generator(), cgb.Generator(), cgb.Discriminator(), cgb.Discriminator())
+    for m, o in zip(mods, onets):
+        m.load_state_dict(o.state_dict())
+    return cgb.CycleGANTrainer(*mods, **kw), mods
+
+
+def _check_losses(losses, want, tol=1e-2, tol_gan=2e-2):
+    for k, v in want.items():
+        t = tol_gan if k in ("loss_G_A", "loss_G_B", "loss_D_A", "loss_D_B") else tol
+        assert abs(losses[k] - v) / abs(v) < t, (k, losses[k], v)
+
+
+def test_train_step_512_vs_golden(large):
+    """BASELINE.json configs[3] geometry: 512x512 (InstanceNorm reductions over 262144 / 65536 / 16384 pixels)"""
+    _need_gpu()
+    g, samples = large
+    case = g["cases"]["fp32_512_b1"]
+    tr, _ = _trainer()
+    real_A, real_B = ref.synthetic_pair(1, 512, seed=1234)
+    imgs = tr.forward_only(real_A.cuda(), real_B.cuda())
+    for k in ("fake_B", "fake_A", "idt_A", "idt_B"):
+        got = imgs[k][0, :, ::16, ::16].cpu().numpy()
+        want = samples[f"fp32_512_b1.img_{k}"]
+        err = np.linalg.norm(got - want) / np.linalg.norm(want)
+        assert err < 6e-2, (k, err)
+    losses = tr.backward_only(real_A.cuda(), real_B.cuda())
+    _check_losses(losses, case["losses_step0"])
+    # one optimiser step, then the losses of the second step's forward are those of the stand-in's second step
+    step = tr.train_step(real_A.cuda(), real_B.cuda())
+    _check_losses(step, case["losses_steps"][0])
+
+
+def test_batch2_256_vs_golden(large):
+    """BASELINE.json configs[2] geometry: more than one pair per GPU"""
+    _need_gpu()
+    g, _ = large
+    tr, _ = _trainer()
+    real_A, real_B = ref.synthetic_pair(2, 256, seed=1234)
+    losses = tr.backward_only(real_A.cuda(), real_B.cuda())
+    _check_losses(losses, g["cases"]["fp32_256_b2"]["losses_step0"])
+
+
+@pytest.mark.parametrize("name", ["gen_512_b2", "gen_1024_b1"])
+def test_generator_inference_vs_golden(large, name):
+    """BASELINE.json configs[4]: Generator.forward alone, through an inference-only engine (one pass of workspace)"""
+    _need_gpu()
+    g, samples = large
+    case = g["cases"][name]
+    size, batch = case["size"], case["batch"]
+    G = cgb.Generator()
+    G.load_state_dict(ref.build_models(seed=0)[0].state_dict())
+    x, _ = ref.synthetic_pair(batch, size, seed=4321)
+    y = G(x.cuda())
+    assert y.shape == (batch, 3, size, size)
+    stride = size // 32
+    got = y[:, :, ::stride, ::stride].cpu().numpy()
+    want = samples[f"{name}.y"]
+    err = np.linalg.norm(got - want) / np.linalg.norm(want)
+    assert err < 6e-2, err
+    l2 = float(y.double().norm())
+    assert abs(l2 - case["out"]["l2"]) / case["out"]["l2"] < 2e-2
+    eng = G._private[(batch, size)]
+    assert eng.inference
+    # an inference engine has no training entry points and a fraction of the training workspace
+    with pytest.raises(RuntimeError, match="inference-only"):
+        eng.train_step()
+    train_bytes = cgb.engine.describe(batch, size)["workspace_bytes"]
+    assert eng.workspace_bytes < 0.3 * train_bytes, (eng.workspace_bytes, train_bytes)
+
+
+def test_generator_inference_batch64_is_batch_independent():
+    """configs[4] upper batch: every image of a batch-64 forward equals the same image run alone (per-sample
+    InstanceNorm), up to the order-dependent rounding of the fp32 statistics atomics"""
+    _need_gpu()
+    G = cgb.Generator(seed=7)
+    x = torch.rand(64, 3, 256, 256, generator=torch.Generator().manual_seed(5)) * 2 - 1
+    y = G(x.cuda())
+    assert y.shape == (64, 3, 256, 256) and bool(torch.isfinite(y).all())
+    for i in (0, 17, 63):
+        yi = G(x[i:i + 1].cuda())
+        err = float((y[i:i + 1] - yi).norm() / yi.norm())
+        assert err < 2e-2, (i, err)
+    # linearity-free sanity: tanh output range
+    assert float(y.abs().max()) <= 1.0
+
+
+def test_paired_schedule_matches_unpaired(monkeypatch):
+    """CGB_PAIR=1 batches (fake, identity) passes of each generator into one 2N pass: same losses and gradients"""
+    _need_gpu()
+    real_A, real_B = ref.synthetic_pair(1, 128, seed=99)
+    tr0, _ = _trainer()
+    l0 = tr0.backward_only(real_A.cuda(), real_B.cuda())
+    g0 = {n: v.clone() for n, v in tr0.grads("G_AB").items()}
+    monkeypatch.setenv("CGB_PAIR", "1")
+    tr1, _ = _trainer()
+    l1 = tr1.backward_only(real_A.cuda(), real_B.cuda())
+    g1 = tr1.grads("G_AB")
+    for k in l0:
+        assert abs(l1[k] - l0[k]) / abs(l0[k]) < 1e-2, (k, l0[k], l1[k])
+    for n in ("head.weight", "res.4.conv1.weight", "stem.weight", "up2.weight"):
+        a, b = g1[n].float(), g0[n].float()
+        cos = float((a * b).sum() / (a.norm() * b.norm()))
+        assert cos > 0.95, (n, cos)
+        assert abs(float(a.norm() / b.norm()) - 1.0) < 0.15, n
+    imgs0 = tr0.forward_only(real_A.cuda(), real_B.cuda())
+    imgs1 = tr1.forward_only(real_A.cuda(), real_B.cuda())
+    for k in imgs0:
+        err = float((imgs1[k] - imgs0[k]).norm() / imgs0[k].norm())
+        # reconstructions pass through two generators: the atomics-order noise of the statistics is amplified
+        # twice (rec_A sits 7e-2..1.2e-1 from fp32 for ANY bf16 implementation)
+        assert err < (0.15 if k.startswith("rec") else 3e-2), (k, err)

@@ -110,3 +110,35 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cc", ".h", ".cuh")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_inference_engine_workspace_is_one_forward_pass():
+    """cgb_engine_create_ex(CGB_FLAG_INFERENCE): host-only creation; the workspace drops the training passes"""
+    import ctypes
+    from unpaired_image_generation_b200 import _lib
+    lib = _lib.load()
+    sizes = {}
+    for flags in (0, 1):
+        cfg = _lib.CgbConfig(4, 256, 9, 10.0, 10.0, 0.5, 2e-4, 0.5, 0.999, 1e-8)
+        h = ctypes.c_void_p()
+        _lib.check(lib.cgb_engine_create_ex(ctypes.byref(cfg), flags, ctypes.byref(h)))
+        sizes[flags] = lib.cgb_workspace_bytes(h)
+        assert lib.cgb_group_numel(h, 0) == 22_756_360  # same parameter inventory either way
+        lib.cgb_engine_destroy(h)
+    assert 0 < sizes[1] < 0.25 * sizes[0], sizes
+
+
+def test_paired_schedule_workspace(monkeypatch):
+    """CGB_PAIR=1 re-plans the workspace (2N-image passes instead of the identity passes): host-only check"""
+    import ctypes
+    from unpaired_image_generation_b200 import _lib
+    lib = _lib.load()
+    out = {}
+    for pair in ("0", "1"):
+        monkeypatch.setenv("CGB_PAIR", pair)
+        cfg = _lib.CgbConfig(2, 128, 9, 10.0, 10.0, 0.5, 2e-4, 0.5, 0.999, 1e-8)
+        h = ctypes.c_void_p()
+        _lib.check(lib.cgb_engine_create(ctypes.byref(cfg), ctypes.byref(h)))
+        out[pair] = lib.cgb_workspace_bytes(h)
+        lib.cgb_engine_destroy(h)
+    assert 0.8 * out["0"] < out["1"] < 1.35 * out["0"], out

@@ -30,6 +30,7 @@ SIGNATURES = {
     "cgb_last_error": (c_char_p, []),
     "cgb_version": (c_int, []),
     "cgb_engine_create": (c_int, [POINTER(CgbConfig), POINTER(_P)]),
+    "cgb_engine_create_ex": (c_int, [POINTER(CgbConfig), c_int, POINTER(_P)]),
     "cgb_engine_destroy": (None, [_P]),
     "cgb_num_params": (c_int, [_P, c_int]),
     "cgb_param_info": (c_int, [_P, c_int, c_int, POINTER(CgbParamInfo)]),

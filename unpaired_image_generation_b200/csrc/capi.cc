@@ -31,7 +31,9 @@ extern "C" {
 const char* cgb_last_error(void) { return cgb::g_last_error.c_str(); }
 int cgb_version(void) { return 100; }
 
-int cgb_engine_create(const cgb_config_t* cfg, cgb_engine_t** out) {
+int cgb_engine_create(const cgb_config_t* cfg, cgb_engine_t** out) { return cgb_engine_create_ex(cfg, 0, out); }
+
+int cgb_engine_create_ex(const cgb_config_t* cfg, int flags, cgb_engine_t** out) {
   CGB_API_BEGIN
   CGB_CHECK(cfg && out, "null argument");
   CGB_CHECK(cfg->batch >= 1, "batch must be >= 1");
@@ -39,6 +41,7 @@ int cgb_engine_create(const cgb_config_t* cfg, cgb_engine_t** out) {
   CGB_CHECK(cfg->n_blocks >= 1 && cfg->n_blocks <= 32, "n_blocks must be in [1, 32]");
   cgb_engine* e = new cgb_engine();
   e->cfg = *cfg;
+  e->infer_only = (flags & CGB_FLAG_INFERENCE) != 0;
   e->build_inventory();
   Arena A;
   e->layout(A);
@@ -149,6 +152,7 @@ int cgb_discriminator_forward(cgb_engine_t* e, int net, const float* x, float* l
 int cgb_set_inputs(cgb_engine_t* e, const float* real_A, const float* real_B, void* stream) {
   CGB_API_BEGIN
   CGB_CHECK(e && e->bound && real_A && real_B, "bad argument / engine not bound");
+  CGB_CHECK(!e->infer_only, "inference-only engine: training entry points are unavailable");
   const size_t bytes = (size_t)e->cfg.batch * 3 * e->cfg.size * e->cfg.size * sizeof(float);
   CGB_CUDA(cudaMemcpyAsync(e->staging[0], real_A, bytes, cudaMemcpyDefault, S(stream)));
   CGB_CUDA(cudaMemcpyAsync(e->staging[1], real_B, bytes, cudaMemcpyDefault, S(stream)));
@@ -159,6 +163,7 @@ int cgb_set_inputs(cgb_engine_t* e, const float* real_A, const float* real_B, vo
 int cgb_forward_cycle(cgb_engine_t* e, void* stream) {
   CGB_API_BEGIN
   CGB_CHECK(e && e->bound, "engine not bound");
+  CGB_CHECK(!e->infer_only, "inference-only engine: training entry points are unavailable");
   e->prog_cycle.run(S(stream));
   CGB_API_END
 }
@@ -166,6 +171,7 @@ int cgb_forward_cycle(cgb_engine_t* e, void* stream) {
 int cgb_get_image(cgb_engine_t* e, int which, float* out, void* stream) {
   CGB_API_BEGIN
   CGB_CHECK(e && e->bound && which >= 0 && which < 8 && out, "bad argument / engine not bound");
+  CGB_CHECK(!e->infer_only, "inference-only engine: training entry points are unavailable");
   nhwc_to_nchw(e->img[which], 3, out, S(stream));
   CGB_API_END
 }
@@ -173,6 +179,7 @@ int cgb_get_image(cgb_engine_t* e, int which, float* out, void* stream) {
 int cgb_phase_generators(cgb_engine_t* e, void* stream) {
   CGB_API_BEGIN
   CGB_CHECK(e && e->bound, "engine not bound");
+  CGB_CHECK(!e->infer_only, "inference-only engine: training entry points are unavailable");
   e->prog_cycle.run(S(stream));
   e->prog_G.run(S(stream));
   CGB_API_END
@@ -181,6 +188,7 @@ int cgb_phase_generators(cgb_engine_t* e, void* stream) {
 int cgb_phase_discriminators(cgb_engine_t* e, void* stream) {
   CGB_API_BEGIN
   CGB_CHECK(e && e->bound, "engine not bound");
+  CGB_CHECK(!e->infer_only, "inference-only engine: training entry points are unavailable");
   e->prog_D.run(S(stream));
   CGB_API_END
 }
@@ -188,6 +196,7 @@ int cgb_phase_discriminators(cgb_engine_t* e, void* stream) {
 int cgb_adam(cgb_engine_t* e, int group, void* stream) {
   CGB_API_BEGIN
   CGB_CHECK(e && e->bound && group >= 0 && group < 2, "bad argument / engine not bound");
+  CGB_CHECK(!e->infer_only, "inference-only engine: training entry points are unavailable");
   e->prog_adam[group].run(S(stream));
   CGB_API_END
 }
@@ -195,6 +204,7 @@ int cgb_adam(cgb_engine_t* e, int group, void* stream) {
 int cgb_train_step(cgb_engine_t* e, void* stream) {
   CGB_API_BEGIN
   CGB_CHECK(e && e->bound, "engine not bound");
+  CGB_CHECK(!e->infer_only, "inference-only engine: training entry points are unavailable");
   e->run_segment(CGB_SEG_STEP, S(stream));
   CGB_API_END
 }
@@ -202,6 +212,7 @@ int cgb_train_step(cgb_engine_t* e, void* stream) {
 int cgb_run_segment(cgb_engine_t* e, int segment, void* stream) {
   CGB_API_BEGIN
   CGB_CHECK(e && e->bound && segment >= 0 && segment < CGB_NUM_SEGMENTS, "bad argument / engine not bound");
+  CGB_CHECK(!e->infer_only, "inference-only engine: training entry points are unavailable");
   e->run_segment(segment, S(stream));
   CGB_API_END
 }
@@ -209,6 +220,7 @@ int cgb_run_segment(cgb_engine_t* e, int segment, void* stream) {
 int cgb_stage_inputs(cgb_engine_t* e, const float* real_A, const float* real_B, void* stream) {
   CGB_API_BEGIN
   CGB_CHECK(e && e->bound && real_A && real_B, "bad argument / engine not bound");
+  CGB_CHECK(!e->infer_only, "inference-only engine: training entry points are unavailable");
   const size_t bytes = (size_t)e->cfg.batch * 3 * e->cfg.size * e->cfg.size * sizeof(float);
   CGB_CUDA(cudaMemcpyAsync(e->staging[0], real_A, bytes, cudaMemcpyDefault, S(stream)));
   CGB_CUDA(cudaMemcpyAsync(e->staging[1], real_B, bytes, cudaMemcpyDefault, S(stream)));
@@ -218,6 +230,7 @@ int cgb_stage_inputs(cgb_engine_t* e, const float* real_A, const float* real_B, 
 int cgb_get_losses_host(cgb_engine_t* e, float* losses_host, void* stream) {
   CGB_API_BEGIN
   CGB_CHECK(e && e->bound && losses_host, "bad argument / engine not bound");
+  CGB_CHECK(!e->infer_only, "inference-only engine: training entry points are unavailable");
   CGB_CUDA(cudaMemcpyAsync(losses_host, e->losses, CGB_NUM_LOSSES * sizeof(float), cudaMemcpyDeviceToHost, S(stream)));
   CGB_CUDA(cudaStreamSynchronize(S(stream)));
   losses_host[CGB_LOSS_G] = 0.f;
@@ -229,6 +242,7 @@ int cgb_train_step_host(cgb_engine_t* e, const float* real_A_host, const float* 
                         void* stream) {
   CGB_API_BEGIN
   CGB_CHECK(e && e->bound && real_A_host && real_B_host && losses_host, "bad argument / engine not bound");
+  CGB_CHECK(!e->infer_only, "inference-only engine: training entry points are unavailable");
   const size_t bytes = (size_t)e->cfg.batch * 3 * e->cfg.size * e->cfg.size * sizeof(float);
   CGB_CUDA(cudaMemcpyAsync(e->staging[0], real_A_host, bytes, cudaMemcpyHostToDevice, S(stream)));
   CGB_CUDA(cudaMemcpyAsync(e->staging[1], real_B_host, bytes, cudaMemcpyHostToDevice, S(stream)));
@@ -250,6 +264,7 @@ int cgb_profile_kind(cgb_engine_t* e, int kind, int reps, void* stream, float* m
                      double* flops) {
   CGB_API_BEGIN
   CGB_CHECK(e && e->bound && kind > 0 && kind < kNumOpKinds && reps > 0, "bad argument / engine not bound");
+  CGB_CHECK(!e->infer_only, "inference-only engine: training entry points are unavailable");
   cudaStream_t st = S(stream);
   const Program* progs[3] = {&e->prog_cycle, &e->prog_G, &e->prog_D};
   long long count = 0;
@@ -276,6 +291,7 @@ int cgb_profile_kind(cgb_engine_t* e, int kind, int reps, void* stream, float* m
 int cgb_profile_timeline(cgb_engine_t* e, void* stream, char* buf, int buf_cap) {
   CGB_API_BEGIN
   CGB_CHECK(e && e->bound && buf && buf_cap > 0, "bad argument / engine not bound");
+  CGB_CHECK(!e->infer_only, "inference-only engine: training entry points are unavailable");
   const std::string t = buf_cap < 0 ? std::string() : (std::getenv("CGB_PROFILE_OPS") ? e->profile_ops(S(stream), 5) : e->timeline(S(stream)));
   std::strncpy(buf, t.c_str(), buf_cap - 1);
   buf[buf_cap - 1] = 0;

@@ -101,7 +101,9 @@ void cgb_engine::build_inventory() {
 // 3-pixel reflect halo; residual-stream tensors carry a 1-pixel reflect halo).
 // ------------------------------------------------------------------------------------------------
 void cgb_engine::layout(Arena& A) {
-  const int N = cfg.batch, S = cfg.size, nb = cfg.n_blocks;
+  // inference-only engines (cgb_engine_create_ex, CGB_FLAG_INFERENCE) carry the packed weights and the
+  // module-forward pass; every training tensor is allocated with batch 0
+  const int N = infer_only ? 0 : cfg.batch, S = cfg.size, nb = cfg.n_blocks;
   const int H2 = S / 2, H4 = S / 4, H8 = S / 8;
   for (int g = 0; g < 2; ++g) pack[g] = static_cast<bf16*>(A.alloc((size_t)pack_elems[g] * sizeof(bf16)));
   auto images = [](const TensorDesc& t, int first, int n) {  // view of n consecutive images
@@ -130,8 +132,8 @@ void cgb_engine::layout(Arena& A) {
   } else {
     for (int i = 0; i < 8; ++i) img[i] = A.tensor(N, S, S, 16, 3);
   }
-  mod_in = A.tensor(N, S, S, 16, 3);
-  mod_out = A.tensor(N, S, S, 16, 3);
+  mod_in = A.tensor(cfg.batch, S, S, 16, 3);
+  mod_out = A.tensor(cfg.batch, S, S, 16, 3);
   for (int i = 0; i < 2; ++i) staging[i] = static_cast<float*>(A.alloc((size_t)N * 3 * S * S * sizeof(float)));
   losses = static_cast<float*>(A.alloc(64 * sizeof(float)));
   for (int g = 0; g < 2; ++g) {
@@ -143,7 +145,7 @@ void cgb_engine::layout(Arena& A) {
   for (size_t gi = 0; gi < gen.size(); ++gi) {
     GenPass& P = gen[gi];
     // paired schedule: passes 0 / 2 carry 2N images, the identity passes 4 / 5 do not exist
-    const int N = !pair ? cfg.batch : (gi == 0 || gi == 2) ? 2 * cfg.batch : (gi == 4 || gi == 5) ? 0 : cfg.batch;
+    const int N = gi == 6 ? cfg.batch : infer_only ? 0 : !pair ? cfg.batch : (gi == 0 || gi == 2) ? 2 * cfg.batch : (gi == 4 || gi == 5) ? 0 : cfg.batch;
     P.y_stem = A.tensor(N, S, S, 64, 0);
     P.a_stem = A.tensor(N, S, S, 64, 0);
     P.y_d1 = A.tensor(N, H2, H2, 128, 0);
@@ -176,7 +178,9 @@ void cgb_engine::layout(Arena& A) {
     P.bstats = static_cast<float2*>(A.alloc(P.stats_bytes));
   }
   dis.resize(5);
-  for (DisPass& D : dis) {
+  for (size_t di = 0; di < dis.size(); ++di) {
+    DisPass& D = dis[di];
+    const int N = (di == 4 || !infer_only) ? cfg.batch : 0;
     D.l0 = A.tensor(N, H2, H2, 64, 0);
     D.y1 = A.tensor(N, H4, H4, 128, 0);
     D.a1 = A.tensor(N, H4, H4, 128, 0);
@@ -195,7 +199,7 @@ void cgb_engine::layout(Arena& A) {
   for (int gi = 0; gi < kPassLanes; ++gi) {  // one backward scratch set per lane
     GenScratch& g = gs[gi];
     // paired schedule: sets 0 / 1 serve the cycle passes (N images), sets 2 / 3 the paired passes (2N)
-    const int N = (pair && gi >= 2) ? 2 * cfg.batch : cfg.batch;
+    const int N = infer_only ? 0 : (pair && gi >= 2) ? 2 * cfg.batch : cfg.batch;
     g.dpre_head = A.tensor(N, S, S, 16, 0);
     g.dxp_head = A.tensor(N, S + 6, S + 6, 64, 0);
     g.dyF = A.tensor(N, S, S, 64, 0);
@@ -702,6 +706,7 @@ void cgb_engine::record_programs() {
     pr.dep(wlane, main_lane);
   };
 
+  if (!infer_only) {
   // ---------------------------------------------------------------- step programs
   const TensorDesc &fake_B = img[CGB_IMG_FAKE_B], &rec_A = img[CGB_IMG_REC_A], &fake_A = img[CGB_IMG_FAKE_A],
                    &rec_B = img[CGB_IMG_REC_B], &idt_A = img[CGB_IMG_IDT_A], &idt_B = img[CGB_IMG_IDT_B],
@@ -955,6 +960,7 @@ void cgb_engine::record_programs() {
     pr.cur_lane = 0;
     pr.mark("step end (before Adam)");
   }
+  }  // !infer_only
   // ---- optimiser + bf16 weight refresh
   for (int g = 0; g < 2; ++g) {
     std::vector<PackEntry> table;

@@ -217,6 +217,7 @@ struct cgb_engine {
   cgb_config_t cfg;
   int sm_count = 148;
   bool bound = false;
+  bool infer_only = false;  // CGB_FLAG_INFERENCE: module forwards only
   float grad_scale = 1.f;
 
   std::vector<cgb::LayerParam> layers[4];

@@ -73,7 +73,8 @@ def describe(batch: int, size: int, n_blocks: int = 9) -> Dict[int, List[ParamIn
 
 class StepEngine:
     def __init__(self, batch: int, size: int, n_blocks: int = 9, lambda_A: float = 10.0, lambda_B: float = 10.0,
-                 lambda_idt: float = 0.5, lr: float = 2e-4, betas=(0.5, 0.999), eps: float = 1e-8, device=None):
+                 lambda_idt: float = 0.5, lr: float = 2e-4, betas=(0.5, 0.999), eps: float = 1e-8, device=None,
+                 inference: bool = False):
         if not torch.cuda.is_available():
             raise RuntimeError("unpaired_image_generation_b200 needs a CUDA device (B200, sm_100a); "
                                "there is no CPU fallback")
@@ -82,7 +83,9 @@ class StepEngine:
         self.batch, self.size, self.n_blocks = batch, size, n_blocks
         cfg = _lib.CgbConfig(batch, size, n_blocks, lambda_A, lambda_B, lambda_idt, lr, betas[0], betas[1], eps)
         self._h = ctypes.c_void_p()
-        _lib.check(self.lib.cgb_engine_create(ctypes.byref(cfg), ctypes.byref(self._h)))
+        # inference=True: module forwards only (CGB_FLAG_INFERENCE): the workspace holds one forward pass
+        self.inference = bool(inference)
+        _lib.check(self.lib.cgb_engine_create_ex(ctypes.byref(cfg), 1 if inference else 0, ctypes.byref(self._h)))
         self.infos: Dict[int, List[ParamInfo]] = {}
         for net in range(4):
             lst = []

@@ -76,7 +76,7 @@ class _NetModule:
             return self._engine, self._net
         key = (batch, h)
         if key not in self._private:
-            eng = _engine.StepEngine(batch, h, self.n_blocks)
+            eng = _engine.StepEngine(batch, h, self.n_blocks, inference=True)
             net = 0 if self._KIND == "G" else 2
             for k, v in eng.param_views(net).items():
                 v.copy_(self._params[k].to(v.device))
