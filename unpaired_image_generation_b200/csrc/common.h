@@ -112,6 +112,24 @@ struct WgradArgs {
   int ncols;               // GEMM N extent (0: same as Cin)
 };
 
+// Launch with the programmatic-dependent-launch attribute (see ptx.cuh: pdl_wait / pdl_launch_dependents).
+// Every kernel launched through this helper MUST call pdl_wait() before touching global memory.
+bool pdl_enabled();  // CGB_PDL=0 disables (conv_plan.cc)
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CGB_CUDA(cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...));
+}
+
 enum Act { kActNone = 0, kActLeaky = 1, kActTanh = 2, kActRelu = 3 };
 
 }  // namespace cgb

@@ -100,6 +100,7 @@ igemm_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; its outputs are visible from here on
   if (prof && threadIdx.x == 0) prof[1] = clock64();
 
   // The producer / MMA loops are executed by ONE thread each and their per-stage instruction latency is on the
@@ -216,6 +217,7 @@ igemm_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
     mbar_wait_relaxed(tmem_full_bar, 0);
     tc_fence_after();
+    pdl_launch_dependents();  // main loop done: the next kernel may start launching behind the epilogue
     if (prof && threadIdx.x == 64) prof[5] = clock64();
 #pragma unroll 1
     for (int mt = 0; mt < MT; ++mt) {
@@ -266,8 +268,7 @@ static void launch_patch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const
   CGB_CHECK(BN < 64 || ring >= 128 * BN * 2, "patch igemm: weight ring smaller than the epilogue staging area");
   const int smem = 1024 + ring + 2 * MT * pa.patch_bytes + kPatchMisc;
   CGB_CHECK(smem <= kPatchSmemMax, "patch igemm: shared memory budget exceeded");
-  kern<<<grid, 224, smem, stream>>>(tmA, tmB, args, pa);
-  CGB_CUDA(cudaGetLastError());
+  launch_pdl(kern, grid, dim3(224), (size_t)smem, stream, tmA, tmB, args, pa);
 }
 
 void launch_igemm_patch(int BN, int MT, const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmArgs& args,

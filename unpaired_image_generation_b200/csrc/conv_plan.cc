@@ -7,6 +7,11 @@
 
 namespace cgb {
 
+bool pdl_enabled() {
+  static const bool on = !(std::getenv("CGB_PDL") && std::atoi(std::getenv("CGB_PDL")) == 0);
+  return on;
+}
+
 int padded_rows(int c) { return c <= 16 ? 16 : (c + 63) / 64 * 64; }
 long long packed_wf_elems(const ConvSpec& s) { return (long long)padded_rows(s.CoutS) * s.taps() * s.CinS; }
 long long packed_wt_elems(const ConvSpec& s) { return (long long)padded_rows(s.CinS) * s.taps() * s.CoutS; }

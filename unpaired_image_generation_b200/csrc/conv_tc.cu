@@ -110,6 +110,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if constexpr (kCluster) cluster_sync_all();  // peers' barriers are initialised before anyone multicasts
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();
   if (prof && threadIdx.x == 0) prof[1] = clock64();
 
   if (warp == 0) {
@@ -206,6 +207,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     mbar_wait_relaxed(tmem_full_bar, 0);
     tc_fence_after();
+    pdl_launch_dependents();
     if (prof && threadIdx.x == 64) prof[5] = clock64();
     epilogue_tile<BN>(args, tmem_base, smem, s_bias, n, ho, wo, nblk, args.out_off[cls], q, lane, prof);
   }
@@ -278,6 +280,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();
 
   if (warp == 0) {
     // TMA producer: whole warp converged, one elected lane issues
@@ -345,6 +348,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
     const bool vec_ok = (args.Cin & 3) == 0 && args.col_map == nullptr;
     mbar_wait_relaxed(tmem_full_bar, 0);
     tc_fence_after();
+    pdl_launch_dependents();
 #pragma unroll 1
     for (int c = 0; c < BNW; c += 32) {
       uint32_t r[32];
@@ -395,7 +399,7 @@ static void launch_igemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const
     configured = true;
   }
   if (CM * CN == 1) {
-    kern<<<grid, 192, Cfg::kSmemBytes, stream>>>(tmA, tmB, args);
+    launch_pdl(kern, grid, dim3(192), (size_t)Cfg::kSmemBytes, stream, tmA, tmB, args);
   } else {
     grid.x = (grid.x + CM - 1) / CM * CM;  // padded tiles compute masked-out pixels
     CGB_CHECK(grid.y % CN == 0, "cluster N extent must divide the number of N blocks");
@@ -451,8 +455,7 @@ static void launch_wgrad_t(const CUtensorMap& tmDY, const CUtensorMap& tmX, cons
     CGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
-  kern<<<grid, 192, Cfg::kSmemBytes, stream>>>(tmDY, tmX, args);
-  CGB_CUDA(cudaGetLastError());
+  launch_pdl(kern, grid, dim3(192), (size_t)Cfg::kSmemBytes, stream, tmDY, tmX, args);
 }
 
 void launch_wgrad(int BNW, const CUtensorMap& tmDY, const CUtensorMap& tmX, const WgradArgs& args, int m_blocks,

@@ -2,9 +2,19 @@
 // the channel count a multiple of 8, so every thread moves 16-byte vectors.
 #include "pointwise.h"
 
+#include "ptx.cuh"
+
+#ifndef CGB_PW_TRIGGER
+#define CGB_PW_TRIGGER 0
+#endif
+
 namespace cgb {
 
 namespace {
+
+// 1: pointwise kernels let their successor start launching right away.  Measured: a conv CTA that is launched
+// early then sits in griddepcontrol.wait holding ~200 KB of shared memory, which starves the other lanes.
+constexpr bool kPwTrigger = CGB_PW_TRIGGER != 0;
 
 struct DevTensor {
   bf16* p;  // interior origin
@@ -160,6 +170,8 @@ __global__ void nhwc_to_nchw_kernel(DevTensor src, int C, float* __restrict__ ds
 }
 
 __global__ void fill_halo_kernel(DevTensor t) {
+  ptx::pdl_wait();  // launched with programmatic stream serialization (see launch_pdl)
+  if (kPwTrigger) ptx::pdl_launch_dependents();
   const int HP = t.H + 2 * t.halo, WP = t.W + 2 * t.halo, C8 = t.C / 8;
   const long long total = (long long)t.N * HP * WP * C8;
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -182,6 +194,8 @@ __global__ void fill_halo_kernel(DevTensor t) {
 // MODE 1: sum only of the first Cvalid channels -> float* (bias gradients).
 template <int MODE>
 __global__ void colsum_kernel(DevTensor y, float* __restrict__ out, int pix_per_block, int Cvalid) {
+  ptx::pdl_wait();  // launched with programmatic stream serialization (see launch_pdl)
+  if (kPwTrigger) ptx::pdl_launch_dependents();
   const int C8 = y.C / 8;
   const int lanes = C8 < 256 ? C8 : 256;
   const int rows = 256 / lanes;
@@ -277,6 +291,8 @@ __device__ __forceinline__ void load_norm8(const float2* __restrict__ stats, lon
 template <int PPT>
 __global__ void __launch_bounds__(256)
 in_apply_kernel(DevTensor y, const float2* __restrict__ stats, int act, DevTensor res, DevTensor out, int ppb) {
+  ptx::pdl_wait();  // launched with programmatic stream serialization (see launch_pdl)
+  if (kPwTrigger) ptx::pdl_launch_dependents();
   const int C8 = out.C / 8;
   const int lanes = C8 < 256 ? C8 : 256;
   const int rows = 256 / lanes;
@@ -406,6 +422,8 @@ template <int PPT>
 __global__ void __launch_bounds__(256)
 in_bwd_reduce_kernel(DevTensor y, const float2* __restrict__ stats, DevGrad g, int act, DevTensor da,
                      float* __restrict__ bstats, int ppb) {
+  ptx::pdl_wait();  // launched with programmatic stream serialization (see launch_pdl)
+  if (kPwTrigger) ptx::pdl_launch_dependents();
   const int C8 = y.C / 8;
   const int lanes = C8 < 256 ? C8 : 256;
   const int rows = 256 / lanes;
@@ -478,6 +496,8 @@ template <int PPT>
 __global__ void __launch_bounds__(256)
 in_bwd_apply_kernel(DevTensor y, const float2* __restrict__ stats, const float2* __restrict__ bstats, DevGrad g,
                     int act, DevTensor dy, int ppb) {
+  ptx::pdl_wait();  // launched with programmatic stream serialization (see launch_pdl)
+  if (kPwTrigger) ptx::pdl_launch_dependents();
   const int C8 = y.C / 8;
   const int lanes = C8 < 256 ? C8 : 256;
   const int rows = 256 / lanes;
@@ -541,6 +561,8 @@ __device__ __forceinline__ float block_sum(float v) {
 // one thread per pixel; tensors have 16 stored channels, the first C (<= 8) are real
 __global__ void tanh_bwd_kernel(DevTensor out, DevTensor target, float l1_scale, DevGrad g, int C, DevTensor dpre,
                                 float* __restrict__ loss_slot) {
+  ptx::pdl_wait();  // launched with programmatic stream serialization (see launch_pdl)
+  if (kPwTrigger) ptx::pdl_launch_dependents();
   const long long total = (long long)out.N * out.H * out.W;
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   float lsum = 0.f;
@@ -699,6 +721,8 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 // one thread per (pixel, tap): an 8-byte load (channels 0..3) and an 8-byte store; the taps of a pixel are
 // consecutive threads, so stores are contiguous
 __global__ void im2col4_kernel(DevTensor src, int k, int stride, int sgn, int off, int use_halo, DevTensor dst) {
+  ptx::pdl_wait();  // launched with programmatic stream serialization (see launch_pdl)
+  if (kPwTrigger) ptx::pdl_launch_dependents();
   const int T = k * k;
   const long long total = (long long)dst.N * dst.H * dst.W * T;
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -766,8 +790,7 @@ void nhwc_to_nchw(const TensorDesc& src, int C, float* dst, cudaStream_t st) {
 void fill_reflect_halo(const TensorDesc& t, cudaStream_t st) {
   if (t.halo == 0) return;
   const long long total = (long long)t.N * (t.H + 2 * t.halo) * (t.W + 2 * t.halo) * (t.C / 8);
-  fill_halo_kernel<<<blocks_for(total, 256), 256, 0, st>>>(dev(t));
-  CGB_CUDA(cudaGetLastError());
+  launch_pdl(fill_halo_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, st, dev(t));
 }
 
 void in_stats(const TensorDesc& y, float2* stats, cudaStream_t st) {
@@ -775,16 +798,14 @@ void in_stats(const TensorDesc& y, float2* stats, cudaStream_t st) {
   const int HW = y.H * y.W;
   const int ppb = pick_pix_per_block(HW);
   dim3 grid((HW + ppb - 1) / ppb, y.N);
-  colsum_kernel<0><<<grid, 256, 0, st>>>(dev(y), reinterpret_cast<float*>(stats), ppb, y.C);
-  CGB_CUDA(cudaGetLastError());
+  launch_pdl(colsum_kernel<0>, grid, dim3(256), 0, st, dev(y), reinterpret_cast<float*>(stats), ppb, y.C);
 }
 
 void bias_grad(const TensorDesc& dy, int C, float* gbias, cudaStream_t st) {
   const int HW = dy.H * dy.W;
   const int ppb = pick_pix_per_block(HW);
   dim3 grid((HW + ppb - 1) / ppb, dy.N);
-  colsum_kernel<1><<<grid, 256, 0, st>>>(dev(dy), gbias, ppb, C);
-  CGB_CUDA(cudaGetLastError());
+  launch_pdl(colsum_kernel<1>, grid, dim3(256), 0, st, dev(dy), gbias, ppb, C);
 }
 
 // Streaming kernels: blocks of `ppb` pixels sized for ~8 CTAs per SM over the whole batch (but at least one
@@ -804,8 +825,7 @@ void in_apply(const TensorDesc& y, const float2* stats, int act, const TensorDes
   const int lanes = std::min(256, out.C / 8), rows = 256 / lanes;
   const int ppb = stream_ppb(total, rows, 2, out.N);
   dim3 grid((total + ppb - 1) / ppb, out.N);
-  in_apply_kernel<2><<<grid, 256, 0, st>>>(dev(y), stats, act, residual ? dev(*residual) : dev_null(), dev(out), ppb);
-  CGB_CUDA(cudaGetLastError());
+  launch_pdl(in_apply_kernel<2>, grid, dim3(256), 0, st, dev(y), stats, act, residual ? dev(*residual) : dev_null(), dev(out), ppb);
 }
 
 static void check_grad(const TensorDesc& y, const GradSrc& g) {
@@ -828,9 +848,8 @@ void in_bwd_reduce(const TensorDesc& y, const float2* stats, const GradSrc& g, i
   int ppb = (HW + blocks_per_image - 1) / blocks_per_image;
   ppb = std::max(unit, (ppb + unit - 1) / unit * unit);
   dim3 grid((HW + ppb - 1) / ppb, y.N);
-  in_bwd_reduce_kernel<2><<<grid, 256, 0, st>>>(dev(y), stats, dev(g), act, da_out ? dev(*da_out) : dev_null(),
-                                                reinterpret_cast<float*>(bstats), ppb);
-  CGB_CUDA(cudaGetLastError());
+  launch_pdl(in_bwd_reduce_kernel<2>, grid, dim3(256), 0, st, dev(y), stats, dev(g), act,
+             da_out ? dev(*da_out) : dev_null(), reinterpret_cast<float*>(bstats), ppb);
 }
 
 void in_bwd_apply(const TensorDesc& y, const float2* stats, const float2* bstats, const GradSrc& g, int act,
@@ -840,8 +859,7 @@ void in_bwd_apply(const TensorDesc& y, const float2* stats, const float2* bstats
   const int lanes = std::min(256, y.C / 8), rows = 256 / lanes;
   const int ppb = stream_ppb(total, rows, 2, y.N);
   dim3 grid((total + ppb - 1) / ppb, y.N);
-  in_bwd_apply_kernel<2><<<grid, 256, 0, st>>>(dev(y), stats, bstats, dev(g), act, dev(dy), ppb);
-  CGB_CUDA(cudaGetLastError());
+  launch_pdl(in_bwd_apply_kernel<2>, grid, dim3(256), 0, st, dev(y), stats, bstats, dev(g), act, dev(dy), ppb);
 }
 
 void tanh_bwd(const TensorDesc& out, const TensorDesc* target, float l1_scale, const GradSrc& g, int C,
@@ -849,9 +867,8 @@ void tanh_bwd(const TensorDesc& out, const TensorDesc* target, float l1_scale, c
   CGB_CHECK(out.C == 16 && dpre.C == 16 && C <= 8, "tanh_bwd expects 16-channel image tensors");
   if (g.g1 || g.g2) check_grad(out, g);
   const long long total = (long long)out.N * out.H * out.W;
-  tanh_bwd_kernel<<<blocks_for(total, 256), 256, 0, st>>>(dev(out), target ? dev(*target) : dev_null(), l1_scale,
-                                                          dev(g), C, dev(dpre), loss_slot);
-  CGB_CUDA(cudaGetLastError());
+  launch_pdl(tanh_bwd_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, st, dev(out),
+             target ? dev(*target) : dev_null(), l1_scale, dev(g), C, dev(dpre), loss_slot);
 }
 
 void l1_loss(const TensorDesc& a, const TensorDesc& b, int C, float scale, float* loss_slot, cudaStream_t st) {
@@ -895,8 +912,8 @@ void im2col4(const TensorDesc& src, int k, int stride, int sgn, int off, bool us
              cudaStream_t st) {
   CGB_CHECK(src.C >= 4 && dst.C >= 4 * k * k && dst.halo == 0, "im2col4: bad source / destination");
   const long long total = (long long)dst.N * dst.H * dst.W * k * k;
-  im2col4_kernel<<<blocks_for(total, 256), 256, 0, st>>>(dev(src), k, stride, sgn, off, use_halo ? 1 : 0, dev(dst));
-  CGB_CUDA(cudaGetLastError());
+  launch_pdl(im2col4_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, st, dev(src), k, stride, sgn, off, use_halo ? 1 : 0,
+             dev(dst));
 }
 
 void wgrad_direct(const ConvSpec& s, const TensorDesc& x, const TensorDesc& dy, float* g, cudaStream_t st) {
