@@ -87,6 +87,7 @@ struct PatchArgs {
   int sbo;          // bytes between consecutive 8-pixel row groups of the M tile
   int base_offset;  // 1: put (start address >> 7) & 7 into the descriptor's base-offset field
   int b_stages;     // weight-tile ring depth
+  int num_items;    // M-direction work items (MT stacked tiles each); a CTA loops over blockIdx.x + i * gridDim.x
 };
 
 // One filter tap of the weight-gradient GEMM: offsets for both operands.

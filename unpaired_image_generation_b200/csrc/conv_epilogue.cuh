@@ -14,7 +14,9 @@ namespace cgb {
 //   stage    : shared-memory staging area of the CTA, >= 128 * BN * 2 bytes, idle pipeline buffers (BN >= 64)
 //   s_bias   : BN floats (this CTA's slice of the bias) or unused when args.bias == nullptr
 //   ho, wo   : this thread's output pixel (row q*32 + lane of the tile); n : image; out_off : class offset
-template <int BN>
+//   SC       : columns staged per write-out round (BN: whole rows through `stage` of 128*BN*2 bytes; 64: rounds of
+//              128-byte row pieces through 16 KB, for kernels whose pipeline buffers stay busy during the epilogue)
+template <int BN, int SC = BN>
 __device__ __forceinline__ void epilogue_tile(const IgemmArgs& args, uint32_t tmem_acc, uint8_t* stage,
                                               const float* s_bias, int n, int ho, int wo, int nblk, long long out_off,
                                               int q, int lane, long long* prof) {
@@ -25,8 +27,10 @@ __device__ __forceinline__ void epilogue_tile(const IgemmArgs& args, uint32_t tm
   // BN >= 64: rows are staged in shared memory (the pipeline buffers are idle once the accumulator is
   // complete) and written out with every warp instruction covering whole 128-byte lines of one pixel.
   constexpr bool kStaged = BN >= 64;
-  constexpr int kRowBytes = BN * 2;
+  constexpr int kRowBytes = SC * 2;
+  static_assert(!kStaged || (SC >= 64 && BN % SC == 0), "staging round must be a multiple of 64 columns dividing BN");
   uint8_t* stage_base = stage + (size_t)q * 32 * kRowBytes;  // this warp's 32 rows
+  const unsigned long long optr0 = reinterpret_cast<unsigned long long>(orow + nblk * BN);
 #pragma unroll 1
   for (int c = 0; c < BN; c += CH) {
     float v[CH];
@@ -109,7 +113,7 @@ __device__ __forceinline__ void epilogue_tile(const IgemmArgs& args, uint32_t tm
         pk.y = pack_bf16x2(v[j + 2], v[j + 3]);
         pk.z = pack_bf16x2(v[j + 4], v[j + 5]);
         pk.w = pack_bf16x2(v[j + 6], v[j + 7]);
-        const int piece = (c + j) >> 3;  // 16-byte piece index within the row
+        const int piece = ((c % SC) + j) >> 3;  // 16-byte piece index within the staged row
         *reinterpret_cast<uint4*>(srow + (((piece & ~7) | ((piece ^ lane) & 7)) << 4)) = pk;
       }
     } else if (valid) {
@@ -129,26 +133,28 @@ __device__ __forceinline__ void epilogue_tile(const IgemmArgs& args, uint32_t tm
         }
       }
     }
+    if constexpr (kStaged) {
+      if ((c + CH) % SC == 0) {  // a staging round is complete: write it out
+        __syncwarp();
+        // each warp instruction writes kRowsPerInst pixel rows of SC channels (>= 128 contiguous bytes each)
+        constexpr int kLanesPerRow = kRowBytes / 16;  // 8, 16 or 32
+        constexpr int kRowsPerInst = 32 / kLanesPerRow;
+        const int sub = lane / kLanesPerRow, piece = lane % kLanesPerRow;
+        const unsigned long long optr = optr0 + (unsigned long long)(c + CH - SC) * 2;
+#pragma unroll 4
+        for (int r0 = 0; r0 < 32; r0 += kRowsPerInst) {
+          const int r = r0 + sub;
+          const unsigned long long p = __shfl_sync(0xffffffffu, optr, r);
+          const int ok = __shfl_sync(0xffffffffu, valid ? 1 : 0, r);
+          const uint4 val = *reinterpret_cast<const uint4*>(stage_base + (size_t)r * kRowBytes +
+                                                            (((piece & ~7) | ((piece ^ r) & 7)) << 4));
+          if (ok) *reinterpret_cast<uint4*>(p + (unsigned long long)piece * 16) = val;
+        }
+        __syncwarp();  // the staging rows are rewritten by the next round / the caller's next tile
+      }
+    }
   }
   if (prof && threadIdx.x == 64) prof[10] = clock64();
-  if constexpr (kStaged) {
-    __syncwarp();
-    // each warp instruction writes kRowsPerInst whole pixel rows of BN channels (>= 128 contiguous bytes each)
-    constexpr int kLanesPerRow = kRowBytes / 16;  // 8, 16 or 32
-    constexpr int kRowsPerInst = 32 / kLanesPerRow;
-    const int sub = lane / kLanesPerRow, piece = lane % kLanesPerRow;
-    const unsigned long long optr = reinterpret_cast<unsigned long long>(orow + nblk * BN);
-#pragma unroll 4
-    for (int r0 = 0; r0 < 32; r0 += kRowsPerInst) {
-      const int r = r0 + sub;
-      const unsigned long long p = __shfl_sync(0xffffffffu, optr, r);
-      const int ok = __shfl_sync(0xffffffffu, valid ? 1 : 0, r);
-      const uint4 val = *reinterpret_cast<const uint4*>(stage_base + (size_t)r * kRowBytes +
-                                                        (((piece & ~7) | ((piece ^ r) & 7)) << 4));
-      if (ok) *reinterpret_cast<uint4*>(p + (unsigned long long)piece * 16) = val;
-    }
-    __syncwarp();  // the staging rows may be rewritten by the caller's next tile
-  }
 }
 
 }  // namespace cgb

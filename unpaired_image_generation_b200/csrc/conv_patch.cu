@@ -26,7 +26,8 @@ namespace cgb {
 using namespace ptx;
 
 namespace {
-constexpr int kPatchMisc = 256 /*barriers*/ + 512 /*tap tables*/ + 1024 /*bias*/;
+constexpr int kPatchStageBytes = 16384;  // epilogue staging: 128 rows x 64 columns x bf16
+constexpr int kPatchMisc = kPatchStageBytes + 256 /*barriers*/ + 512 /*tap tables*/ + 1024 /*bias*/;
 constexpr int kPatchMaxBStages = 8;
 constexpr int kPatchSmemMax = 232448;
 }  // namespace
@@ -39,20 +40,24 @@ igemm_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   constexpr int kBBytes = (kBBytesTx + 1023) / 1024 * 1024;
   constexpr int kStageBytes = KPS * kBBytes;
   constexpr int kAcc = BN < 32 ? 32 : BN;  // TMEM columns per accumulator
-  constexpr int kTmemCols = MT * kAcc;
+  // two accumulator sets when they fit: the epilogue of tile i drains one while the MMAs of tile i+1 fill the other
+  constexpr int NACC = (2 * MT * kAcc <= 512) ? 2 : 1;
+  constexpr int kTmemCols = NACC * MT * kAcc;
   static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM allocation must be a power of two <= 512");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int ring_bytes = pa.b_stages * kStageBytes;
   uint8_t* patches = smem + ring_bytes;
-  uint8_t* misc = patches + 2 * MT * pa.patch_bytes;
+  uint8_t* stage = patches + 2 * MT * pa.patch_bytes;  // epilogue staging: 4 warps x 32 rows x 128 bytes
+  uint8_t* misc = stage + kPatchStageBytes;
   uint64_t* b_full = reinterpret_cast<uint64_t*>(misc);
   uint64_t* b_empty = b_full + kPatchMaxBStages;
   uint64_t* a_full = b_empty + kPatchMaxBStages;
   uint64_t* a_empty = a_full + 2;
-  uint64_t* tmem_full_bar = a_empty + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = a_empty + 2;    // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;  // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   uint32_t* s_aoff = reinterpret_cast<uint32_t*>(misc + 256);  // per tap: descriptor start offset (16 B units)
   int32_t* s_bk = reinterpret_cast<int32_t*>(misc + 256 + 256);  // per tap: K offset in the packed weights
   float* s_bias = reinterpret_cast<float*>(misc + 256 + 512);
@@ -65,14 +70,10 @@ igemm_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
   const int T = pa.k * pa.k;
   const int nbs = (T + KPS - 1) / KPS;  // weight stages per channel chunk
-
-  // CTA -> (image, CTA row, tile column); a CTA row is MT stacked tiles of 16 x 8 output pixels
-  int t = blockIdx.x;
-  const int tw = t % args.tiles_w;
-  t /= args.tiles_w;
-  const int th = t % args.tiles_h;
-  const int n = t / args.tiles_h;
-  const int wo0 = tw * 8, ho0 = th * 16 * MT;
+  // persistent: this CTA owns the M-direction work items blockIdx.x, blockIdx.x + gridDim.x, ...
+  // (a work item is MT stacked tiles of 16 x 8 output pixels of one image)
+  const int items = pa.num_items;
+  const int tiles_per_img = args.tiles_w * args.tiles_h;
 
   for (int i = threadIdx.x; i < T; i += blockDim.x) {
     const int py = i / pa.k, px = i - py * pa.k;
@@ -89,8 +90,9 @@ igemm_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     for (int s = 0; s < 2; ++s) {
       mbar_init(&a_full[s], 1);
       mbar_init(&a_empty[s], 1);
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 128);  // every epilogue thread arrives once its TMEM reads are done
     }
-    mbar_init(tmem_full_bar, 1);
     fence_mbar_init();
   } else if (warp == 1) {
     tmem_alloc(tmem_ptr, kTmemCols);
@@ -108,45 +110,53 @@ igemm_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (warp == 6) {
     // ===================== patch producer =====================
     uint32_t ph = 1;  // parity to wait for on a_empty: the first pass over the two buffers does not block
-    for (int c = 0; c < pa.chunks; ++c) {
-      const int ca = c & 1;
-      mbar_wait(&a_empty[ca], ph);
-      if (elect_one()) {
-        mbar_arrive_expect_tx(&a_full[ca], MT * pa.nbox * pa.box_bytes);
+    int ca = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      const int n = item / tiles_per_img, r = item - n * tiles_per_img;
+      const int th = r / args.tiles_w, tw = r - th * args.tiles_w;
+      const int wo0 = tw * 8, ho0 = th * 16 * MT;
+      for (int c = 0; c < pa.chunks; ++c) {
+        mbar_wait(&a_empty[ca], ph);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&a_full[ca], MT * pa.nbox * pa.box_bytes);
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-          uint8_t* dst = patches + (ca * MT + mt) * pa.patch_bytes;
-          for (int b = 0; b < pa.nbox; ++b)
-            tma_load_5d(dst + b * pa.box_bytes, &tmA, &a_full[ca], c * 64, wo0 + pa.ox + b, 0,
-                        ho0 + mt * 16 + pa.oy, n);
+          for (int mt = 0; mt < MT; ++mt) {
+            uint8_t* dst = patches + (ca * MT + mt) * pa.patch_bytes;
+            for (int b = 0; b < pa.nbox; ++b)
+              tma_load_5d(dst + b * pa.box_bytes, &tmA, &a_full[ca], c * 64, wo0 + pa.ox + b, 0,
+                          ho0 + mt * 16 + pa.oy, n);
+          }
+          if (prof && c == 0 && item == (int)blockIdx.x) prof[2] = clock64();
         }
-        if (prof && c == 0) prof[2] = clock64();
+        __syncwarp();
+        if (ca == 1) ph ^= 1;
+        ca ^= 1;
       }
-      __syncwarp();
-      if (ca == 1) ph ^= 1;
     }
   } else if (warp == 0) {
     // ===================== weight-tile producer =====================
     int s = 0;
     uint32_t ph = 1;
     uint8_t* sb = smem;
-    for (int c = 0; c < pa.chunks; ++c) {
-      for (int bs = 0; bs < nbs; ++bs) {
-        mbar_wait(&b_empty[s], ph);
-        if (elect_one()) {
-          const int nk = min(KPS, T - bs * KPS);
-          mbar_arrive_expect_tx(&b_full[s], nk * kBBytesTx);
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      for (int c = 0; c < pa.chunks; ++c) {
+        for (int bs = 0; bs < nbs; ++bs) {
+          mbar_wait(&b_empty[s], ph);
+          if (elect_one()) {
+            const int nk = min(KPS, T - bs * KPS);
+            mbar_arrive_expect_tx(&b_full[s], nk * kBBytesTx);
 #pragma unroll
-          for (int j = 0; j < KPS; ++j) {
-            if (j < nk) tma_load_2d(sb + j * kBBytes, &tmB, &b_full[s], s_bk[bs * KPS + j] + c * 64, nblk * BN);
+            for (int j = 0; j < KPS; ++j) {
+              if (j < nk) tma_load_2d(sb + j * kBBytes, &tmB, &b_full[s], s_bk[bs * KPS + j] + c * 64, nblk * BN);
+            }
           }
-        }
-        __syncwarp();
-        sb += kStageBytes;
-        if (++s == pa.b_stages) {
-          s = 0;
-          ph ^= 1;
-          sb = smem;
+          __syncwarp();
+          sb += kStageBytes;
+          if (++s == pa.b_stages) {
+            s = 0;
+            ph ^= 1;
+            sb = smem;
+          }
         }
       }
     }
@@ -159,48 +169,59 @@ igemm_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const uint32_t lo_ring = smem_u32(smem) >> 4;
     const uint32_t lo_patch = smem_u32(patches) >> 4;
     const uint32_t patch_units = (uint32_t)pa.patch_bytes >> 4;
-    int s = 0;
-    uint32_t ph = 0, acc = 0;
+    int s = 0, ca = 0, acc_i = 0;
+    uint32_t ph = 0, a_ph = 0, e_ph = 1;  // e_ph: parity to wait for on tmem_empty (first use of each set: free)
     uint32_t b_lo0 = lo_ring;
-    for (int c = 0; c < pa.chunks; ++c) {
-      const int ca = c & 1;
-      mbar_wait(&a_full[ca], (c >> 1) & 1);
-      const uint32_t a_base = lo_patch + (uint32_t)(ca * MT) * patch_units;
-      for (int bs = 0; bs < nbs; ++bs) {
-        mbar_wait(&b_full[s], ph);
-        tc_fence_after();
-        if (elect_one()) {
-          const int nk = min(KPS, T - bs * KPS);
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      mbar_wait(&tmem_empty_bar[acc_i], e_ph);  // the epilogue has drained this accumulator set
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + acc_i * (MT * kAcc);
+      uint32_t accumulate = 0;
+      for (int c = 0; c < pa.chunks; ++c) {
+        mbar_wait(&a_full[ca], a_ph);
+        const uint32_t a_base = lo_patch + (uint32_t)(ca * MT) * patch_units;
+        for (int bs = 0; bs < nbs; ++bs) {
+          mbar_wait(&b_full[s], ph);
+          tc_fence_after();
+          if (elect_one()) {
+            const int nk = min(KPS, T - bs * KPS);
 #pragma unroll
-          for (int j = 0; j < KPS; ++j) {
-            if (j < nk) {
-              const uint32_t b_lo = b_lo0 + j * (kBBytes >> 4);
-              const uint32_t aoff = s_aoff[bs * KPS + j];
+            for (int j = 0; j < KPS; ++j) {
+              if (j < nk) {
+                const uint32_t b_lo = b_lo0 + j * (kBBytes >> 4);
+                const uint32_t aoff = s_aoff[bs * KPS + j];
 #pragma unroll
-              for (int mt = 0; mt < MT; ++mt) {
-                const uint32_t a_lo = a_base + mt * patch_units + aoff;
+                for (int mt = 0; mt < MT; ++mt) {
+                  const uint32_t a_lo = a_base + mt * patch_units + aoff;
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {  // 4 x (K = 16 channels = 32 bytes inside the swizzle atom)
-                  umma_bf16(tmem_base + mt * kAcc, smem_desc_join(a_lo + 2 * kk, desc_hi_a),
-                            smem_desc_join(b_lo + 2 * kk, desc_hi_b), idesc, (kk == 0 && j == 0) ? acc : 1u);
+                  for (int kk = 0; kk < 4; ++kk) {  // 4 x (K = 16 channels = 32 bytes inside the swizzle atom)
+                    umma_bf16(tmem_acc + mt * kAcc, smem_desc_join(a_lo + 2 * kk, desc_hi_a),
+                              smem_desc_join(b_lo + 2 * kk, desc_hi_b), idesc, (kk == 0 && j == 0) ? accumulate : 1u);
+                  }
                 }
               }
             }
+            umma_commit(&b_empty[s]);  // weight slot free once these MMAs retire
+            if (bs == nbs - 1) {
+              umma_commit(&a_empty[ca]);  // ... and the patch buffer after the chunk's last tap
+              if (c == pa.chunks - 1) umma_commit(&tmem_full_bar[acc_i]);
+            }
           }
-          umma_commit(&b_empty[s]);  // weight slot free once these MMAs retire
-          if (bs == nbs - 1) {
-            umma_commit(&a_empty[ca]);  // ... and the patch buffer after the chunk's last tap
-            if (c == pa.chunks - 1) umma_commit(tmem_full_bar);
+          __syncwarp();
+          accumulate = 1;
+          b_lo0 += kStageBytes >> 4;
+          if (++s == pa.b_stages) {
+            s = 0;
+            ph ^= 1;
+            b_lo0 = lo_ring;
           }
         }
-        __syncwarp();
-        acc = 1;
-        b_lo0 += kStageBytes >> 4;
-        if (++s == pa.b_stages) {
-          s = 0;
-          ph ^= 1;
-          b_lo0 = lo_ring;
-        }
+        if (ca == 1) a_ph ^= 1;
+        ca ^= 1;
+      }
+      if (++acc_i == NACC) {
+        acc_i = 0;
+        e_ph ^= 1;
       }
     }
     if (prof && lane == 0) prof[4] = clock64();
@@ -215,15 +236,29 @@ igemm_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
     }
-    mbar_wait_relaxed(tmem_full_bar, 0);
-    tc_fence_after();
-    pdl_launch_dependents();  // main loop done: the next kernel may start launching behind the epilogue
-    if (prof && threadIdx.x == 64) prof[5] = clock64();
+    int acc_i = 0;
+    uint32_t f_ph = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      const int n = item / tiles_per_img, r = item - n * tiles_per_img;
+      const int th = r / args.tiles_w, tw = r - th * args.tiles_w;
+      const int wo0 = tw * 8, ho0 = th * 16 * MT;
+      mbar_wait_relaxed(&tmem_full_bar[acc_i], f_ph);
+      tc_fence_after();
+      if (item + (int)gridDim.x >= items) pdl_launch_dependents();  // last main loop done: the next kernel may launch
+      if (prof && threadIdx.x == 64 && item == (int)blockIdx.x) prof[5] = clock64();
+      const uint32_t tmem_acc = tmem_base + acc_i * (MT * kAcc);
 #pragma unroll 1
-    for (int mt = 0; mt < MT; ++mt) {
-      if (ho0 + mt * 16 >= args.Ho) break;  // ragged CTA row: the stacked tile is entirely outside
-      epilogue_tile<BN>(args, tmem_base + mt * kAcc, smem, s_bias, n, ho0 + mt * 16 + (row >> 3), wo0 + (row & 7), nblk,
-                        args.out_off[0], q, lane, prof);
+      for (int mt = 0; mt < MT; ++mt) {
+        if (ho0 + mt * 16 >= args.Ho) break;  // ragged CTA row: the stacked tile is entirely outside
+        epilogue_tile<BN, (BN >= 64 ? 64 : BN)>(args, tmem_acc + mt * kAcc, stage, s_bias, n, ho0 + mt * 16 + (row >> 3),
+                                                wo0 + (row & 7), nblk, args.out_off[0], q, lane, prof);
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[acc_i]);  // this thread's TMEM reads of the set are complete
+      if (++acc_i == NACC) {
+        acc_i = 0;
+        f_ph ^= 1;
+      }
     }
   }
   if (prof && threadIdx.x == 64) prof[6] = clock64();
@@ -265,7 +300,6 @@ static void launch_patch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const
   CGB_CHECK(pa.b_stages >= 2 && pa.b_stages <= kPatchMaxBStages, "patch igemm: weight ring depth out of range");
   CGB_CHECK(pa.k * pa.k <= 64, "patch igemm: at most 64 filter taps");
   const int ring = pa.b_stages * KPS * kBBytes;
-  CGB_CHECK(BN < 64 || ring >= 128 * BN * 2, "patch igemm: weight ring smaller than the epilogue staging area");
   const int smem = 1024 + ring + 2 * MT * pa.patch_bytes + kPatchMisc;
   CGB_CHECK(smem <= kPatchSmemMax, "patch igemm: shared memory budget exceeded");
   launch_pdl(kern, grid, dim3(224), (size_t)smem, stream, tmA, tmB, args, pa);

@@ -189,7 +189,6 @@ static bool try_patch(IgemmPlan& p, const TensorDesc& act, bool padded_view, con
     int st = budget / stage;
     if (st > 8) st = 8;
     if (st < 2) return false;
-    if (bn >= 64 && st * stage < 128 * bn * 2) return false;
     *stages = st;
     return true;
   };
@@ -211,6 +210,9 @@ static bool try_patch(IgemmPlan& p, const TensorDesc& act, bool padded_view, con
         if (done || (forced_mt && mt != forced_mt)) continue;
         // stacking wastes a whole tile when the tile-row count is odd (the 66-row padded-domain gradients: 5 rows)
         if (mt == 2 && !forced_mt && tile_rows % 2 != 0 && tile_rows < 9) continue;
+        // BN = 256: two stacked tiles would take all 512 TMEM columns and leave no second accumulator set for the
+        // epilogue / main-loop overlap of the persistent kernel
+        if (mt == 2 && !forced_mt && bn == 256) continue;
         if (!fits(bn, mt, &st)) continue;
         const long long ctas = (long long)act.N * tiles_w * ((tile_rows + mt - 1) / mt) * (prow / bn);
         best_bn = bn, best_mt = mt, best_stages = st;  // the last (smallest) candidate wins if none reaches the target
@@ -232,8 +234,12 @@ static bool try_patch(IgemmPlan& p, const TensorDesc& act, bool padded_view, con
   p.args.tiles_h = (tile_rows + p.MT - 1) / p.MT;  // CTA rows
   p.args.Ho = Ho;
   p.args.Wo = Wo;
-  p.num_ctas_m = act.N * tiles_w * p.args.tiles_h;
-  p.num_tiles = p.num_ctas_m;
+  // persistent CTAs: at most one per SM (per N block); each loops over its share of the work items, overlapping
+  // the epilogue of one item with the main loop of the next (two TMEM accumulator sets)
+  pa.num_items = act.N * tiles_w * p.args.tiles_h;
+  p.pargs.num_items = pa.num_items;
+  p.num_ctas_m = std::min(pa.num_items, std::max(1, sm_count / p.n_blocks));
+  p.num_tiles = pa.num_items;
   p.tmA = view_s1(act, padded_view, 64, box_w, pa.PH);
   p.tmB = make_tmap_2d(w, prow, Kw, Kw, 64, p.BN, 128);
   return true;
