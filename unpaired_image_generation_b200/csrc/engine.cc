@@ -706,6 +706,45 @@ void cgb_engine::record_programs() {
     pr.dep(wlane, main_lane);
   };
 
+  // ---- optimiser + bf16 weight refresh
+  for (int g = 0; g < 2; ++g) {
+    std::vector<PackEntry> table;
+    int max_elems = 0;
+    for (int net = g * 2; net < g * 2 + 2; ++net)
+      for (const LayerParam& p : layers[net]) {
+        PackEntry e{};
+        e.src_off = p.w_off;
+        e.wf_off = p.wf_off;
+        e.wt_off = p.wt_off;
+        e.Cout = p.spec.Cout;
+        e.Cin = p.spec.Cin;
+        e.T = p.spec.taps();
+        e.CinS = p.spec.CinS;
+        e.CoutS = p.spec.CoutS;
+        e.wx_off = p.wx_off;
+        e.wx_pitch = 256;
+        table.push_back(e);
+        max_elems = std::max(max_elems, e.Cout * e.Cin * e.T);
+      }
+    pack_table[g] = static_cast<PackEntry*>(meta_upload(table.data(), table.size() * sizeof(PackEntry)));
+    pack_count[g] = (int)table.size();
+    pack_max[g] = max_elems;
+    const PackEntry* tb = pack_table[g];
+    const int cnt = pack_count[g], mx = pack_max[g];
+    float* p = P[g];
+    bf16* arena = pack[g];
+    prog_refresh[g].add([p, tb, cnt, mx, arena](cudaStream_t s) { pack_weights(p, tb, cnt, mx, arena, s); });
+    float *gg = G[g], *mm = M[g], *vv = V[g];
+    const long long n = group_numel[g];
+    int* stp = adam_step[g];
+    float* hyp = adam_hyper[g];
+    prog_adam[g].add(
+        [E, p, gg, mm, vv, n, stp, hyp](cudaStream_t s) {
+          cgb::adam_step(p, gg, mm, vv, n, E->cfg.lr, E->cfg.beta1, E->cfg.beta2, E->cfg.eps, stp, hyp, E->grad_scale, s);
+        },
+        2);
+    prog_adam[g].add([p, tb, cnt, mx, arena](cudaStream_t s) { pack_weights(p, tb, cnt, mx, arena, s); });
+  }
   if (!infer_only) {
   // ---------------------------------------------------------------- step programs
   const TensorDesc &fake_B = img[CGB_IMG_FAKE_B], &rec_A = img[CGB_IMG_REC_A], &fake_A = img[CGB_IMG_FAKE_A],
@@ -933,6 +972,17 @@ void cgb_engine::record_programs() {
     emit_dis_backward(pr, &sink, dis[3], ds[1], 1.f, 0.5f, CGB_LOSS_D_B, true, nullptr);
     emit_dis_backward(pr, &sink, dis[1], ds[1], 0.f, 0.5f, CGB_LOSS_D_B, true, nullptr);
     pr.mark("D_B all done");
+    // both discriminators' gradients are complete: Adam(D) + bf16 refresh run here, in the shadow of the generator
+    // backward chains (nothing later in the step reads the discriminator weights)
+    pr.dep(3, 2);
+    pr.cur_lane = 2;
+    {
+      const long long before = pr.launches;
+      for (size_t i = 0; i < prog_adam[CGB_GROUP_D].ops.size(); ++i)
+        pr.add(prog_adam[CGB_GROUP_D].ops[i], 0, prog_adam[CGB_GROUP_D].kinds[i]);
+      pr.launches = before + prog_adam[CGB_GROUP_D].launches;
+    }
+    pr.mark("Adam(D) done");
     // the passes that produced the fakes
     GradSrc g;
     g.fold = 3;
@@ -961,45 +1011,6 @@ void cgb_engine::record_programs() {
     pr.mark("step end (before Adam)");
   }
   }  // !infer_only
-  // ---- optimiser + bf16 weight refresh
-  for (int g = 0; g < 2; ++g) {
-    std::vector<PackEntry> table;
-    int max_elems = 0;
-    for (int net = g * 2; net < g * 2 + 2; ++net)
-      for (const LayerParam& p : layers[net]) {
-        PackEntry e{};
-        e.src_off = p.w_off;
-        e.wf_off = p.wf_off;
-        e.wt_off = p.wt_off;
-        e.Cout = p.spec.Cout;
-        e.Cin = p.spec.Cin;
-        e.T = p.spec.taps();
-        e.CinS = p.spec.CinS;
-        e.CoutS = p.spec.CoutS;
-        e.wx_off = p.wx_off;
-        e.wx_pitch = 256;
-        table.push_back(e);
-        max_elems = std::max(max_elems, e.Cout * e.Cin * e.T);
-      }
-    pack_table[g] = static_cast<PackEntry*>(meta_upload(table.data(), table.size() * sizeof(PackEntry)));
-    pack_count[g] = (int)table.size();
-    pack_max[g] = max_elems;
-    const PackEntry* tb = pack_table[g];
-    const int cnt = pack_count[g], mx = pack_max[g];
-    float* p = P[g];
-    bf16* arena = pack[g];
-    prog_refresh[g].add([p, tb, cnt, mx, arena](cudaStream_t s) { pack_weights(p, tb, cnt, mx, arena, s); });
-    float *gg = G[g], *mm = M[g], *vv = V[g];
-    const long long n = group_numel[g];
-    int* stp = adam_step[g];
-    float* hyp = adam_hyper[g];
-    prog_adam[g].add(
-        [E, p, gg, mm, vv, n, stp, hyp](cudaStream_t s) {
-          cgb::adam_step(p, gg, mm, vv, n, E->cfg.lr, E->cfg.beta1, E->cfg.beta2, E->cfg.eps, stp, hyp, E->grad_scale, s);
-        },
-        2);
-    prog_adam[g].add([p, tb, cnt, mx, arena](cudaStream_t s) { pack_weights(p, tb, cnt, mx, arena, s); });
-  }
   {  // both optimisers side by side
     Program& pr = prog_adams;
     pr.fork(2);
@@ -1011,7 +1022,7 @@ void cgb_engine::record_programs() {
     pr.join(2);
     pr.cur_lane = 0;
   }
-  segments[CGB_SEG_STEP].seq = {&prog_set_inputs, &prog_step, &prog_adams};
+  segments[CGB_SEG_STEP].seq = {&prog_set_inputs, &prog_step, &prog_adam[CGB_GROUP_G]};
   segments[CGB_SEG_G].seq = {&prog_set_inputs, &prog_cycle, &prog_G};
   segments[CGB_SEG_D].seq = {&prog_D};
   segments[CGB_SEG_ADAM_G].seq = {&prog_adam[0]};
