@@ -252,12 +252,31 @@ def run_b200(args):
                 res_fprop, res_dgrad, res_wgrad = pick("fprop res."), pick("dgrad res."), pick("wgrad res.")
             except Exception:
                 os.environ.pop("CGB_PROFILE_OPS", None)
-        achieved = fl_ig / (ms_ig * 1e-3) / 1e12
+        # Dominant kernel: igemm_patch_kernel on the residual-block conv (256->256, 3x3 reflect, 64x64 map at 256x256):
+        # 216 of the 330 fprop/dgrad launches of a step and 83 % of its conv FLOPs.  `achieved` = algorithmic FLOPs of
+        # one launch (2 * pixels * 256 * 256 * 9; dgrad: the same taps on the 66x66 padded domain, counted on the
+        # 64x64 map) / the average launch duration measured live with CUDA events on the launching stream.
+        res_flops = 2.0 * batch * (size // 4) ** 2 * 256 * 256 * 9
+        agg = fl_ig / (ms_ig * 1e-3) / 1e12
+        if res_fprop and res_dgrad:
+            us = 0.5 * (res_flops / (res_fprop * 1e12) + res_flops / (res_dgrad * 1e12)) * 1e6
+            achieved = res_flops / (us * 1e-6) / 1e12
+        else:
+            us, achieved = None, agg
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r01_e_ncu_full_res_conv.txt)
+        ncu_traffic = {(1, 256): 3.456e6, (8, 256): 19.067e6}.get((batch, size))
         roofline = {
-            "bound": "tensor", "kernel": "igemm_conv_kernel (tcgen05 implicit-GEMM conv fprop/dgrad, all layer shapes)",
+            "bound": "tensor",
+            "kernel": "igemm_patch_kernel<BN,MT,KPS> (persistent tcgen05 patch-resident implicit GEMM), residual-block conv "
+                      "256->256 3x3 reflect, fprop + dgrad",
             "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"],
-            "traffic": None, "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
-            "launches_per_step": n_ig, "ms_per_step": ms_ig, "flops_per_step": fl_ig,
+            "traffic": ncu_traffic,
+            "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
+            "us_per_launch": us, "flops_per_launch": res_flops, "launches_per_step": 216,
+            "algorithmic_bytes_per_launch": 2.0 * batch * ((size // 4 + 2) ** 2 + (size // 4) ** 2) * 256 + 2.0 * 256 * 256 * 9,
+            "res_block_conv_tflops": {"fprop": res_fprop, "dgrad": res_dgrad, "wgrad": res_wgrad},
+            "all_igemm_launches": {"achieved": agg, "frac": agg / peaks["tf_sustained"], "launches_per_step": n_ig,
+                                   "ms_per_step_serial": ms_ig, "flops_per_step": fl_ig},
             "other_kernels": {
                 "wgrad_kernel(tcgen05)": {"ms_per_step": ms_wg, "launches": n_wg,
                                           "tflops": fl_wg / (ms_wg * 1e-3) / 1e12 if ms_wg > 0 else None},
@@ -266,8 +285,6 @@ def run_b200(args):
                 "instnorm_pointwise": {"ms_per_step": ms_pw, "launches": n_pw},
             },
             "segments_ms": seg_ms,
-            "res_block_conv_tflops": {"fprop": res_fprop, "dgrad": res_dgrad, "wgrad": res_wgrad,
-                                      "frac_of_peak_fprop": (res_fprop / peaks["tf_sustained"]) if res_fprop else None},
             "step_conv_tflops": eng.conv_flops_per_step / (ms_step * 1e-3) / 1e12,
             "step_conv_frac_of_peak": eng.conv_flops_per_step / (ms_step * 1e-3) / 1e12 / peaks["tf_sustained"],
         }

@@ -529,10 +529,10 @@ WgradPlan plan_wgrad(const ConvSpec& s, const TensorDesc& x, const TensorDesc& d
   // split-K so that the launch has about `frac` of a wave of CTAs: long K per CTA amortises the prologue and
   // the fp32 reduction epilogue, and leaves room for the other lanes of the step graph
   static const double frac = std::getenv("CGB_WGRAD_FRAC") ? std::atof(std::getenv("CGB_WGRAD_FRAC")) : 0.85;
-  // ... but never shorter than `min_chunks` 64-pixel chunks per CTA: below that the prologue and the fp32
+  // ... but never shorter than `min_chunks` (64) 64-pixel chunks per CTA: below that the prologue and the fp32
   // reduction of the 128 x BNW tile dominate (measured at batch 1: split 6 -> 2 on the residual layers is
   // 7 % faster end to end although the isolated kernel is slower)
-  static const long long min_chunks = std::getenv("CGB_WGRAD_MIN_CHUNKS") ? std::atoll(std::getenv("CGB_WGRAD_MIN_CHUNKS")) : 32;
+  static const long long min_chunks = std::getenv("CGB_WGRAD_MIN_CHUNKS") ? std::atoll(std::getenv("CGB_WGRAD_MIN_CHUNKS")) : 64;
   long long split = (long long)(sm_count * frac) / base_ctas;
   split = std::max(1LL, std::min(split, std::max(1LL, total_chunks / min_chunks)));
   p.args.split_k = (int)split;

@@ -207,6 +207,7 @@ void cgb_engine::layout(Arena& A) {
     g.dyH = A.tensor(N, H2, H2, 128, 0);
     g.dxH = A.tensor(N, H2, H2, 128, 0);
     g.dyQ = A.tensor(N, H4, H4, 256, 0);
+    g.dyQ2 = A.tensor(N, H4, H4, 256, 0);
     g.GQ[0] = A.tensor(N, H4, H4, 256, 0);
     g.GQ[1] = A.tensor(N, H4, H4, 256, 0);
     g.dbpQ = A.tensor(N, H4 + 2, H4 + 2, 256, 0);
@@ -530,17 +531,21 @@ void cgb_engine::record_programs() {
     float2* bs = P.bstats;
     const int main_lane = pr.cur_lane, wlane = pr.cur_lane + kPassLanes;
     // weight gradient on the side lane, beside the input gradient of the same layer
+    std::vector<int> wgrad_done;  // record ids on the side lane, one per weight gradient issued so far
     auto add_wgrad = [&](Program& pr_, double* fl_, const LayerParam& Lp, const TensorDesc& x, const TensorDesc& dy,
                          bf16* colbuf, size_t colbuf_elems, const TensorDesc* precol = nullptr) {
       pr_.dep(main_lane, wlane);
       pr_.cur_lane = wlane;
       add_wgrad_on_lane(pr_, fl_, Lp, x, dy, colbuf, colbuf_elems, precol);
+      wgrad_done.push_back(pr_.record(wlane));
       pr_.cur_lane = main_lane;
     };
-    // the next layer overwrites the dy buffer: wait for the side lane first
+    // A layer's dy buffer is read by its weight gradient on the side lane.  Consecutive layers never share a dy
+    // buffer (dyQ / dyQ2 alternate along the residual chain), layers two apart may: before overwriting, wait for
+    // the weight gradient issued two layers back -- the previous one keeps running beside this layer's chain.
     auto add_in_bwd = [&](Program& pr_, const TensorDesc& y, const float2* stats, float2* bstats, GradSrc g, int act,
                           const TensorDesc* da_store, const TensorDesc& dy) {
-      pr_.dep(wlane, main_lane);
+      if (wgrad_done.size() >= 2) pr_.wait(main_lane, wgrad_done[wgrad_done.size() - 2]);
       add_in_bwd_raw(pr_, y, stats, bstats, g, act, da_store, dy);
     };
     pr.add([bs, bytes = P.stats_bytes](cudaStream_t s) { CGB_CUDA(cudaMemsetAsync(bs, 0, bytes, s)); }, 0, kOpMemset);
@@ -606,9 +611,9 @@ void cgb_engine::record_programs() {
       g = GradSrc();
       g.g2 = &S.dbpQ;
       g.fold = 1;
-      add_in_bwd(pr, P.y1[k], st + P.stat_off[3 + 2 * k], bs + P.stat_off[3 + 2 * k], g, kActRelu, nullptr, S.dyQ);
-      add_wgrad(pr, fl, L[3 + 2 * k], P.xp[k], S.dyQ, S.colbuf, S.colbuf_elems);
-      add_dgrad(pr, fl, L[3 + 2 * k], S.dyQ, S.dxpQ);
+      add_in_bwd(pr, P.y1[k], st + P.stat_off[3 + 2 * k], bs + P.stat_off[3 + 2 * k], g, kActRelu, nullptr, S.dyQ2);
+      add_wgrad(pr, fl, L[3 + 2 * k], P.xp[k], S.dyQ2, S.colbuf, S.colbuf_elems);
+      add_dgrad(pr, fl, L[3 + 2 * k], S.dyQ2, S.dxpQ);
     }
     // down2 output feeds block 0 twice (conv path + skip): G_0 = G_1 + fold(dxp_0)
     g = GradSrc();

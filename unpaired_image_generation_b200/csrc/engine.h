@@ -201,7 +201,7 @@ struct DisPass {
 };
 
 struct GenScratch {  // backward scratch of one generator pass (one set per lane)
-  TensorDesc dpre_head, dxp_head, dyF, dxF, dyH, dxH, dyQ, GQ[2], dbpQ, dxpQ;
+  TensorDesc dpre_head, dxp_head, dyF, dxF, dyH, dxH, dyQ, dyQ2, GQ[2], dbpQ, dxpQ;  // dyQ / dyQ2 alternate along the residual chain
   bf16* colbuf = nullptr;  // im2col scratch of the 3-channel operands (stem / head weight gradients)
   size_t colbuf_elems = 0;
 };
