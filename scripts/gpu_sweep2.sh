@@ -11,7 +11,7 @@ try:
     d = json.load(open("gpurun_out/bench_combo.json"))
     r = d["roofline"]
     e = d.get("extra_batch") or {}
-    print("%-50s b1 %.3f ms (%.1f img/s) serial igemm %.2f wgrad %.2f pw %.2f | b8 %s" % (sys.argv[1], d["ms_per_step"], d["value"], r["ms_per_step"], r["other_kernels"]["wgrad_kernel(tcgen05)"]["ms_per_step"], r["other_kernels"]["instnorm_pointwise"]["ms_per_step"], ("%.2f ms" % e["ms_per_step"]) if e else "-"))
+    print("%-50s b1 %.3f ms (%.1f img/s) serial igemm %.2f wgrad %.2f pw %.2f | b8 %s" % (sys.argv[1], d["ms_per_step"], d["value"], r["all_igemm_launches"]["ms_per_step_serial"], r["other_kernels"]["wgrad_kernel(tcgen05)"]["ms_per_step"], r["other_kernels"]["instnorm_pointwise"]["ms_per_step"], ("%.2f ms" % e["ms_per_step"]) if e else "-"))
 except Exception as ex:
     print(sys.argv[1], "parse error", ex)
 PY

@@ -87,6 +87,8 @@ struct PatchArgs {
   int sbo;          // bytes between consecutive 8-pixel row groups of the M tile
   int base_offset;  // 1: put (start address >> 7) & 7 into the descriptor's base-offset field
   int b_stages;     // weight-tile ring depth
+  int ka;           // channels per patch row: 64 (128-byte rows) or 16 (32-byte rows of the image-like tensors)
+  int b_resident;   // 1: the ring holds the whole filter; it is loaded once and never recycled
   int num_items;    // M-direction work items (MT stacked tiles each); a CTA loops over blockIdx.x + i * gridDim.x
 };
 

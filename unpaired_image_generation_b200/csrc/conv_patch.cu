@@ -27,15 +27,21 @@ using namespace ptx;
 
 namespace {
 constexpr int kPatchStageBytes = 16384;  // epilogue staging: 128 rows x 64 columns x bf16
-constexpr int kPatchMisc = kPatchStageBytes + 256 /*barriers*/ + 512 /*tap tables*/ + 1024 /*bias*/;
-constexpr int kPatchMaxBStages = 8;
+constexpr int kPatchMisc = kPatchStageBytes + 512 /*barriers*/ + 512 /*tap tables*/ + 1024 /*bias*/;
+constexpr int kPatchMaxBStages = 16;
 constexpr int kPatchSmemMax = 232448;
 }  // namespace
 
-template <int BN, int MT, int KPS>
+// KA = channels per patch row: 64 (128-byte rows, SWIZZLE_128B, four K = 16 MMAs per tap) or 16 (the 16-stored-
+// channel image-like tensors: 32-byte rows, SWIZZLE_32B, one MMA per tap).  Weight boxes are always 64 K-elements
+// wide (SWIZZLE_128B): with KA = 16 one box carries four consecutive taps.
+template <int BN, int MT, int KPS, int KA>
 __global__ void __launch_bounds__(224, 1)
 igemm_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const IgemmArgs args, const PatchArgs pa) {
+  static_assert(KA == 64 || KA == 16, "patch rows carry 64 or 16 channels");
+  constexpr int TPB = 64 / KA;   // taps per weight box
+  constexpr int kKK = KA / 16;   // K = 16 MMAs per tap
   constexpr int kBBytesTx = BN * 128;
   constexpr int kBBytes = (kBBytesTx + 1023) / 1024 * 1024;
   constexpr int kStageBytes = KPS * kBBytes;
@@ -58,9 +64,9 @@ igemm_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   uint64_t* tmem_full_bar = a_empty + 2;    // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;  // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-  uint32_t* s_aoff = reinterpret_cast<uint32_t*>(misc + 256);  // per tap: descriptor start offset (16 B units)
-  int32_t* s_bk = reinterpret_cast<int32_t*>(misc + 256 + 256);  // per tap: K offset in the packed weights
-  float* s_bias = reinterpret_cast<float*>(misc + 256 + 512);
+  uint32_t* s_aoff = reinterpret_cast<uint32_t*>(misc + 512);  // per tap: descriptor start offset (16 B units)
+  int32_t* s_bk = reinterpret_cast<int32_t*>(misc + 512 + 256);  // per tap: K offset in the packed weights
+  float* s_bias = reinterpret_cast<float*>(misc + 512 + 512);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -69,16 +75,19 @@ igemm_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (prof && threadIdx.x == 0) prof[0] = clock64();
 
   const int T = pa.k * pa.k;
-  const int nbs = (T + KPS - 1) / KPS;  // weight stages per channel chunk
+  const int nbox = (T + TPB - 1) / TPB;      // weight boxes per channel chunk
+  const int nbs = (nbox + KPS - 1) / KPS;    // weight stages per channel chunk
   // persistent: this CTA owns the M-direction work items blockIdx.x, blockIdx.x + gridDim.x, ...
   // (a work item is MT stacked tiles of 16 x 8 output pixels of one image)
   const int items = pa.num_items;
   const int tiles_per_img = args.tiles_w * args.tiles_h;
 
-  for (int i = threadIdx.x; i < T; i += blockDim.x) {
+  // tables indexed by the WEIGHT tap w (taps are swept in weight order; input gradients read the patch backwards)
+  for (int w = threadIdx.x; w < T; w += blockDim.x) {
+    const int i = pa.flip ? T - 1 - w : w;
     const int py = i / pa.k, px = i - py * pa.k;
-    s_aoff[i] = (uint32_t)(py * pa.row_step + px * pa.col_step);
-    s_bk[i] = (pa.flip ? T - 1 - i : i) * pa.tap_stride;
+    s_aoff[w] = (uint32_t)(py * pa.row_step + px * pa.col_step);
+    s_bk[w] = w * pa.tap_stride;
   }
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -123,7 +132,7 @@ igemm_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           for (int mt = 0; mt < MT; ++mt) {
             uint8_t* dst = patches + (ca * MT + mt) * pa.patch_bytes;
             for (int b = 0; b < pa.nbox; ++b)
-              tma_load_5d(dst + b * pa.box_bytes, &tmA, &a_full[ca], c * 64, wo0 + pa.ox + b, 0,
+              tma_load_5d(dst + b * pa.box_bytes, &tmA, &a_full[ca], c * KA, wo0 + pa.ox + b, 0,
                           ho0 + mt * 16 + pa.oy, n);
           }
           if (prof && c == 0 && item == (int)blockIdx.x) prof[2] = clock64();
@@ -139,15 +148,20 @@ igemm_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     uint32_t ph = 1;
     uint8_t* sb = smem;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      if (pa.b_resident && item != (int)blockIdx.x) break;  // the whole filter stays in shared memory after the first item
       for (int c = 0; c < pa.chunks; ++c) {
         for (int bs = 0; bs < nbs; ++bs) {
           mbar_wait(&b_empty[s], ph);
           if (elect_one()) {
-            const int nk = min(KPS, T - bs * KPS);
+            const int nk = min(KPS, nbox - bs * KPS);
             mbar_arrive_expect_tx(&b_full[s], nk * kBBytesTx);
 #pragma unroll
             for (int j = 0; j < KPS; ++j) {
-              if (j < nk) tma_load_2d(sb + j * kBBytes, &tmB, &b_full[s], s_bk[bs * KPS + j] + c * 64, nblk * BN);
+              if (j < nk) {
+                const int box = bs * KPS + j;
+                const int kcoord = (KA == 64) ? s_bk[box] + c * 64 : box * 64;
+                tma_load_2d(sb + j * kBBytes, &tmB, &b_full[s], kcoord, nblk * BN);
+              }
             }
           }
           __syncwarp();
@@ -165,7 +179,7 @@ igemm_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = make_idesc_bf16(128, BN < 16 ? 16 : BN, 0, 0);
     constexpr uint32_t desc_hi_b = smem_desc_hi(1024, 2);
-    const uint32_t desc_hi_a = smem_desc_hi((uint32_t)pa.sbo, 2);
+    const uint32_t desc_hi_a = smem_desc_hi((uint32_t)pa.sbo, swizzle_layout_type(KA * 2));
     const uint32_t lo_ring = smem_u32(smem) >> 4;
     const uint32_t lo_patch = smem_u32(patches) >> 4;
     const uint32_t patch_units = (uint32_t)pa.patch_bytes >> 4;
@@ -181,27 +195,34 @@ igemm_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         mbar_wait(&a_full[ca], a_ph);
         const uint32_t a_base = lo_patch + (uint32_t)(ca * MT) * patch_units;
         for (int bs = 0; bs < nbs; ++bs) {
-          mbar_wait(&b_full[s], ph);
+          mbar_wait(&b_full[s], pa.b_resident ? 0u : ph);  // resident filter: filled once, never recycled
           tc_fence_after();
           if (elect_one()) {
-            const int nk = min(KPS, T - bs * KPS);
+            const int nk = min(KPS, nbox - bs * KPS);
 #pragma unroll
             for (int j = 0; j < KPS; ++j) {
               if (j < nk) {
-                const uint32_t b_lo = b_lo0 + j * (kBBytes >> 4);
-                const uint32_t aoff = s_aoff[bs * KPS + j];
+                const int box = bs * KPS + j;
 #pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {
-                  const uint32_t a_lo = a_base + mt * patch_units + aoff;
+                for (int ts = 0; ts < TPB; ++ts) {
+                  const int w = box * TPB + ts;  // weight tap
+                  if (TPB > 1 && w >= T) break;
+                  const uint32_t b_lo = b_lo0 + j * (kBBytes >> 4) + ts * (KA * 2 / 16);
+                  const uint32_t aoff = s_aoff[w];
 #pragma unroll
-                  for (int kk = 0; kk < 4; ++kk) {  // 4 x (K = 16 channels = 32 bytes inside the swizzle atom)
-                    umma_bf16(tmem_acc + mt * kAcc, smem_desc_join(a_lo + 2 * kk, desc_hi_a),
-                              smem_desc_join(b_lo + 2 * kk, desc_hi_b), idesc, (kk == 0 && j == 0) ? accumulate : 1u);
+                  for (int mt = 0; mt < MT; ++mt) {
+                    const uint32_t a_lo = a_base + mt * patch_units + aoff;
+#pragma unroll
+                    for (int kk = 0; kk < kKK; ++kk) {  // K = 16 channels = 32 bytes inside the swizzle atom
+                      umma_bf16(tmem_acc + mt * kAcc, smem_desc_join(a_lo + 2 * kk, desc_hi_a),
+                                smem_desc_join(b_lo + 2 * kk, desc_hi_b), idesc,
+                                (kk == 0 && j == 0 && ts == 0) ? accumulate : 1u);
+                    }
                   }
                 }
               }
             }
-            umma_commit(&b_empty[s]);  // weight slot free once these MMAs retire
+            if (!pa.b_resident) umma_commit(&b_empty[s]);  // weight slot free once these MMAs retire
             if (bs == nbs - 1) {
               umma_commit(&a_empty[ca]);  // ... and the patch buffer after the chunk's last tap
               if (c == pa.chunks - 1) umma_commit(&tmem_full_bar[acc_i]);
@@ -284,21 +305,22 @@ static bool patch_kps1() {
   static const bool v = std::getenv("CGB_PATCH_KPS1") != nullptr;
   return v;
 }
-int igemm_patch_kps(int BN) { return BN >= 256 ? 1 : BN >= 64 ? (patch_kps1() ? 1 : 3) : 7; }
+int igemm_patch_kps(int BN, int ka) { return (ka == 16 || BN >= 256) ? 1 : BN >= 64 ? (patch_kps1() ? 1 : 3) : 7; }
 int igemm_patch_smem_budget() { return patch_smem_cap() - 1024 - kPatchMisc; }
 
-template <int BN, int MT, int KPS>
+template <int BN, int MT, int KPS, int KA>
 static void launch_patch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmArgs& args, const PatchArgs& pa,
                            dim3 grid, cudaStream_t stream) {
   constexpr int kBBytes = (BN * 128 + 1023) / 1024 * 1024;
   static bool configured = false;
-  auto kern = igemm_patch_kernel<BN, MT, KPS>;
+  auto kern = igemm_patch_kernel<BN, MT, KPS, KA>;
   if (!configured) {
     CGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPatchSmemMax));
     configured = true;
   }
   CGB_CHECK(pa.b_stages >= 2 && pa.b_stages <= kPatchMaxBStages, "patch igemm: weight ring depth out of range");
   CGB_CHECK(pa.k * pa.k <= 64, "patch igemm: at most 64 filter taps");
+  CGB_CHECK(pa.ka == KA && (KA == 64 || pa.chunks == 1), "patch igemm: channel-chunk width mismatch");
   const int ring = pa.b_stages * KPS * kBBytes;
   const int smem = 1024 + ring + 2 * MT * pa.patch_bytes + kPatchMisc;
   CGB_CHECK(smem <= kPatchSmemMax, "patch igemm: shared memory budget exceeded");
@@ -308,19 +330,30 @@ static void launch_patch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const
 void launch_igemm_patch(int BN, int MT, const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmArgs& args,
                         const PatchArgs& pa, int num_ctas_m, int n_blocks, cudaStream_t stream) {
   dim3 grid(num_ctas_m, n_blocks, 1);
+  if (pa.ka == 16) {
+    switch (BN * 10 + MT) {
+      case 2561: return launch_patch_t<256, 1, 1, 16>(tmA, tmB, args, pa, grid, stream);
+      case 1282: return launch_patch_t<128, 2, 1, 16>(tmA, tmB, args, pa, grid, stream);
+      case 1281: return launch_patch_t<128, 1, 1, 16>(tmA, tmB, args, pa, grid, stream);
+      case 642: return launch_patch_t<64, 2, 1, 16>(tmA, tmB, args, pa, grid, stream);
+      case 641: return launch_patch_t<64, 1, 1, 16>(tmA, tmB, args, pa, grid, stream);
+      default: break;
+    }
+    CGB_CHECK(false, "launch_igemm_patch: unsupported 16-channel config BN=" + std::to_string(BN) + " MT=" + std::to_string(MT));
+  }
   switch (BN * 10 + MT) {
-    case 2562: return launch_patch_t<256, 2, 1>(tmA, tmB, args, pa, grid, stream);
-    case 2561: return launch_patch_t<256, 1, 1>(tmA, tmB, args, pa, grid, stream);
-    case 1282: return patch_kps1() ? launch_patch_t<128, 2, 1>(tmA, tmB, args, pa, grid, stream)
-                                   : launch_patch_t<128, 2, 3>(tmA, tmB, args, pa, grid, stream);
-    case 1281: return patch_kps1() ? launch_patch_t<128, 1, 1>(tmA, tmB, args, pa, grid, stream)
-                                   : launch_patch_t<128, 1, 3>(tmA, tmB, args, pa, grid, stream);
-    case 642: return patch_kps1() ? launch_patch_t<64, 2, 1>(tmA, tmB, args, pa, grid, stream)
-                                  : launch_patch_t<64, 2, 3>(tmA, tmB, args, pa, grid, stream);
-    case 641: return patch_kps1() ? launch_patch_t<64, 1, 1>(tmA, tmB, args, pa, grid, stream)
-                                  : launch_patch_t<64, 1, 3>(tmA, tmB, args, pa, grid, stream);
-    case 162: return launch_patch_t<16, 2, 7>(tmA, tmB, args, pa, grid, stream);
-    case 161: return launch_patch_t<16, 1, 7>(tmA, tmB, args, pa, grid, stream);
+    case 2562: return launch_patch_t<256, 2, 1, 64>(tmA, tmB, args, pa, grid, stream);
+    case 2561: return launch_patch_t<256, 1, 1, 64>(tmA, tmB, args, pa, grid, stream);
+    case 1282: return patch_kps1() ? launch_patch_t<128, 2, 1, 64>(tmA, tmB, args, pa, grid, stream)
+                                   : launch_patch_t<128, 2, 3, 64>(tmA, tmB, args, pa, grid, stream);
+    case 1281: return patch_kps1() ? launch_patch_t<128, 1, 1, 64>(tmA, tmB, args, pa, grid, stream)
+                                   : launch_patch_t<128, 1, 3, 64>(tmA, tmB, args, pa, grid, stream);
+    case 642: return patch_kps1() ? launch_patch_t<64, 2, 1, 64>(tmA, tmB, args, pa, grid, stream)
+                                  : launch_patch_t<64, 2, 3, 64>(tmA, tmB, args, pa, grid, stream);
+    case 641: return patch_kps1() ? launch_patch_t<64, 1, 1, 64>(tmA, tmB, args, pa, grid, stream)
+                                  : launch_patch_t<64, 1, 3, 64>(tmA, tmB, args, pa, grid, stream);
+    case 162: return launch_patch_t<16, 2, 7, 64>(tmA, tmB, args, pa, grid, stream);
+    case 161: return launch_patch_t<16, 1, 7, 64>(tmA, tmB, args, pa, grid, stream);
     default: break;
   }
   CGB_CHECK(false, "launch_igemm_patch: unsupported config BN=" + std::to_string(BN) + " MT=" + std::to_string(MT));

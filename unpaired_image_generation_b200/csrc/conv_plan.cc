@@ -144,14 +144,19 @@ static int patch_mode() {
 static bool try_patch(IgemmPlan& p, const TensorDesc& act, bool padded_view, const bf16* w, int rows, int Kw, int k,
                       int chans, int Ho, int Wo, int ox, int oy, bool flip, int sm_count) {
   const int mode = patch_mode();
-  if (mode <= 0 || k < 2 || k > 8 || chans % 64 != 0) return false;
+  // patch rows carry 64 channels (128 bytes) or, for the 16-stored-channel image-like tensors, 16 channels (32 bytes)
+  const int ka = chans % 64 == 0 ? 64 : 16;
+  static const bool no16 = std::getenv("CGB_PATCH_NO16") != nullptr;
+  if (mode <= 0 || k < 2 || k > 8 || (ka == 16 && (chans != 16 || mode != 1 || no16 || padded_rows(rows) < 64))) return false;
+  const int rb = ka * 2;  // bytes per patch row
   PatchArgs pa;
   std::memset(&pa, 0, sizeof(pa));
   pa.k = k;
+  pa.ka = ka;
   pa.flip = flip ? 1 : 0;
   pa.ox = ox;
   pa.oy = oy;
-  pa.chunks = chans / 64;
+  pa.chunks = chans / ka;
   pa.tap_stride = chans;
   pa.PH = 16 + k - 1;
   int box_w;
@@ -163,14 +168,14 @@ static bool try_patch(IgemmPlan& p, const TensorDesc& act, bool padded_view, con
     pa.row_step = 64;
     pa.col_step = pa.PH * 64;
     pa.sbo = 1024;
-  } else {                 // one box; taps start at arbitrary 128-byte rows of it
+  } else {                 // one box; taps start at arbitrary rows of it
     box_w = (mode == 5) ? 16 : 8 + k - 1;  // mode 5: 2048-byte pitch, so SBO is a multiple of the 1024-byte swizzle atom
     pa.nbox = 1;
-    pa.box_bytes = pa.PH * box_w * 128;
+    pa.box_bytes = pa.PH * box_w * rb;
     pa.patch_bytes = (pa.box_bytes + 1023) / 1024 * 1024;
-    pa.row_step = box_w * 8;
-    pa.col_step = 8;
-    pa.sbo = box_w * 128;
+    pa.row_step = box_w * rb / 16;
+    pa.col_step = rb / 16;
+    pa.sbo = box_w * rb;
     pa.base_offset = 0;  // measured on B200: the swizzle XOR uses absolute smem address bits; the base-offset field must stay 0
   }
   const int tiles_w = (Wo + 7) / 8, tile_rows = (Ho + 15) / 16;
@@ -182,13 +187,20 @@ static bool try_patch(IgemmPlan& p, const TensorDesc& act, bool padded_view, con
   if (const char* f = std::getenv("CGB_FORCE_MT")) forced_mt = std::atoi(f);
   const int bn_cands[3] = {256, 128, 64};
   int best_bn = 0, best_mt = 0, best_stages = 0;
+  const int T = k * k;
+  bool resident = false;
   auto fits = [&](int bn, int mt, int* stages) {
-    const int kps = igemm_patch_kps(bn);
+    const int kps = igemm_patch_kps(bn, ka);
     const int stage = kps * ((bn * 128 + 1023) / 1024 * 1024);
     const int budget = igemm_patch_smem_budget() - 2 * mt * pa.patch_bytes;
     int st = budget / stage;
-    if (st > 8) st = 8;
+    if (st > 16) st = 16;
     if (st < 2) return false;
+    // the whole filter fits the ring: load it once per CTA and keep it (persistent CTAs sweep many work items)
+    const int boxes = ka == 64 ? T : (T * ka + 63) / 64;
+    const int per_item = (boxes + kps - 1) / kps * pa.chunks;
+    resident = per_item >= 2 && per_item <= st;
+    if (resident) st = per_item;
     *stages = st;
     return true;
   };
@@ -199,7 +211,9 @@ static bool try_patch(IgemmPlan& p, const TensorDesc& act, bool padded_view, con
       if (!fits(16, mt, &st)) continue;
       const long long ctas = (long long)act.N * tiles_w * ((tile_rows + mt - 1) / mt);
       best_bn = 16, best_mt = mt, best_stages = st;
-      if (ctas >= 4 * target) break;  // short per-tile work: only stack tiles when there are plenty of them
+      // short per-tile work: only stack tiles when there are plenty of them (measured: stacking beats a resident
+      // filter on the 64 -> 3 head, 143 vs 161 us at batch 8: N = 16 MMAs are bound by the A-operand reads)
+      if (ctas >= 4 * target) break;
     }
   } else {
     bool done = false;
@@ -222,6 +236,11 @@ static bool try_patch(IgemmPlan& p, const TensorDesc& act, bool padded_view, con
   }
   if (best_bn == 0) return false;
   pa.b_stages = best_stages;
+  {
+    int st;
+    fits(best_bn, best_mt, &st);  // re-evaluate `resident` for the chosen shape
+    pa.b_resident = resident ? 1 : 0;
+  }
   p.patch = true;
   p.pargs = pa;
   p.BN = best_bn;
@@ -240,7 +259,7 @@ static bool try_patch(IgemmPlan& p, const TensorDesc& act, bool padded_view, con
   p.pargs.num_items = pa.num_items;
   p.num_ctas_m = std::min(pa.num_items, std::max(1, sm_count / p.n_blocks));
   p.num_tiles = pa.num_items;
-  p.tmA = view_s1(act, padded_view, 64, box_w, pa.PH);
+  p.tmA = view_s1(act, padded_view, ka, box_w, pa.PH);
   p.tmB = make_tmap_2d(w, prow, Kw, Kw, 64, p.BN, 128);
   return true;
 }
@@ -339,7 +358,7 @@ IgemmPlan plan_fprop(const ConvSpec& s, const TensorDesc& x, const bf16* wf, con
       }
   }
   bool patched = false;
-  if (!s.transposed && s.stride == 1 && BK == 64)
+  if (!s.transposed && s.stride == 1)
     patched = try_patch(p, x, s.reflect, wf, s.CoutS, Kw, k, s.CinS, Ho, Wo, s.reflect ? 0 : -s.pad,
                         s.reflect ? 0 : -s.pad, false, sm_count);
   if (!patched) finalize(p, vk, x, wf, s.CoutS, Kw, sm_count);
@@ -445,7 +464,7 @@ IgemmPlan plan_dgrad(const ConvSpec& s, const TensorDesc& dy, const bf16* wt, co
     p.args.k_count[0] = (int)p.kiters.size();
   }
   bool patched = false;
-  if (!s.transposed && s.stride == 1 && BK == 64) {
+  if (!s.transposed && s.stride == 1) {
     // dx[h] = sum_r dy[h + off - r] w[r]: the patch starts at off - (k - 1) and the filter is walked backwards
     const int off = s.reflect ? 0 : s.pad;
     patched = try_patch(p, dy, false, wt, s.CinS, Kw, k, s.CoutS, dx.H, dx.W, off - (k - 1), off - (k - 1), true,

@@ -24,7 +24,7 @@ void launch_igemm(int BN, int BK, int CM, int CN, const CUtensorMap& tmA, const 
 // MT = M tiles (16 x 8 output pixels each, stacked along h) per CTA; KPS = filter taps per weight stage.
 void launch_igemm_patch(int BN, int MT, const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmArgs& args,
                         const PatchArgs& pa, int num_ctas_m, int n_blocks, cudaStream_t stream);
-int igemm_patch_kps(int BN);   // filter taps carried by one weight stage for this N tile
+int igemm_patch_kps(int BN, int ka);  // weight boxes carried by one stage for this N tile / patch-row width
 int igemm_patch_smem_budget(); // bytes available for the weight ring + patches
 
 void launch_wgrad(int BNW, const CUtensorMap& tmDY, const CUtensorMap& tmX, const WgradArgs& args, int m_blocks,

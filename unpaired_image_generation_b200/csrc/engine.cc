@@ -485,8 +485,10 @@ void cgb_engine::record_programs() {
     const std::vector<LayerParam>& L = E->layers[net];
     float2* st = P.stats;
     pr.add([st, bytes = P.stats_bytes](cudaStream_t s) { CGB_CUDA(cudaMemsetAsync(st, 0, bytes, s)); }, 0, kOpMemset);
-    if (xcol_in) {
-      // stem as a plain GEMM over the im2col4 matrix: K = 256 (49 taps x 4 channels, zero padded)
+    static const bool stem_gemm = std::getenv("CGB_STEM_GEMM") != nullptr;
+    if (xcol_in && stem_gemm) {
+      // stem as a plain GEMM over the im2col4 matrix: K = 256 (49 taps x 4 channels, zero padded); superseded by the
+      // 16-channel patch-resident conv (the im2col4 matrix still feeds the stem weight gradient)
       LayerParam Lx = L[0];
       Lx.name = "stem(gemm)";
       Lx.spec.Cin = L[0].spec.Cin * L[0].spec.taps(); Lx.spec.CinS = 256; Lx.spec.k = 1; Lx.spec.stride = 1; Lx.spec.pad = 0; Lx.spec.reflect = false;
