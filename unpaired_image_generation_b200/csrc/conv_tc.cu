@@ -349,29 +349,43 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
     mbar_wait_relaxed(tmem_full_bar, 0);
     tc_fence_after();
     pdl_launch_dependents();
+    // Coalesced reductions: a thread owns one gradient ROW (cout), so a direct red.v4 per thread touches 32
+    // different rows per warp instruction (32 L2 transactions of 16 bytes).  The 32 x 32 fp32 block of each
+    // chunk is transposed through shared memory (the pipeline buffers are idle now) so that every warp
+    // instruction covers 4 rows x 128 contiguous bytes.
+    float* tstage = reinterpret_cast<float*>(smem) + q * (32 * 33);
+    const unsigned long long grow_u = reinterpret_cast<unsigned long long>(grow);
 #pragma unroll 1
     for (int c = 0; c < BNW; c += 32) {
       uint32_t r[32];
       tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, r);
       tmem_ld_wait();
-      if (valid) {
-        const int ci0 = nblk * BNW + c;
-        if (vec_ok && ci0 + 32 <= args.Cin) {
+      const int ci0 = nblk * BNW + c;
+      if (vec_ok && ci0 + 32 <= args.Cin) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(grow + ci0 + j),
-                         "f"(__uint_as_float(r[j])), "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])),
-                         "f"(__uint_as_float(r[j + 3]))
+        for (int j = 0; j < 32; ++j) tstage[lane * 33 + j] = __uint_as_float(r[j]);
+        __syncwarp();
+        const int sub = lane >> 3, piece = lane & 7;  // 4 rows per instruction, 8 x 16 bytes per row
+#pragma unroll
+        for (int r0 = 0; r0 < 32; r0 += 4) {
+          const int rr = r0 + sub;
+          const unsigned long long gp = __shfl_sync(0xffffffffu, grow_u, rr);
+          const int ok = __shfl_sync(0xffffffffu, valid ? 1 : 0, rr);
+          const float* sp = tstage + rr * 33 + piece * 4;
+          if (ok) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gp + (unsigned long long)(ci0 + piece * 4) * 4),
+                         "f"(sp[0]), "f"(sp[1]), "f"(sp[2]), "f"(sp[3])
                          : "memory");
           }
-        } else {
+        }
+        __syncwarp();
+      } else if (valid) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            int cc = ci0 + j;
-            if (cc < ncols) {
-              if (args.col_map != nullptr) cc = __ldg(args.col_map + cc);
-              if (cc >= 0 && cc < args.Cin) atomicAdd(grow + cc, __uint_as_float(r[j]));
-            }
+        for (int j = 0; j < 32; ++j) {
+          int cc = ci0 + j;
+          if (cc < ncols) {
+            if (args.col_map != nullptr) cc = __ldg(args.col_map + cc);
+            if (cc >= 0 && cc < args.Cin) atomicAdd(grow + cc, __uint_as_float(r[j]));
           }
         }
       }
