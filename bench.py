@@ -153,8 +153,20 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # rank 0 prints ONE JSON line on stdout: NCCL writes its version banner to stdout when NCCL_DEBUG is set
+        # (by us or by the environment), so stdout points at stderr while the communicator is created
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            warm = torch.zeros(1, device="cuda")
+            dist.all_reduce(warm)  # forces communicator creation (and the banner) now
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     peaks = load_peaks()
     batch, size = args.batch, args.size
 

@@ -108,7 +108,10 @@ int cgb_stage_inputs(cgb_engine_t* e, const float* real_A, const float* real_B, 
  * CGB_SEG_D = D-phase forward/backward; CGB_SEG_ADAM_G / CGB_SEG_ADAM_D = optimiser + bf16 weight refresh.
  * First call of a segment runs eagerly, the second captures it (independent passes on parallel branches). */
 enum { CGB_SEG_STEP = 0, CGB_SEG_G = 1, CGB_SEG_D = 2, CGB_SEG_ADAM_G = 3, CGB_SEG_ADAM_D = 4,
-       CGB_SEG_FORWARD = 5 /* staged inputs -> images + the six generator forwards */, CGB_NUM_SEGMENTS = 6 };
+       CGB_SEG_FORWARD = 5 /* staged inputs -> images + the six generator forwards */,
+       CGB_SEG_STEP_NOOPT = 6 /* staged inputs -> forward + G-phase + D-phase backward in the merged schedule, no
+                                 optimiser: grads_G and grads_D are complete afterwards (data parallel) */,
+       CGB_NUM_SEGMENTS = 7 };
 int cgb_run_segment(cgb_engine_t* e, int segment, void* stream);
 /* copies the CGB_NUM_LOSSES loss values to host memory (synchronises the stream) */
 int cgb_get_losses_host(cgb_engine_t* e, float* losses_host, void* stream);

@@ -100,7 +100,7 @@ int cgb_engine_bind(cgb_engine_t* e, float* pG, float* gG, float* mG, float* vG,
   A.base = static_cast<uint8_t*>(workspace);
   e->layout(A);
   CGB_CUDA(cudaMemset(workspace, 0, e->workspace_bytes));
-  e->meta_cap = 16u << 20;
+  e->meta_cap = 32u << 20;
   CGB_CUDA(cudaMalloc(&e->meta, e->meta_cap));
   e->record_programs();
   e->bound = true;

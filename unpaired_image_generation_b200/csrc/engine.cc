@@ -905,10 +905,11 @@ void cgb_engine::record_programs() {
     pr.cur_lane = 0;
     pr.mark("D phase end");
   }
-  {  // ---- the whole step as one schedule.  Lanes 0/1 carry the critical chains
+  // ---- the whole step as one schedule, recorded twice: with Adam(D) in the shadow of the generator backward
+  //      chains (single GPU) and without any optimiser (data parallel: the gradients are all-reduced first).
+  auto record_step = [&](Program& pr, bool with_adam_d) {  // Lanes 0/1 carry the critical chains
      //      fwd fake -> fwd rec -> bwd rec -> bwd fake; lanes 2/3 do the identity passes, the frozen-D input
      //      gradients and then the entire D phase in the shadow of those chains.
-    Program& pr = prog_step;
     double sink = 0;  // FLOPs are already accounted by prog_cycle / prog_G / prog_D
     float* gG = G[CGB_GROUP_G];
     float* gD = G[CGB_GROUP_D];
@@ -983,7 +984,7 @@ void cgb_engine::record_programs() {
     // backward chains (nothing later in the step reads the discriminator weights)
     pr.dep(3, 2);
     pr.cur_lane = 2;
-    {
+    if (with_adam_d) {
       const long long before = pr.launches;
       for (size_t i = 0; i < prog_adam[CGB_GROUP_D].ops.size(); ++i)
         pr.add(prog_adam[CGB_GROUP_D].ops[i], 0, prog_adam[CGB_GROUP_D].kinds[i]);
@@ -1016,7 +1017,9 @@ void cgb_engine::record_programs() {
     pr.join();
     pr.cur_lane = 0;
     pr.mark("step end (before Adam)");
-  }
+  };
+  record_step(prog_step, true);
+  record_step(prog_step_dp, false);
   }  // !infer_only
   {  // both optimisers side by side
     Program& pr = prog_adams;
@@ -1035,6 +1038,7 @@ void cgb_engine::record_programs() {
   segments[CGB_SEG_ADAM_G].seq = {&prog_adam[0]};
   segments[CGB_SEG_ADAM_D].seq = {&prog_adam[1]};
   segments[CGB_SEG_FORWARD].seq = {&prog_set_inputs, &prog_cycle};
+  segments[CGB_SEG_STEP_NOOPT].seq = {&prog_set_inputs, &prog_step_dp};
   // ---- module-level forward programs (Generator.forward / Discriminator.forward)
   for (int net = 0; net < 2; ++net) {
     emit_gen_forward(prog_mod_gen[net], &dummy_flops, gen[6], net, mod_in, mod_out, false, nullptr, nullptr);

@@ -264,6 +264,7 @@ struct cgb_engine {
   std::deque<cgb::SmallWgradPlan> small_wgrad_plans;
   cgb::Program prog_set_inputs, prog_cycle, prog_G, prog_D, prog_adam[2], prog_refresh[2];
   cgb::Program prog_step;   // forward + G phase + D phase as ONE schedule (no joins between the phases)
+  cgb::Program prog_step_dp;  // the same without Adam(D): data-parallel callers all-reduce the gradients first
   cgb::Program prog_adams;  // both optimisers side by side
   cgb::Program prog_mod_gen[2], prog_mod_dis[2];
   double conv_flops = 0;  // accumulated while recording prog_cycle/prog_G/prog_D
