@@ -4,6 +4,8 @@
 
 #include "ptx.cuh"
 
+#include <cstdlib>
+
 #ifndef CGB_PW_TRIGGER
 #define CGB_PW_TRIGGER 0
 #endif
@@ -542,6 +544,279 @@ in_bwd_apply_kernel(DevTensor y, const float2* __restrict__ stats, const float2*
   }
 }
 
+// ------------------------------------------------------------------------------------------ cp.async variants
+// Large maps: the register versions above keep 4-6 16-byte loads per thread in flight at 2 blocks / SM (117-120
+// registers), ~40 KB per SM, which tops out near 2.5 TB/s.  Here every thread prefetches its vectors for the next
+// kAsyncStages-1 loop iterations into private shared-memory slots with cp.async (no registers held while in
+// flight), so ~100 KB per SM are in flight.  Used when a thread has >= 3 iterations (pick_async()).
+constexpr int kAsyncStages = 3;
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ptx::smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// slot of (stage, vector kind v < NV, pixel k < PPT) of this thread: consecutive threads -> consecutive 16 bytes
+template <int PPT, int NV>
+__device__ __forceinline__ uint4* async_slot(uint4* ring, int stage, int v, int k) {
+  return ring + ((stage * NV + v) * PPT + k) * 256 + threadIdx.x;
+}
+
+template <int PPT>
+__device__ __forceinline__ void bwd_async_issue(const DevTensor& y, const DevGrad& g, int n, int pb, int p1, int c0,
+                                                uint4* ring, int stage) {
+  if (pb < p1) {
+    PixIter it(pb, y.W);
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      if (pb + k < p1) {
+        cp_async16(async_slot<PPT, 3>(ring, stage, 0, k), y.p + n * y.sN + it.hp * y.sH + it.wp * y.sW + c0);
+        if (g.g1.p != nullptr)
+          cp_async16(async_slot<PPT, 3>(ring, stage, 1, k), g.g1.p + n * g.g1.sN + it.hp * g.g1.sH + it.wp * g.g1.sW + c0);
+        if (g.g2.p != nullptr)
+          cp_async16(async_slot<PPT, 3>(ring, stage, 2, k),
+                     g.g2.p + n * g.g2.sN + (it.hp + g.fold) * g.g2.sH + (it.wp + g.fold) * g.g2.sW + c0);
+      }
+      it.next(y.W);
+    }
+  }
+  cp_async_commit();  // one group per iteration, empty past the end, so wait_group counts stay uniform
+}
+
+template <int PPT>
+__device__ __forceinline__ void bwd_async_collect(const DevTensor& y, const DevGrad& g, int pb, int p1, uint4* ring,
+                                                  int stage, BwdLoads<PPT>& L) {
+  PixIter it(pb, y.W);
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    L.ok[k] = pb + k < p1;
+    L.h[k] = it.hp;
+    L.w[k] = it.wp;
+    if (L.ok[k]) {
+      L.yraw[k] = *async_slot<PPT, 3>(ring, stage, 0, k);
+      if (g.g1.p != nullptr) L.g1raw[k] = *async_slot<PPT, 3>(ring, stage, 1, k);
+      if (g.g2.p != nullptr) L.g2raw[k] = *async_slot<PPT, 3>(ring, stage, 2, k);
+    }
+    it.next(y.W);
+  }
+}
+
+template <int PPT>
+__global__ void __launch_bounds__(256)
+in_bwd_apply_async_kernel(DevTensor y, const float2* __restrict__ stats, const float2* __restrict__ bstats, DevGrad g,
+                          int act, DevTensor dy, int ppb) {
+  ptx::pdl_wait();
+  extern __shared__ uint4 ring[];
+  const int C8 = y.C / 8;
+  const int lanes = C8 < 256 ? C8 : 256;
+  const int rows = 256 / lanes;
+  const int cl = threadIdx.x % lanes, pr = threadIdx.x / lanes;
+  const int n = blockIdx.y;
+  const int total = y.H * y.W;
+  const float inv = 1.f / (float)total;
+  const int p0 = blockIdx.x * ppb, p1 = min(total, p0 + ppb);
+  const int step = rows * PPT;
+  if (pr >= rows) return;
+  for (int cb = cl; cb < C8; cb += lanes) {
+    const int c0 = cb * 8;
+    const int pfirst = p0 + pr * PPT;
+#pragma unroll
+    for (int s = 0; s < kAsyncStages - 1; ++s) bwd_async_issue<PPT>(y, g, n, pfirst + s * step, p1, c0, ring, s);
+    float a[8], b[8], c[8], d[8];
+    load_norm8(stats, (long long)n * y.C + c0, inv, a, b);
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+      const float4 bs = __ldg(reinterpret_cast<const float4*>(bstats + (long long)n * y.C + c0 + i));
+      c[i] = a[i] * bs.x * inv;
+      d[i] = a[i] * bs.y * inv;
+      c[i + 1] = a[i + 1] * bs.z * inv;
+      d[i + 1] = a[i + 1] * bs.w * inv;
+    }
+    int stage = 0;
+#pragma unroll 1
+    for (int pb = pfirst; pb < p1; pb += step) {
+      int pre = stage + kAsyncStages - 1;
+      if (pre >= kAsyncStages) pre -= kAsyncStages;
+      bwd_async_issue<PPT>(y, g, n, pb + (kAsyncStages - 1) * step, p1, c0, ring, pre);
+      cp_async_wait<kAsyncStages - 1>();
+      BwdLoads<PPT> L;
+      bwd_async_collect<PPT>(y, g, pb, p1, ring, stage, L);
+#pragma unroll
+      for (int k = 0; k < PPT; ++k) {
+        if (!L.ok[k]) continue;
+        float v[8], gr[8];
+        unpack8(L.yraw[k], v);
+        bwd_grad<PPT>(y, g, n, c0, L, k, gr);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xh = fmaf(v[i], a[i], b[i]);
+          const float dz = gr[i] * act_grad(xh, act);
+          v[i] = fmaf(a[i], dz, -c[i]) - d[i] * xh;
+        }
+        store8(dy.p + n * dy.sN + L.h[k] * dy.sH + L.w[k] * dy.sW + c0, v);
+      }
+      if (++stage == kAsyncStages) stage = 0;
+    }
+    cp_async_wait<0>();
+  }
+}
+
+template <int PPT>
+__global__ void __launch_bounds__(256)
+in_bwd_reduce_async_kernel(DevTensor y, const float2* __restrict__ stats, DevGrad g, int act, DevTensor da,
+                           float* __restrict__ bstats, int ppb) {
+  ptx::pdl_wait();
+  extern __shared__ uint4 ring[];
+  __shared__ float red[256 * 16];
+  const int C8 = y.C / 8;
+  const int lanes = C8 < 256 ? C8 : 256;
+  const int rows = 256 / lanes;
+  const int cl = threadIdx.x % lanes, pr = threadIdx.x / lanes;
+  const int n = blockIdx.y;
+  const int HW = y.H * y.W;
+  const float inv = 1.f / (float)HW;
+  const int p0 = blockIdx.x * ppb, p1 = min(HW, p0 + ppb);
+  const int step = rows * PPT;
+  for (int cb = cl; cb < C8; cb += lanes) {
+    const int c0 = cb * 8;
+    float s1[8], s2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
+    if (pr < rows) {
+      const int pfirst = p0 + pr * PPT;
+#pragma unroll
+      for (int s = 0; s < kAsyncStages - 1; ++s) bwd_async_issue<PPT>(y, g, n, pfirst + s * step, p1, c0, ring, s);
+      float a[8], b[8];
+      load_norm8(stats, (long long)n * y.C + c0, inv, a, b);
+      int stage = 0;
+#pragma unroll 1
+      for (int pb = pfirst; pb < p1; pb += step) {
+        int pre = stage + kAsyncStages - 1;
+        if (pre >= kAsyncStages) pre -= kAsyncStages;
+        bwd_async_issue<PPT>(y, g, n, pb + (kAsyncStages - 1) * step, p1, c0, ring, pre);
+        cp_async_wait<kAsyncStages - 1>();
+        BwdLoads<PPT> L;
+        bwd_async_collect<PPT>(y, g, pb, p1, ring, stage, L);
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+          if (!L.ok[k]) continue;
+          float v[8], gr[8];
+          unpack8(L.yraw[k], v);
+          bwd_grad<PPT>(y, g, n, c0, L, k, gr);
+          if (da.p != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) gr[i] = round_bf16(gr[i]);
+            store8(da.p + n * da.sN + L.h[k] * da.sH + L.w[k] * da.sW + c0, gr);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float xh = fmaf(v[i], a[i], b[i]);
+            const float dz = gr[i] * act_grad(xh, act);
+            s1[i] += dz;
+            s2[i] = fmaf(dz, xh, s2[i]);
+          }
+        }
+        if (++stage == kAsyncStages) stage = 0;
+      }
+      cp_async_wait<0>();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      red[threadIdx.x * 16 + i] = s1[i];
+      red[threadIdx.x * 16 + 8 + i] = s2[i];
+    }
+    __syncthreads();
+    if (pr == 0) {
+      for (int r = 1; r < rows; ++r) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s1[i] += red[(r * lanes + cl) * 16 + i];
+          s2[i] += red[(r * lanes + cl) * 16 + 8 + i];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; i += 2) {
+        const int c = cb * 8 + i;
+        red_add_v4(bstats + ((long long)n * y.C + c) * 2, s1[i], s2[i], s1[i + 1], s2[i + 1]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int PPT>
+__global__ void __launch_bounds__(256)
+in_apply_async_kernel(DevTensor y, const float2* __restrict__ stats, int act, DevTensor res, DevTensor out, int ppb) {
+  ptx::pdl_wait();
+  extern __shared__ uint4 ring[];
+  const int C8 = out.C / 8;
+  const int lanes = C8 < 256 ? C8 : 256;
+  const int rows = 256 / lanes;
+  const int cl = threadIdx.x % lanes, pr = threadIdx.x / lanes;
+  const int n = blockIdx.y;
+  const int HP = out.H + 2 * out.halo, WP = out.W + 2 * out.halo;
+  const int total = HP * WP;
+  const float inv = 1.f / (float)(y.H * y.W);
+  const int p0 = blockIdx.x * ppb, p1 = min(total, p0 + ppb);
+  const int step = rows * PPT;
+  if (pr >= rows) return;
+  auto issue = [&](int pb, int c0, int stage) {
+    if (pb < p1) {
+      PixIter it(pb, WP);
+#pragma unroll
+      for (int k = 0; k < PPT; ++k) {
+        if (pb + k < p1) {
+          const int h = reflect_idx(it.hp - out.halo, out.H), w = reflect_idx(it.wp - out.halo, out.W);
+          cp_async16(async_slot<PPT, 2>(ring, stage, 0, k), y.p + n * y.sN + h * y.sH + w * y.sW + c0);
+          if (res.p != nullptr)
+            cp_async16(async_slot<PPT, 2>(ring, stage, 1, k), res.p + n * res.sN + h * res.sH + w * res.sW + c0);
+        }
+        it.next(WP);
+      }
+    }
+    cp_async_commit();
+  };
+  for (int cb = cl; cb < C8; cb += lanes) {
+    const int c0 = cb * 8;
+    const int pfirst = p0 + pr * PPT;
+#pragma unroll
+    for (int s = 0; s < kAsyncStages - 1; ++s) issue(pfirst + s * step, c0, s);
+    float a[8], b[8];
+    load_norm8(stats, (long long)n * y.C + c0, inv, a, b);
+    int stage = 0;
+#pragma unroll 1
+    for (int pb = pfirst; pb < p1; pb += step) {
+      int pre = stage + kAsyncStages - 1;
+      if (pre >= kAsyncStages) pre -= kAsyncStages;
+      issue(pb + (kAsyncStages - 1) * step, c0, pre);
+      cp_async_wait<kAsyncStages - 1>();
+      PixIter it(pb, WP);
+#pragma unroll
+      for (int k = 0; k < PPT; ++k) {
+        if (pb + k < p1) {
+          float v[8];
+          unpack8(*async_slot<PPT, 2>(ring, stage, 0, k), v);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = act_fwd(fmaf(v[i], a[i], b[i]), act);
+          if (res.p != nullptr) {
+            float rv[8];
+            unpack8(*async_slot<PPT, 2>(ring, stage, 1, k), rv);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += rv[i];
+          }
+          store8(out.p + n * out.sN + (long long)(it.hp - out.halo) * out.sH + (long long)(it.wp - out.halo) * out.sW + c0, v);
+        }
+        it.next(WP);
+      }
+      if (++stage == kAsyncStages) stage = 0;
+    }
+    cp_async_wait<0>();
+  }
+}
+
 // ------------------------------------------------------------------------------------------ head / losses
 __device__ __forceinline__ float block_sum(float v) {
   __shared__ float sh[32];
@@ -830,6 +1105,22 @@ void bias_grad(const TensorDesc& dy, int C, float* gbias, cudaStream_t st) {
   launch_pdl(colsum_kernel<1>, grid, dim3(256), 0, st, dev(dy), gbias, ppb, C);
 }
 
+static bool async_enabled() {
+  static const bool on = !(std::getenv("CGB_PW_ASYNC") && std::atoi(std::getenv("CGB_PW_ASYNC")) == 0);
+  return on;
+}
+// cp.async variants: ~2 blocks per SM over the whole batch, used when that leaves every thread >= 3 iterations
+static bool pick_async(long long pixels, int rows, int images, int /*unused*/, int* ppb_out) {
+  if (!async_enabled()) return false;
+  const int unit = rows * 2;
+  const long long per_image = std::max(1LL, 2LL * 148 / images);
+  long long ppb = (pixels + per_image - 1) / per_image;
+  ppb = (ppb + unit - 1) / unit * unit;
+  if (ppb / unit < 3) return false;
+  *ppb_out = (int)ppb;
+  return true;
+}
+
 // Streaming kernels: blocks of `ppb` pixels sized for ~8 CTAs per SM over the whole batch (but at least one
 // PPT-batch per pixel row of the block, so small maps still spread over the machine).
 static int stream_ppb(long long pixels, int rows, int ppt, int images) {
@@ -845,6 +1136,19 @@ void in_apply(const TensorDesc& y, const float2* stats, int act, const TensorDes
   CGB_CHECK(y.C == out.C && y.H == out.H && y.W == out.W && y.N == out.N, "in_apply: shape mismatch");
   const int total = (out.H + 2 * out.halo) * (out.W + 2 * out.halo);
   const int lanes = std::min(256, out.C / 8), rows = 256 / lanes;
+  int appb;
+  if (pick_async(total, rows, out.N, 0, &appb)) {
+    static bool configured = false;
+    constexpr int kSmem = kAsyncStages * 2 * 2 * 256 * 16;
+    if (!configured) {
+      CGB_CUDA(cudaFuncSetAttribute(in_apply_async_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+      configured = true;
+    }
+    dim3 grid((total + appb - 1) / appb, out.N);
+    launch_pdl(in_apply_async_kernel<2>, grid, dim3(256), (size_t)kSmem, st, dev(y), stats, act,
+               residual ? dev(*residual) : dev_null(), dev(out), appb);
+    return;
+  }
   const int ppb = stream_ppb(total, rows, 2, out.N);
   dim3 grid((total + ppb - 1) / ppb, out.N);
   launch_pdl(in_apply_kernel<2>, grid, dim3(256), 0, st, dev(y), stats, act, residual ? dev(*residual) : dev_null(), dev(out), ppb);
@@ -870,6 +1174,17 @@ void in_bwd_reduce(const TensorDesc& y, const float2* stats, const GradSrc& g, i
   int ppb = (HW + blocks_per_image - 1) / blocks_per_image;
   ppb = std::max(unit, (ppb + unit - 1) / unit * unit);
   dim3 grid((HW + ppb - 1) / ppb, y.N);
+  if (async_enabled() && ppb / unit >= 3) {
+    static bool configured = false;
+    constexpr int kSmem = kAsyncStages * 3 * 2 * 256 * 16;
+    if (!configured) {
+      CGB_CUDA(cudaFuncSetAttribute(in_bwd_reduce_async_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+      configured = true;
+    }
+    launch_pdl(in_bwd_reduce_async_kernel<2>, grid, dim3(256), (size_t)kSmem, st, dev(y), stats, dev(g), act,
+               da_out ? dev(*da_out) : dev_null(), reinterpret_cast<float*>(bstats), ppb);
+    return;
+  }
   launch_pdl(in_bwd_reduce_kernel<2>, grid, dim3(256), 0, st, dev(y), stats, dev(g), act,
              da_out ? dev(*da_out) : dev_null(), reinterpret_cast<float*>(bstats), ppb);
 }
@@ -879,6 +1194,19 @@ void in_bwd_apply(const TensorDesc& y, const float2* stats, const float2* bstats
   check_grad(y, g);
   const int total = y.H * y.W;
   const int lanes = std::min(256, y.C / 8), rows = 256 / lanes;
+  int appb;
+  if (pick_async(total, rows, y.N, 0, &appb)) {
+    static bool configured = false;
+    constexpr int kSmem = kAsyncStages * 3 * 2 * 256 * 16;
+    if (!configured) {
+      CGB_CUDA(cudaFuncSetAttribute(in_bwd_apply_async_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+      configured = true;
+    }
+    dim3 grid((total + appb - 1) / appb, y.N);
+    launch_pdl(in_bwd_apply_async_kernel<2>, grid, dim3(256), (size_t)kSmem, st, dev(y), stats, bstats, dev(g), act,
+               dev(dy), appb);
+    return;
+  }
   const int ppb = stream_ppb(total, rows, 2, y.N);
   dim3 grid((total + ppb - 1) / ppb, y.N);
   launch_pdl(in_bwd_apply_kernel<2>, grid, dim3(256), 0, st, dev(y), stats, bstats, dev(g), act, dev(dy), ppb);
