@@ -275,7 +275,7 @@ def run_b200(args):
             achieved = res_flops / (us * 1e-6) / 1e12
         else:
             us, achieved = None, agg
-        # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r01_e_ncu_full_res_conv.txt)
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r01_f_ncu_full_res_conv.txt)
         ncu_traffic = {(1, 256): 3.456e6, (8, 256): 19.067e6}.get((batch, size))
         roofline = {
             "bound": "tensor",
