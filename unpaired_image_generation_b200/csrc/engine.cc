@@ -942,15 +942,7 @@ void cgb_engine::record_programs() {
     emit_gen_forward(pr, &sink, gen[2], CGB_NET_G_BA, real_B, img[CGB_IMG_FAKE_A], true, &xcol[1], &xcol[3]);
     ev_fake_A = pr.record(1);
     pr.mark("fwd fake_A done");
-    // identity passes: forward and backward back to back
-    pr.cur_lane = 2;
-    emit_gen_forward(pr, &sink, gen[4], CGB_NET_G_AB, real_B, img[CGB_IMG_IDT_A], false, &xcol[1], nullptr);
-    emit_gen_backward(pr, &sink, gen[4], gs[2], &real_B, cfg.lambda_B * cfg.lambda_idt / numel_img, CGB_LOSS_IDT_A, GradSrc(), nullptr);
-    pr.mark("idt_A fwd+bwd done");
-    pr.cur_lane = 3;
-    emit_gen_forward(pr, &sink, gen[5], CGB_NET_G_BA, real_A, img[CGB_IMG_IDT_B], false, &xcol[0], nullptr);
-    emit_gen_backward(pr, &sink, gen[5], gs[3], &real_A, cfg.lambda_A * cfg.lambda_idt / numel_img, CGB_LOSS_IDT_B, GradSrc(), nullptr);
-    pr.mark("idt_B fwd+bwd done");
+    // (identity passes: emitted below together with the rest of lanes 2 / 3)
     }
     // cycle passes
     pr.cur_lane = 0;
@@ -961,25 +953,58 @@ void cgb_engine::record_programs() {
     emit_gen_forward(pr, &sink, gen[3], CGB_NET_G_AB, fake_A, img[CGB_IMG_REC_B], false, &xcol[3], nullptr);
     emit_gen_backward(pr, &sink, gen[3], gs[1], &real_B, cfg.lambda_B / numel_img, CGB_LOSS_CYCLE_B, GradSrc(), &dxp_img[1]);
     pr.mark("rec_B fwd+bwd done");
-    // adversarial terms on the fakes (D frozen), then the whole D phase, on lanes 2/3
-    pr.cur_lane = 2;
-    pr.wait(2, ev_fake_B);
-    emit_dis_forward(pr, &sink, dis[0], CGB_NET_D_A, fake_B);
-    emit_dis_backward(pr, &sink, dis[0], ds[0], 1.f, 1.f, CGB_LOSS_G_A, false, &dx_D0[0]);
-    const int ev_dD_A = pr.record(2);
-    emit_dis_forward(pr, &sink, dis[2], CGB_NET_D_A, real_B);
-    emit_dis_backward(pr, &sink, dis[2], ds[0], 1.f, 0.5f, CGB_LOSS_D_A, true, nullptr);
-    emit_dis_backward(pr, &sink, dis[0], ds[0], 0.f, 0.5f, CGB_LOSS_D_A, true, nullptr);
-    pr.mark("D_A all done");
-    pr.cur_lane = 3;
-    pr.wait(3, ev_fake_A);
-    emit_dis_forward(pr, &sink, dis[1], CGB_NET_D_B, fake_A);
-    emit_dis_backward(pr, &sink, dis[1], ds[1], 1.f, 1.f, CGB_LOSS_G_B, false, &dx_D0[1]);
-    const int ev_dD_B = pr.record(3);
-    emit_dis_forward(pr, &sink, dis[3], CGB_NET_D_B, real_A);
-    emit_dis_backward(pr, &sink, dis[3], ds[1], 1.f, 0.5f, CGB_LOSS_D_B, true, nullptr);
-    emit_dis_backward(pr, &sink, dis[1], ds[1], 0.f, 0.5f, CGB_LOSS_D_B, true, nullptr);
-    pr.mark("D_B all done");
+    // Lanes 2 / 3: the identity pass of one generator, the adversarial term on the fake (D frozen: input gradient
+    // only, needed by the fake's backward on lane 0 / 1) and the whole D phase of one discriminator.
+    // CGB_SCHED orders them: 1 = identity fwd+bwd first (default); 2 = adversarial term first, identity pass after
+    // it; 3 = identity forward, adversarial term, identity backward.
+    static const int sched = std::getenv("CGB_SCHED") ? std::atoi(std::getenv("CGB_SCHED")) : 1;
+    auto side_lane = [&](int lane, int side, int ev_fake) {
+      GenPass& GP = gen[4 + side];
+      GenScratch& GS = gs[2 + side];
+      const int gnet = side == 0 ? CGB_NET_G_AB : CGB_NET_G_BA;
+      const TensorDesc& real_in = side == 0 ? real_B : real_A;   // idt_A = G_AB(real_B), idt_B = G_BA(real_A)
+      const TensorDesc& idt_out = img[side == 0 ? CGB_IMG_IDT_A : CGB_IMG_IDT_B];
+      const TensorDesc* xc = &xcol[side == 0 ? 1 : 0];
+      const float idt_scale = (side == 0 ? cfg.lambda_B : cfg.lambda_A) * cfg.lambda_idt / numel_img;
+      const int idt_slot = side == 0 ? CGB_LOSS_IDT_A : CGB_LOSS_IDT_B;
+      const int dnet = side == 0 ? CGB_NET_D_A : CGB_NET_D_B;
+      const TensorDesc& fake = side == 0 ? fake_B : fake_A;      // D_A judges domain-B images
+      auto idt_fwd = [&]() { if (!pair) emit_gen_forward(pr, &sink, GP, gnet, real_in, idt_out, false, xc, nullptr); };
+      auto idt_bwd = [&]() {
+        if (!pair) {
+          emit_gen_backward(pr, &sink, GP, GS, &real_in, idt_scale, idt_slot, GradSrc(), nullptr);
+          pr.mark(side == 0 ? "idt_A fwd+bwd done" : "idt_B fwd+bwd done");
+        }
+      };
+      int ev = -1;
+      auto adv = [&]() {
+        pr.wait(lane, ev_fake);
+        emit_dis_forward(pr, &sink, dis[side], dnet, fake);
+        emit_dis_backward(pr, &sink, dis[side], ds[side], 1.f, 1.f, side == 0 ? CGB_LOSS_G_A : CGB_LOSS_G_B, false, &dx_D0[side]);
+        ev = pr.record(lane);
+      };
+      pr.cur_lane = lane;
+      if (sched == 2) {
+        adv();
+        idt_fwd();
+        idt_bwd();
+      } else if (sched == 3) {
+        idt_fwd();
+        adv();
+        idt_bwd();
+      } else {
+        idt_fwd();
+        idt_bwd();
+        adv();
+      }
+      emit_dis_forward(pr, &sink, dis[2 + side], dnet, real_in);
+      emit_dis_backward(pr, &sink, dis[2 + side], ds[side], 1.f, 0.5f, side == 0 ? CGB_LOSS_D_A : CGB_LOSS_D_B, true, nullptr);
+      emit_dis_backward(pr, &sink, dis[side], ds[side], 0.f, 0.5f, side == 0 ? CGB_LOSS_D_A : CGB_LOSS_D_B, true, nullptr);
+      pr.mark(side == 0 ? "D_A all done" : "D_B all done");
+      return ev;
+    };
+    const int ev_dD_A = side_lane(2, 0, ev_fake_B);
+    const int ev_dD_B = side_lane(3, 1, ev_fake_A);
     // both discriminators' gradients are complete: Adam(D) + bf16 refresh run here, in the shadow of the generator
     // backward chains (nothing later in the step reads the discriminator weights)
     pr.dep(3, 2);
