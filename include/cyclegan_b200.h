@@ -103,6 +103,12 @@ int cgb_adam(cgb_engine_t* e, int group, void* stream);
 int cgb_train_step(cgb_engine_t* e, void* stream);
 /* copies fp32 NCHW inputs (device or pinned host) into the engine's staging buffers, nothing else */
 int cgb_stage_inputs(cgb_engine_t* e, const float* real_A, const float* real_B, void* stream);
+/* same for uint8 interleaved RGB images [batch][size][size][3] (device or pinned host): 4x fewer bytes over PCIe;
+ * converted on the device with x = u8 / 127.5 - 1 (the stand-in's `from_uint8`, oracle/cyclegan_standin.py) */
+int cgb_stage_inputs_u8(cgb_engine_t* e, const unsigned char* real_A, const unsigned char* real_B, void* stream);
+/* learning rate of a parameter group, stream-ordered and held in device memory: an LR schedule
+ * (stand-in: CycleGANTrainer.set_lr / linear_decay_lr) needs no re-capture of the step graph */
+int cgb_set_lr(cgb_engine_t* e, int group, float lr, void* stream);
 /* graph-replayed segments of the step, for callers that interleave their own collectives (data parallel):
  * CGB_SEG_STEP = whole step; CGB_SEG_G = staged inputs -> images, six forwards, G-phase backward;
  * CGB_SEG_D = D-phase forward/backward; CGB_SEG_ADAM_G / CGB_SEG_ADAM_D = optimiser + bf16 weight refresh.

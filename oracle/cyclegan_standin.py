@@ -213,6 +213,21 @@ def dead_bias_names_discriminator():
 
 
 # --------------------------------------------------------------------------------------
+# Input pipeline and learning-rate schedule of the canonical recipe (SURVEY.md section 8 f, items 2 and 3)
+# --------------------------------------------------------------------------------------
+def from_uint8(img_u8_hwc: torch.Tensor) -> torch.Tensor:
+    """uint8 interleaved RGB [N, H, W, 3] -> float32 [N, 3, H, W] in [-1, 1]: ToTensor + Normalize(0.5, 0.5)."""
+    assert img_u8_hwc.dtype == torch.uint8 and img_u8_hwc.dim() == 4 and img_u8_hwc.shape[-1] == 3
+    return (img_u8_hwc.permute(0, 3, 1, 2).to(torch.float32) * (1.0 / 127.5) - 1.0).contiguous()
+
+
+def linear_decay_lr(base_lr: float, epoch: int, n_epochs: int = 100, n_epochs_decay: int = 100) -> float:
+    """Constant for `n_epochs`, then linear decay to zero over `n_epochs_decay` (the canonical 'linear' policy):
+    lr = base_lr * (1 - max(0, epoch + 1 - n_epochs) / (n_epochs_decay + 1)), epoch counted from 0."""
+    return base_lr * (1.0 - max(0, epoch + 1 - n_epochs) / float(n_epochs_decay + 1))
+
+
+# --------------------------------------------------------------------------------------
 # Training step
 # --------------------------------------------------------------------------------------
 class CycleGANTrainer:
@@ -237,6 +252,12 @@ class CycleGANTrainer:
         self.opt_G = torch.optim.Adam(list(G_AB.parameters()) + list(G_BA.parameters()), lr=lr, betas=betas, eps=eps)
         self.opt_D = torch.optim.Adam(list(D_A.parameters()) + list(D_B.parameters()), lr=lr, betas=betas, eps=eps)
         self.last_images: Dict[str, torch.Tensor] = {}
+
+    def set_lr(self, lr: float) -> None:
+        """learning rate of both optimisers from the next step on (drive it with linear_decay_lr)"""
+        for opt in (self.opt_G, self.opt_D):
+            for group in opt.param_groups:
+                group["lr"] = float(lr)
 
     # -- the six generated images, for activation parity -------------------------------
     @torch.no_grad()

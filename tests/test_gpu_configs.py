@@ -147,3 +147,50 @@ def test_paired_schedule_matches_unpaired(monkeypatch):
         # reconstructions pass through two generators: the atomics-order noise of the statistics is amplified
         # twice (rec_A sits 7e-2..1.2e-1 from fp32 for ANY bf16 implementation)
         assert err < (0.15 if k.startswith("rec") else 3e-2), (k, err)
+
+
+def test_uint8_inputs_match_float_inputs():
+    """cgb_stage_inputs_u8: uint8 HWC images are normalised on the device exactly like the stand-in's from_uint8"""
+    _need_gpu()
+    g = torch.Generator().manual_seed(11)
+    a8 = torch.randint(0, 256, (1, 64, 64, 3), generator=g, dtype=torch.uint8)
+    b8 = torch.randint(0, 256, (1, 64, 64, 3), generator=g, dtype=torch.uint8)
+    tr_f, _ = _trainer()
+    lf = tr_f.train_step(ref.from_uint8(a8).cuda(), ref.from_uint8(b8).cuda())
+    tr_u, _ = _trainer()
+    lu = tr_u.train_step(a8.cuda(), b8.cuda())
+    lh = _trainer()[0].train_step(a8.pin_memory(), b8.pin_memory())  # pinned host uint8
+    for k in lf:
+        # identical inputs after conversion (checked bit-exactly below): only the order of the fp32 atomics differs
+        # between runs, which the 6x6-logit LSGAN terms at 64x64 amplify most (same gates as test_gpu_parity.py)
+        tol = 5e-2 if k in ("loss_G_A", "loss_G_B", "loss_D_A", "loss_D_B") else 1e-2
+        assert abs(lu[k] - lf[k]) / abs(lf[k]) < tol, (k, lu[k], lf[k])
+        assert abs(lh[k] - lf[k]) / abs(lf[k]) < tol, (k, lh[k], lf[k])
+    real = tr_u.engine.get_image("real_A").cpu()
+    assert float((real - ref.from_uint8(a8).to(torch.bfloat16).float()).abs().max()) == 0.0  # bit-exact bf16 image
+
+
+def test_set_lr_matches_standin_schedule():
+    """device-resident learning rate: lr = 0 leaves the weights untouched, a later lr applies without re-capture"""
+    _need_gpu()
+    tr, mods = _trainer()
+    otr = ref.CycleGANTrainer(*ref.build_models(seed=0))
+    real_A, real_B = ref.synthetic_pair(1, 64, seed=1234)
+    w0 = mods[0].state_dict()["head.weight"].clone()
+    for lr in (0.0, 0.0, ref.linear_decay_lr(2e-4, 150)):  # steps 1-2 are graph warm-up / capture with lr 0
+        tr.set_lr(lr)
+        otr.set_lr(lr)
+        tr.train_step(real_A.cuda(), real_B.cuda())
+        otr.train_step(real_A, real_B)
+        if lr == 0.0:
+            assert torch.equal(mods[0].state_dict()["head.weight"], w0)
+    got = mods[0].state_dict()["head.weight"].cpu()
+    want = otr.G_AB.head.weight.detach()
+    # Adam's third step with zero-lr history: the update is lr * m_hat / (sqrt(v_hat) + eps), same sign pattern
+    d_got, d_want = got - w0.cpu(), want - ref.build_models(seed=0)[0].head.weight.detach()
+    # |update| = lr * |m_hat| / (sqrt(v_hat) + eps): ~lr for a steady gradient, a little above it where the three
+    # steps' gradients differ (order-dependent fp32 atomics); far below the constructor's 2e-4
+    lr3 = ref.linear_decay_lr(2e-4, 150)
+    assert 0.5 * lr3 < float(d_got.abs().median()) < 1.5 * lr3 and float(d_got.abs().max()) < 1.9e-4
+    cos = float((d_got * d_want).sum() / (d_got.norm() * d_want.norm()))
+    assert cos > 0.9, cos

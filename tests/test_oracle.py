@@ -134,3 +134,31 @@ def test_dp_equivalence_batch2_equals_two_ranks():
         acc += G2[0].res[2].conv1.weight.grad
     rel = float((acc / 2 - full).norm() / full.norm())
     assert rel < 5e-3, rel  # fp32 summation-order noise through sign() of the L1 losses
+
+
+def test_from_uint8_and_linear_decay_schedule():
+    """input pipeline and LR policy of the canonical recipe (SURVEY.md section 8 f), as restated by the stand-in"""
+    from oracle.cyclegan_standin import from_uint8, linear_decay_lr
+    u8 = torch.tensor([[[[0, 127, 255], [128, 64, 1]]]], dtype=torch.uint8)  # [1, 1, 2, 3]
+    x = from_uint8(u8)
+    assert x.shape == (1, 3, 1, 2) and x.dtype == torch.float32
+    assert float(x[0, 0, 0, 0]) == -1.0 and float(x[0, 2, 0, 0]) == 1.0
+    assert abs(float(x[0, 1, 0, 0]) - (127 / 127.5 - 1)) < 1e-7
+    assert linear_decay_lr(2e-4, 0) == 2e-4 and linear_decay_lr(2e-4, 99) == 2e-4
+    assert abs(linear_decay_lr(2e-4, 100) - 2e-4 * (1 - 1 / 101)) < 1e-12
+    assert abs(linear_decay_lr(2e-4, 199) - 2e-4 * (1 - 100 / 101)) < 1e-12
+
+
+def test_set_lr_changes_the_next_adam_step():
+    from oracle.cyclegan_standin import CycleGANTrainer, build_models, synthetic_pair
+    nets = build_models(seed=0, n_blocks=1) if "n_blocks" in build_models.__code__.co_varnames else build_models(seed=0)
+    tr = CycleGANTrainer(*nets)
+    a, b = synthetic_pair(1, 32, seed=3)
+    tr.set_lr(0.0)
+    w0 = nets[0].head.weight.detach().clone()
+    tr.train_step(a, b)
+    assert torch.equal(nets[0].head.weight.detach(), w0)  # lr 0: no update
+    tr.set_lr(1e-3)
+    tr.train_step(a, b)
+    step = (nets[0].head.weight.detach() - w0).abs().max()
+    assert 0 < float(step) <= 1.01e-3

@@ -103,6 +103,7 @@ int cgb_engine_bind(cgb_engine_t* e, float* pG, float* gG, float* mG, float* vG,
   e->meta_cap = 32u << 20;
   CGB_CUDA(cudaMalloc(&e->meta, e->meta_cap));
   e->record_programs();
+  for (int g = 0; g < 2; ++g) CGB_CUDA(cudaMemcpy(e->adam_hyper[g] + 2, &e->cfg.lr, sizeof(float), cudaMemcpyHostToDevice));
   e->bound = true;
   e->prog_refresh[0].run(0);
   e->prog_refresh[1].run(0);
@@ -224,6 +225,26 @@ int cgb_stage_inputs(cgb_engine_t* e, const float* real_A, const float* real_B, 
   const size_t bytes = (size_t)e->cfg.batch * 3 * e->cfg.size * e->cfg.size * sizeof(float);
   CGB_CUDA(cudaMemcpyAsync(e->staging[0], real_A, bytes, cudaMemcpyDefault, S(stream)));
   CGB_CUDA(cudaMemcpyAsync(e->staging[1], real_B, bytes, cudaMemcpyDefault, S(stream)));
+  CGB_API_END
+}
+
+int cgb_stage_inputs_u8(cgb_engine_t* e, const unsigned char* real_A, const unsigned char* real_B, void* stream) {
+  CGB_API_BEGIN
+  CGB_CHECK(e && e->bound && real_A && real_B, "bad argument / engine not bound");
+  CGB_CHECK(!e->infer_only, "inference-only engine: training entry points are unavailable");
+  const int N = e->cfg.batch, Sz = e->cfg.size;
+  const size_t bytes = (size_t)N * 3 * Sz * Sz;
+  CGB_CUDA(cudaMemcpyAsync(e->staging_u8[0], real_A, bytes, cudaMemcpyDefault, S(stream)));
+  CGB_CUDA(cudaMemcpyAsync(e->staging_u8[1], real_B, bytes, cudaMemcpyDefault, S(stream)));
+  u8hwc_to_nchw(e->staging_u8[0], N, Sz, Sz, e->staging[0], S(stream));
+  u8hwc_to_nchw(e->staging_u8[1], N, Sz, Sz, e->staging[1], S(stream));
+  CGB_API_END
+}
+
+int cgb_set_lr(cgb_engine_t* e, int group, float lr, void* stream) {
+  CGB_API_BEGIN
+  CGB_CHECK(e && e->bound && group >= 0 && group < 2 && lr >= 0.f, "bad argument / engine not bound");
+  set_device_float(e->adam_hyper[group] + 2, lr, S(stream));
   CGB_API_END
 }
 

@@ -135,6 +135,7 @@ void cgb_engine::layout(Arena& A) {
   mod_in = A.tensor(cfg.batch, S, S, 16, 3);
   mod_out = A.tensor(cfg.batch, S, S, 16, 3);
   for (int i = 0; i < 2; ++i) staging[i] = static_cast<float*>(A.alloc((size_t)N * 3 * S * S * sizeof(float)));
+  for (int i = 0; i < 2; ++i) staging_u8[i] = static_cast<unsigned char*>(A.alloc((size_t)N * 3 * S * S));
   losses = static_cast<float*>(A.alloc(64 * sizeof(float)));
   for (int g = 0; g < 2; ++g) {
     adam_step[g] = static_cast<int*>(A.alloc(64));

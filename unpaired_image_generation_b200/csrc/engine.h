@@ -236,6 +236,7 @@ struct cgb_engine {
   cgb::TensorDesc img[8];
   cgb::TensorDesc mod_in, mod_out;
   float* staging[2] = {nullptr, nullptr};  // fp32 NCHW inputs
+  unsigned char* staging_u8[2] = {nullptr, nullptr};  // uint8 HWC inputs (cgb_stage_inputs_u8)
   float* losses = nullptr;                 // CGB_NUM_LOSSES + padding
   int* adam_step[2] = {nullptr, nullptr};
   float* adam_hyper[2] = {nullptr, nullptr};

@@ -973,11 +973,29 @@ pack_weights_kernel(const float* __restrict__ master, const PackEntry* __restric
   }
 }
 
-__global__ void adam_prep_kernel(int* step, float* hyper, float lr, float beta1, float beta2) {
+// hyper[2] holds the learning rate in device memory (cgb_set_lr), so an LR schedule needs no graph re-capture
+__global__ void adam_prep_kernel(int* step, float* hyper, float beta1, float beta2) {
   const int t = *step + 1;
   *step = t;
+  const float lr = hyper[2];
   hyper[0] = (float)((double)lr / (1.0 - pow((double)beta1, (double)t)));
   hyper[1] = (float)(1.0 / sqrt(1.0 - pow((double)beta2, (double)t)));
+}
+
+__global__ void set_float_kernel(float* dst, float value) { *dst = value; }
+
+// uint8 interleaved RGB [N][H][W][3] -> fp32 planar [N][3][H][W] in [-1, 1]: x = u8 / 127.5 - 1
+// (the canonical ToTensor + Normalize(0.5, 0.5) of the CycleGAN input pipeline)
+__global__ void u8hwc_to_nchw_kernel(const unsigned char* __restrict__ src, int N, int H, int W, float* __restrict__ dst) {
+  const long long total = (long long)N * H * W;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const long long hw = (long long)H * W;
+  const long long n = idx / hw, p = idx - n * hw;
+  const unsigned char* s = src + idx * 3;
+#pragma unroll
+  // two separately rounded operations (no FMA contraction): bit-identical to the stand-in's x * (1 / 127.5) - 1
+  for (int c = 0; c < 3; ++c) dst[(n * 3 + c) * hw + p] = __fsub_rn(__fmul_rn((float)s[c], (float)(1.0 / 127.5)), 1.f);
 }
 
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
@@ -1255,9 +1273,21 @@ void pack_weights(const float* master, const PackEntry* entries_dev, int n_entri
 
 void adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                float eps, int* step_dev, float* hyper_dev, float grad_scale, cudaStream_t st) {
-  adam_prep_kernel<<<1, 1, 0, st>>>(step_dev, hyper_dev, lr, beta1, beta2);
+  (void)lr;  // the live value is hyper_dev[2] (set_device_float), initialised with the configured rate at bind time
+  adam_prep_kernel<<<1, 1, 0, st>>>(step_dev, hyper_dev, beta1, beta2);
   CGB_CUDA(cudaGetLastError());
   adam_kernel<<<blocks_for((n + 3) / 4, 256), 256, 0, st>>>(p, g, m, v, n, beta1, beta2, eps, hyper_dev, grad_scale);
+  CGB_CUDA(cudaGetLastError());
+}
+
+void set_device_float(float* dst, float value, cudaStream_t st) {
+  set_float_kernel<<<1, 1, 0, st>>>(dst, value);
+  CGB_CUDA(cudaGetLastError());
+}
+
+void u8hwc_to_nchw(const unsigned char* src, int N, int H, int W, float* dst, cudaStream_t st) {
+  const long long total = (long long)N * H * W;
+  u8hwc_to_nchw_kernel<<<blocks_for(total, 256), 256, 0, st>>>(src, N, H, W, dst);
   CGB_CUDA(cudaGetLastError());
 }
 

@@ -74,6 +74,11 @@ void pack_weights(const float* master, const PackEntry* entries_dev, int n_entri
 void adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                float eps, int* step_dev, float* hyper_dev, float grad_scale, cudaStream_t st);
 
+// one-element store on the stream (graph- and stream-ordered scalar updates: the learning rate)
+void set_device_float(float* dst, float value, cudaStream_t st);
+// uint8 interleaved RGB [N][H][W][3] -> fp32 planar [N][3][H][W], x = u8 / 127.5 - 1
+void u8hwc_to_nchw(const unsigned char* src, int N, int H, int W, float* dst, cudaStream_t st);
+
 // ---- explicit im2col of a 16-stored-channel tensor with <= 4 real channels (the 3- and 1-channel sides of
 // stem / head / conv0 / conv4), so that those layers become plain tensor-core GEMMs:
 //   dst[n][h][w][t*4 + c] = src[n][h*stride + sgn*r + off][w*stride + sgn*s + off][c],  t = r*k + s, c < 4

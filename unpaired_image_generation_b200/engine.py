@@ -171,6 +171,21 @@ class StepEngine:
         _lib.check(self.lib.cgb_stage_inputs(self._h, _ptr(a), _ptr(b), _stream()))
         self._keep = (a, b)
 
+    def stage_inputs_u8(self, real_A: torch.Tensor, real_B: torch.Tensor):
+        """uint8 interleaved RGB [N, H, W, 3] inputs (device or pinned host): converted on the device with
+        x = u8 / 127.5 - 1 (stand-in: from_uint8); a quarter of the bytes of the fp32 path"""
+        for t in (real_A, real_B):
+            if t.dtype != torch.uint8 or tuple(t.shape) != (self.batch, self.size, self.size, 3) or not t.is_contiguous():
+                raise ValueError(f"expected contiguous uint8 [{self.batch}, {self.size}, {self.size}, 3], got {t.dtype} {tuple(t.shape)}")
+        _lib.check(self.lib.cgb_stage_inputs_u8(self._h, _ptr(real_A), _ptr(real_B), _stream()))
+        self._keep = (real_A, real_B)
+
+    def set_lr(self, lr: float, group: int = -1):
+        """learning rate of one parameter group (0 generators, 1 discriminators) or of both (-1); stream-ordered,
+        held in device memory: no graph re-capture"""
+        for g in ((0, 1) if group < 0 else (group,)):
+            _lib.check(self.lib.cgb_set_lr(self._h, g, float(lr), _stream()))
+
     def run_segment(self, segment: int):
         """graph-replayed part of the step: 0 whole step, 1 G phase (incl. forwards), 2 D phase, 3/4 Adam G/D"""
         _lib.check(self.lib.cgb_run_segment(self._h, segment, _stream()))

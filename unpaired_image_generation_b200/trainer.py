@@ -51,6 +51,8 @@ class CycleGANTrainer:
         self.engine = eng
         self.stream = torch.cuda.Stream(device=eng.device)
         self.comm_stream = torch.cuda.Stream(device=eng.device)
+        if getattr(self, "_lr", None) is not None:  # set_lr() before the first step
+            eng.set_lr(self._lr)
         return eng
 
     def _enter(self):
@@ -81,7 +83,17 @@ class CycleGANTrainer:
         self._exit()
         return losses
 
+    def set_lr(self, lr: float) -> None:
+        """learning rate of both optimisers from the next step on (stand-in: CycleGANTrainer.set_lr)"""
+        self._lr = float(lr)
+        if self.engine is not None:
+            with self._enter():
+                self.engine.set_lr(self._lr)
+            self._exit()
+
     def train_step(self, real_A: torch.Tensor, real_B: torch.Tensor) -> Dict[str, float]:
+        if real_A.dtype == torch.uint8:
+            return self._train_step_u8(real_A, real_B)
         eng = self._ensure_engine(real_A)
         if self.sync.world_size == 1:
             if real_A.device.type == "cpu":
@@ -96,6 +108,20 @@ class CycleGANTrainer:
             self._exit()
             return losses
         return self._train_step_dp(eng, real_A, real_B)
+
+    def _train_step_u8(self, real_A: torch.Tensor, real_B: torch.Tensor) -> Dict[str, float]:
+        """uint8 interleaved RGB [N, H, W, 3] inputs (stand-in: train_step(from_uint8(a), from_uint8(b)))"""
+        if self.sync.world_size != 1:
+            raise NotImplementedError("uint8 inputs: single-process step only")
+        n, h, w, c = real_A.shape
+        probe = torch.empty(n, c, h, w, device="meta")
+        eng = self._ensure_engine(probe)
+        with self._enter():
+            eng.stage_inputs_u8(real_A.contiguous(), real_B.contiguous())
+            eng.train_step()
+            losses = eng.losses()
+        self._exit()
+        return losses
 
     def _train_step_dp(self, eng, real_A, real_B) -> Dict[str, float]:
         self._train_step_dp_nosync(eng, real_A, real_B)
