@@ -476,9 +476,11 @@ void cgb_engine::record_programs() {
   // ---------------------------------------------------------------- generator forward
   // xcol_in: shared im2col4 of `in` (stem as a GEMM) or nullptr (stem as a 49-tap implicit GEMM);
   // xcol_out: when non-null the im2col4 of the generated image is produced for the pass that consumes it
+  // xcol_lane >= 0: the im2col4 of the output (only the stem WEIGHT gradient of the consuming pass reads it) is
+  // issued on that side lane instead of the chain
   auto emit_gen_forward = [&](Program& pr, double* fl, GenPass& P, int net, const TensorDesc& in,
                               const TensorDesc& out, bool fill_out_halo, const TensorDesc* xcol_in,
-                              const TensorDesc* xcol_out) {
+                              const TensorDesc* xcol_out, int xcol_lane = -1) {
     P.net = net;
     P.in = in;
     P.out = out;
@@ -517,7 +519,13 @@ void cgb_engine::record_programs() {
     if (fill_out_halo) pr.add([out](cudaStream_t s) { fill_reflect_halo(out, s); });
     if (xcol_out) {
       const TensorDesc xc = *xcol_out;
+      const int main_lane = pr.cur_lane;
+      if (xcol_lane >= 0) {
+        pr.dep(main_lane, xcol_lane);
+        pr.cur_lane = xcol_lane;
+      }
       pr.add([out, xc](cudaStream_t s) { im2col4(out, 7, 1, +1, -3, true, xc, s); }, 1, kOpNorm);
+      pr.cur_lane = main_lane;
     }
   };
 
@@ -766,12 +774,15 @@ void cgb_engine::record_programs() {
     const TensorDesc ra = real_A, rb = real_B;
     prog_set_inputs.add([sa, ra](cudaStream_t s) { nchw_to_nhwc(sa, 3, ra, s); });
     prog_set_inputs.add([sb, rb](cudaStream_t s) { nchw_to_nhwc(sb, 3, rb, s); });
+    prog_set_inputs_lite.add([sa, ra](cudaStream_t s) { nchw_to_nhwc(sa, 3, ra, s); });
+    prog_set_inputs_lite.add([sb, rb](cudaStream_t s) { nchw_to_nhwc(sb, 3, rb, s); });
     if (pair) {
       // [real_A; real_B; real_A]: images 0..2N feed G_AB, images N..3N feed G_BA; one im2col over all three
       TensorDesc ra2 = reals3;
       ra2.ptr = reals3.ptr + (long long)2 * N * reals3.sN();
       ra2.N = N;
       prog_set_inputs.add([sa, ra2](cudaStream_t s) { nchw_to_nhwc(sa, 3, ra2, s); });
+      prog_set_inputs_lite.add([sa, ra2](cudaStream_t s) { nchw_to_nhwc(sa, 3, ra2, s); });
       const TensorDesc r3 = reals3, x3 = xcol3;
       prog_set_inputs.add([r3, x3](cudaStream_t s) { im2col4(r3, 7, 1, +1, -3, true, x3, s); }, 1, kOpNorm);
     } else {
@@ -908,6 +919,7 @@ void cgb_engine::record_programs() {
   }
   // ---- the whole step as one schedule, recorded twice: with Adam(D) in the shadow of the generator backward
   //      chains (single GPU) and without any optimiser (data parallel: the gradients are all-reduced first).
+  const bool xcol_side = std::getenv("CGB_STEM_GEMM") == nullptr && std::getenv("CGB_XCOL_ON_CHAIN") == nullptr;
   auto record_step = [&](Program& pr, bool with_adam_d) {  // Lanes 0/1 carry the critical chains
      //      fwd fake -> fwd rec -> bwd rec -> bwd fake; lanes 2/3 do the identity passes, the frozen-D input
      //      gradients and then the entire D phase in the shadow of those chains.
@@ -922,25 +934,50 @@ void cgb_engine::record_programs() {
     pr.add([gD, gDb](cudaStream_t s) { CGB_CUDA(cudaMemsetAsync(gD, 0, gDb, s)); }, 0, kOpMemset);
     pr.add([ls](cudaStream_t s) { CGB_CUDA(cudaMemsetAsync(ls, 0, 64 * sizeof(float), s)); }, 0, kOpMemset);
     pr.fork();
+    // The im2col4 matrices feed only the stem WEIGHT gradients (the stem forward is a patch-resident conv), so
+    // they are built on the weight-gradient lanes, off the critical chains (xcol_side; the im2col-GEMM stem of
+    // CGB_STEM_GEMM=1 needs them on the chain and keeps the full prog_set_inputs).
+    if (xcol_side) {
+      if (pair) {
+        pr.cur_lane = 4;
+        add_xcol(pr, reals3, xcol3);
+        const int ev_x = pr.record(4);
+        pr.wait(5, ev_x);
+      } else {
+        pr.cur_lane = 4;
+        add_xcol(pr, real_A, xcol[0]);
+        const int ev_xa = pr.record(4);
+        pr.cur_lane = 5;
+        add_xcol(pr, real_B, xcol[1]);
+        const int ev_xb = pr.record(5);
+        pr.wait(6, ev_xb);  // idt_A = G_AB(real_B): its stem weight gradient runs on lane 6
+        pr.wait(7, ev_xa);  // idt_B = G_BA(real_A)
+      }
+    }
+    const int xl0 = xcol_side ? 4 : -1, xl1 = xcol_side ? 5 : -1;
     int ev_fake_B, ev_fake_A;
     if (pair) {
       pr.cur_lane = 0;
       emit_gen_forward(pr, &sink, gen[0], CGB_NET_G_AB, pair_in[0], pair_out[0], true, &pair_xcol[0], nullptr);
       ev_fake_B = pr.record(0);
+      if (xcol_side) pr.dep(0, 4), pr.cur_lane = 4;
       add_xcol(pr, fake_B, xcol[2]);
+      pr.cur_lane = 0;
       pr.mark("fwd fake_B + idt_A done");
       pr.cur_lane = 1;
       emit_gen_forward(pr, &sink, gen[2], CGB_NET_G_BA, pair_in[1], pair_out[1], true, &pair_xcol[1], nullptr);
       ev_fake_A = pr.record(1);
+      if (xcol_side) pr.dep(1, 5), pr.cur_lane = 5;
       add_xcol(pr, fake_A, xcol[3]);
+      pr.cur_lane = 1;
       pr.mark("fwd fake_A + idt_B done");
     } else {
     pr.cur_lane = 0;
-    emit_gen_forward(pr, &sink, gen[0], CGB_NET_G_AB, real_A, img[CGB_IMG_FAKE_B], true, &xcol[0], &xcol[2]);
+    emit_gen_forward(pr, &sink, gen[0], CGB_NET_G_AB, real_A, img[CGB_IMG_FAKE_B], true, &xcol[0], &xcol[2], xl0);
     ev_fake_B = pr.record(0);
     pr.mark("fwd fake_B done");
     pr.cur_lane = 1;
-    emit_gen_forward(pr, &sink, gen[2], CGB_NET_G_BA, real_B, img[CGB_IMG_FAKE_A], true, &xcol[1], &xcol[3]);
+    emit_gen_forward(pr, &sink, gen[2], CGB_NET_G_BA, real_B, img[CGB_IMG_FAKE_A], true, &xcol[1], &xcol[3], xl1);
     ev_fake_A = pr.record(1);
     pr.mark("fwd fake_A done");
     // (identity passes: emitted below together with the rest of lanes 2 / 3)
@@ -1058,13 +1095,14 @@ void cgb_engine::record_programs() {
     pr.join(2);
     pr.cur_lane = 0;
   }
-  segments[CGB_SEG_STEP].seq = {&prog_set_inputs, &prog_step, &prog_adam[CGB_GROUP_G]};
+  const bool lite = std::getenv("CGB_STEM_GEMM") == nullptr && std::getenv("CGB_XCOL_ON_CHAIN") == nullptr;
+  segments[CGB_SEG_STEP].seq = {lite ? &prog_set_inputs_lite : &prog_set_inputs, &prog_step, &prog_adam[CGB_GROUP_G]};
   segments[CGB_SEG_G].seq = {&prog_set_inputs, &prog_cycle, &prog_G};
   segments[CGB_SEG_D].seq = {&prog_D};
   segments[CGB_SEG_ADAM_G].seq = {&prog_adam[0]};
   segments[CGB_SEG_ADAM_D].seq = {&prog_adam[1]};
   segments[CGB_SEG_FORWARD].seq = {&prog_set_inputs, &prog_cycle};
-  segments[CGB_SEG_STEP_NOOPT].seq = {&prog_set_inputs, &prog_step_dp};
+  segments[CGB_SEG_STEP_NOOPT].seq = {lite ? &prog_set_inputs_lite : &prog_set_inputs, &prog_step_dp};
   // ---- module-level forward programs (Generator.forward / Discriminator.forward)
   for (int net = 0; net < 2; ++net) {
     emit_gen_forward(prog_mod_gen[net], &dummy_flops, gen[6], net, mod_in, mod_out, false, nullptr, nullptr);

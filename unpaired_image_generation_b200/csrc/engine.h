@@ -263,6 +263,7 @@ struct cgb_engine {
   std::deque<cgb::IgemmPlan> igemm_plans;
   std::deque<cgb::WgradPlan> wgrad_plans;
   std::deque<cgb::SmallWgradPlan> small_wgrad_plans;
+  cgb::Program prog_set_inputs_lite;  // staging -> images only (the merged step builds the im2col4 matrices on side lanes)
   cgb::Program prog_set_inputs, prog_cycle, prog_G, prog_D, prog_adam[2], prog_refresh[2];
   cgb::Program prog_step;   // forward + G phase + D phase as ONE schedule (no joins between the phases)
   cgb::Program prog_step_dp;  // the same without Adam(D): data-parallel callers all-reduce the gradients first

@@ -102,7 +102,7 @@ class CycleGANTrainer:
                 self._exit()
                 return losses
             with self._enter():
-                eng.set_inputs(real_A, real_B)
+                eng.stage_inputs(real_A, real_B)  # copy only: the step graph converts / pads the staged images itself
                 eng.train_step()
                 losses = eng.losses()
             self._exit()
