@@ -194,3 +194,26 @@ def test_set_lr_matches_standin_schedule():
     assert 0.5 * lr3 < float(d_got.abs().median()) < 1.5 * lr3 and float(d_got.abs().max()) < 1.9e-4
     cos = float((d_got * d_want).sum() / (d_got.norm() * d_want.norm()))
     assert cos > 0.9, cos
+
+
+@pytest.mark.parametrize("size,batch", [(96, 3), (40, 2)])
+def test_ragged_sizes_and_odd_batches(size, batch):
+    """edge geometry: maps that are not multiples of the 16 x 8 conv tile (24x24, 10x10 residual stream), odd batch,
+    discriminator maps down to 3x3: images within the bf16 noise floor of the fp32 stand-in, losses within tolerance"""
+    _need_gpu()
+    tr, _ = _trainer()
+    real_A, real_B = ref.synthetic_pair(batch, size, seed=77)
+    imgs = tr.forward_only(real_A.cuda(), real_B.cuda())
+    f32 = ref.CycleGANTrainer(*ref.build_models(seed=0)).forward_only(real_A, real_B)
+    emu = ref.CycleGANTrainer(*ref.build_models(seed=0), emulate_bf16=True).forward_only(real_A, real_B)
+    for k in ("fake_B", "fake_A", "idt_A", "idt_B"):
+        rel = lambda a, b: float((a.double().cpu() - b.double()).norm() / b.double().norm())
+        floor = rel(emu[k], f32[k])
+        assert rel(imgs[k], f32[k]) < 1.5 * floor + 2e-3, (k, rel(imgs[k], f32[k]), floor)
+    losses = tr.backward_only(real_A.cuda(), real_B.cuda())
+    want = ref.CycleGANTrainer(*ref.build_models(seed=0)).backward_only(real_A, real_B)
+    for k in ("loss_G", "loss_cycle_A", "loss_cycle_B", "loss_idt_A", "loss_idt_B"):
+        assert abs(losses[k] - want[k]) / abs(want[k]) < 1e-2, (k, losses[k], want[k])
+    for k in ("loss_G_A", "loss_G_B", "loss_D_A", "loss_D_B"):  # a handful of logits: noisy
+        assert abs(losses[k] - want[k]) / abs(want[k]) < 1e-1, (k, losses[k], want[k])
+    assert all(np.isfinite(v) for v in losses.values())
