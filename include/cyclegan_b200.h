@@ -42,7 +42,9 @@ typedef struct cgb_config {
 enum { CGB_NET_G_AB = 0, CGB_NET_G_BA = 1, CGB_NET_D_A = 2, CGB_NET_D_B = 3 };
 enum { CGB_GROUP_G = 0, CGB_GROUP_D = 1 };
 enum { CGB_IMG_FAKE_B = 0, CGB_IMG_REC_A = 1, CGB_IMG_FAKE_A = 2, CGB_IMG_REC_B = 3, CGB_IMG_IDT_A = 4,
-       CGB_IMG_IDT_B = 5, CGB_IMG_REAL_A = 6, CGB_IMG_REAL_B = 7 };
+       CGB_IMG_IDT_B = 5, CGB_IMG_REAL_A = 6, CGB_IMG_REAL_B = 7,
+       /* with the image pool: what the discriminators saw as fakes in the last D phase (pool.query output) */
+       CGB_IMG_POOL_FAKE_B = 8, CGB_IMG_POOL_FAKE_A = 9 };
 /* loss slots, same order as CycleGANTrainer.LOSS_KEYS in the stand-in */
 enum { CGB_LOSS_G = 0, CGB_LOSS_G_A, CGB_LOSS_G_B, CGB_LOSS_CYCLE_A, CGB_LOSS_CYCLE_B, CGB_LOSS_IDT_A,
        CGB_LOSS_IDT_B, CGB_LOSS_D_A, CGB_LOSS_D_B, CGB_NUM_LOSSES };
@@ -73,6 +75,15 @@ int cgb_num_params(const cgb_engine_t* e, int net);                       /* ten
 int cgb_param_info(const cgb_engine_t* e, int net, int index, cgb_param_info_t* out);
 long long cgb_group_numel(const cgb_engine_t* e, int group);              /* floats in the flat buffers */
 long long cgb_workspace_bytes(const cgb_engine_t* e);
+
+/* Image history pool of the canonical recipe (ImagePool, 50 images per domain): call BEFORE cgb_engine_bind (the
+ * workspace grows by 2 * pool_size images).  With a pool the D phase sees pool.query(fake) instead of the current
+ * fake.  The random decisions are made by the caller (host), one (store, ret) pair of ints per image and step:
+ * d_in = ret >= 0 ? pool[ret] : fake; then pool[store] = fake when store >= 0 -- see PoolDecisions in the stand-in
+ * (oracle/cyclegan_standin.py).  decisions: [2][batch][2] ints, [0] = fake_B pool (D_A), [1] = fake_A pool (D_B);
+ * device or pinned host; (-1, -1) until first set. */
+int cgb_engine_set_image_pool(cgb_engine_t* e, int pool_size);
+int cgb_set_pool_decisions(cgb_engine_t* e, const int* decisions, void* stream);
 
 /* ---- binding (needs the GPU) ------------------------------------------------------------------------- */
 /* params/grads/m/v: fp32 flat buffers of cgb_group_numel(group) elements; workspace: cgb_workspace_bytes. */

@@ -227,11 +227,52 @@ def linear_decay_lr(base_lr: float, epoch: int, n_epochs: int = 100, n_epochs_de
     return base_lr * (1.0 - max(0, epoch + 1 - n_epochs) / float(n_epochs_decay + 1))
 
 
+class PoolDecisions:
+    """The random decisions of the canonical ImagePool.query, one per image: (store, ret).
+    ret >= 0: the discriminator sees the OLD pool[ret] instead of the new fake; store >= 0: the new fake is written
+    to pool[store] afterwards.  Filling phase: (count, -1); then with probability 0.5 swap a random slot (i, i),
+    else pass the new image through (-1, -1)."""
+
+    def __init__(self, pool_size: int, seed: int = 0):
+        import random
+        self.size, self.count, self.rng = int(pool_size), 0, random.Random(seed)
+
+    def next(self):
+        if self.size <= 0:
+            return -1, -1
+        if self.count < self.size:
+            self.count += 1
+            return self.count - 1, -1
+        if self.rng.uniform(0.0, 1.0) > 0.5:
+            i = self.rng.randint(0, self.size - 1)
+            return i, i
+        return -1, -1
+
+
+class ImagePool:
+    """History of generated images shown to a discriminator (pool_size 50 in the canonical recipe)."""
+
+    def __init__(self, pool_size: int, seed: int = 0):
+        self.decisions = PoolDecisions(pool_size, seed)
+        self.images = [None] * max(0, int(pool_size))
+
+    def query(self, images: torch.Tensor) -> torch.Tensor:
+        out = []
+        for img in images.detach():
+            store, ret = self.decisions.next()
+            cur = img.clone()
+            out.append(self.images[ret].clone() if ret >= 0 else cur)
+            if store >= 0:
+                self.images[store] = cur
+        return torch.stack(out)
+
+
 # --------------------------------------------------------------------------------------
 # Training step
 # --------------------------------------------------------------------------------------
 class CycleGANTrainer:
-    """Canonical CycleGAN optimisation step (no image pool, constant lr).
+    """Canonical CycleGAN optimisation step (constant lr unless set_lr is driven; image history pool when
+    pool_size > 0: the discriminators then see pool.query(fake), pools seeded pool_seed / pool_seed + 1).
 
     train_step(real_A, real_B) -> dict of python floats:
       loss_G, loss_G_A, loss_G_B, loss_cycle_A, loss_cycle_B, loss_idt_A, loss_idt_B,
@@ -245,8 +286,10 @@ class CycleGANTrainer:
     def __init__(self, G_AB: Generator, G_BA: Generator, D_A: Discriminator, D_B: Discriminator,
                  lambda_A: float = 10.0, lambda_B: float = 10.0, lambda_idt: float = 0.5,
                  lr: float = 2e-4, betas=(0.5, 0.999), eps: float = 1e-8,
-                 emulate_bf16: bool = False):
+                 emulate_bf16: bool = False, pool_size: int = 0, pool_seed: int = 0):
         self.G_AB, self.G_BA, self.D_A, self.D_B = G_AB, G_BA, D_A, D_B
+        self.pool_B = ImagePool(pool_size, pool_seed) if pool_size > 0 else None      # fake_B history, for D_A
+        self.pool_A = ImagePool(pool_size, pool_seed + 1) if pool_size > 0 else None  # fake_A history, for D_B
         self.lambda_A, self.lambda_B, self.lambda_idt = lambda_A, lambda_B, lambda_idt
         self.P = Precision(emulate_bf16)
         self.opt_G = torch.optim.Adam(list(G_AB.parameters()) + list(G_BA.parameters()), lr=lr, betas=betas, eps=eps)
@@ -311,9 +354,11 @@ class CycleGANTrainer:
         for p in list(self.D_A.parameters()) + list(self.D_B.parameters()):
             p.requires_grad_(True)
         self.opt_D.zero_grad(set_to_none=True)
-        loss_D_A = self.compute_D_loss(self.D_A, real_B, imgs["fake_B"])
+        fake_B = self.pool_B.query(imgs["fake_B"]) if self.pool_B else imgs["fake_B"]
+        fake_A = self.pool_A.query(imgs["fake_A"]) if self.pool_A else imgs["fake_A"]
+        loss_D_A = self.compute_D_loss(self.D_A, real_B, fake_B)
         loss_D_A.backward()
-        loss_D_B = self.compute_D_loss(self.D_B, real_A, imgs["fake_A"])
+        loss_D_B = self.compute_D_loss(self.D_B, real_A, fake_A)
         loss_D_B.backward()
         self.last_images = {k: v.detach() for k, v in imgs.items()}
         out = {k: float(v.detach()) for k, v in L.items()}
@@ -333,9 +378,11 @@ class CycleGANTrainer:
         for p in list(self.D_A.parameters()) + list(self.D_B.parameters()):
             p.requires_grad_(True)
         self.opt_D.zero_grad(set_to_none=True)
-        loss_D_A = self.compute_D_loss(self.D_A, real_B, imgs["fake_B"])
+        fake_B = self.pool_B.query(imgs["fake_B"]) if self.pool_B else imgs["fake_B"]
+        fake_A = self.pool_A.query(imgs["fake_A"]) if self.pool_A else imgs["fake_A"]
+        loss_D_A = self.compute_D_loss(self.D_A, real_B, fake_B)
         loss_D_A.backward()
-        loss_D_B = self.compute_D_loss(self.D_B, real_A, imgs["fake_A"])
+        loss_D_B = self.compute_D_loss(self.D_B, real_A, fake_A)
         loss_D_B.backward()
         self.opt_D.step()
         self.last_images = {k: v.detach() for k, v in imgs.items()}

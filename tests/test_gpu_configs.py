@@ -217,3 +217,39 @@ def test_ragged_sizes_and_odd_batches(size, batch):
     for k in ("loss_G_A", "loss_G_B", "loss_D_A", "loss_D_B"):  # a handful of logits: noisy
         assert abs(losses[k] - want[k]) / abs(want[k]) < 1e-1, (k, losses[k], want[k])
     assert all(np.isfinite(v) for v in losses.values())
+
+
+def test_image_pool_on_device_matches_standin():
+    """image history pool: the images the discriminators see are exactly pool.query(fake) replayed from the engine's
+    own fakes with the same decisions; D losses follow the stand-in run with the same pool seed"""
+    _need_gpu()
+    from unpaired_image_generation_b200.trainer import _PoolDecisions
+    onets = ref.build_models(seed=0)
+    mods = (cgb.Generator(), cgb.Generator(), cgb.Discriminator(), cgb.Discriminator())
+    for m, o in zip(mods, onets):
+        m.load_state_dict(o.state_dict())
+    tr = cgb.CycleGANTrainer(*mods, pool_size=2, pool_seed=3)
+    otr = ref.CycleGANTrainer(*onets, pool_size=2, pool_seed=3)
+    shadow = [_PoolDecisions(2, 3), _PoolDecisions(2, 4)]
+    hist = [[None, None], [None, None]]
+    used_history = False
+    for step in range(8):
+        real_A, real_B = ref.synthetic_pair(1, 64, seed=100 + step)
+        got = tr.train_step(real_A.cuda(), real_B.cuda())
+        want = otr.train_step(real_A, real_B)
+        for side, (name, pname) in enumerate((("fake_B", "pool_fake_B"), ("fake_A", "pool_fake_A"))):
+            fake = tr.engine.get_image(name).cpu()
+            seen = tr.engine.get_image(pname).cpu()
+            store, ret = shadow[side].next()
+            expect = hist[side][ret] if ret >= 0 else fake
+            used_history |= ret >= 0
+            assert torch.equal(seen, expect), (step, name, store, ret)
+            if store >= 0:
+                hist[side][store] = fake
+        for k in ("loss_D_A", "loss_D_B"):
+            assert abs(got[k] - want[k]) / abs(want[k]) < 0.25, (step, k, got[k], want[k])  # 36 logits, 8 noisy steps
+        for k in ("loss_cycle_A", "loss_idt_B"):
+            assert abs(got[k] - want[k]) / abs(want[k]) < 3e-2, (step, k, got[k], want[k])
+    assert used_history
+    with pytest.raises(RuntimeError, match="image pool is not enabled"):
+        _trainer()[0]._ensure_engine(torch.empty(1, 3, 64, 64, device="meta")).get_image("pool_fake_B")

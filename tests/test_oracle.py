@@ -162,3 +162,23 @@ def test_set_lr_changes_the_next_adam_step():
     tr.train_step(a, b)
     step = (nets[0].head.weight.detach() - w0).abs().max()
     assert 0 < float(step) <= 1.01e-3
+
+
+def test_image_pool_semantics_and_decisions_match_the_product():
+    """canonical ImagePool: fill, then swap a random slot with probability 0.5; the product's host-side decision
+    generator (trainer._PoolDecisions) restates the stand-in's PoolDecisions and must produce the same sequence"""
+    from oracle.cyclegan_standin import ImagePool, PoolDecisions
+    from unpaired_image_generation_b200.trainer import _PoolDecisions
+    a, b = PoolDecisions(3, seed=5), _PoolDecisions(3, 5)
+    seq = [a.next() for _ in range(200)]
+    assert seq == [b.next() for _ in range(200)]
+    assert seq[:3] == [(0, -1), (1, -1), (2, -1)]
+    swaps = [s for s in seq[3:] if s != (-1, -1)]
+    assert 60 < len(swaps) < 140 and all(s[0] == s[1] and 0 <= s[0] < 3 for s in swaps)
+    pool = ImagePool(2, seed=1)
+    imgs = [torch.full((1, 3, 2, 2), float(i)) for i in range(12)]
+    outs = [float(pool.query(x)[0, 0, 0, 0]) for x in imgs]
+    assert outs[:2] == [0.0, 1.0]                       # filling: images pass through
+    assert all(o <= i for i, o in enumerate(outs))      # never an image from the future
+    assert any(o < i for i, o in enumerate(outs))       # history is used
+    assert PoolDecisions(0).next() == (-1, -1)

@@ -41,6 +41,8 @@ SIGNATURES = {
     "cgb_set_grad_scale": (c_int, [_P, c_float]),
     "cgb_set_step_count": (c_int, [_P, c_int, c_int]),
     "cgb_set_lr": (c_int, [_P, c_int, c_float, _P]),
+    "cgb_engine_set_image_pool": (c_int, [_P, c_int]),
+    "cgb_set_pool_decisions": (c_int, [_P, _P, _P]),
     "cgb_stage_inputs_u8": (c_int, [_P, _P, _P, _P]),
     "cgb_generator_forward": (c_int, [_P, c_int, _P, _P, _P]),
     "cgb_discriminator_forward": (c_int, [_P, c_int, _P, _P, _P]),

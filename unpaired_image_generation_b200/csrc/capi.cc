@@ -102,6 +102,7 @@ int cgb_engine_bind(cgb_engine_t* e, float* pG, float* gG, float* mG, float* vG,
   CGB_CUDA(cudaMemset(workspace, 0, e->workspace_bytes));
   e->meta_cap = 32u << 20;
   CGB_CUDA(cudaMalloc(&e->meta, e->meta_cap));
+  if (e->pool_dec) CGB_CUDA(cudaMemset(e->pool_dec, 0xFF, (size_t)2 * e->cfg.batch * 2 * sizeof(int)));  // (-1, -1): pass-through
   e->record_programs();
   for (int g = 0; g < 2; ++g) CGB_CUDA(cudaMemcpy(e->adam_hyper[g] + 2, &e->cfg.lr, sizeof(float), cudaMemcpyHostToDevice));
   e->bound = true;
@@ -171,9 +172,14 @@ int cgb_forward_cycle(cgb_engine_t* e, void* stream) {
 
 int cgb_get_image(cgb_engine_t* e, int which, float* out, void* stream) {
   CGB_API_BEGIN
-  CGB_CHECK(e && e->bound && which >= 0 && which < 8 && out, "bad argument / engine not bound");
+  CGB_CHECK(e && e->bound && which >= 0 && which < 10 && out, "bad argument / engine not bound");
   CGB_CHECK(!e->infer_only, "inference-only engine: training entry points are unavailable");
-  nhwc_to_nchw(e->img[which], 3, out, S(stream));
+  if (which >= CGB_IMG_POOL_FAKE_B) {
+    CGB_CHECK(e->pool_size > 0, "the image pool is not enabled (cgb_engine_set_image_pool)");
+    nhwc_to_nchw(e->pool_din[which - CGB_IMG_POOL_FAKE_B], 3, out, S(stream));
+  } else {
+    nhwc_to_nchw(e->img[which], 3, out, S(stream));
+  }
   CGB_API_END
 }
 
@@ -238,6 +244,25 @@ int cgb_stage_inputs_u8(cgb_engine_t* e, const unsigned char* real_A, const unsi
   CGB_CUDA(cudaMemcpyAsync(e->staging_u8[1], real_B, bytes, cudaMemcpyDefault, S(stream)));
   u8hwc_to_nchw(e->staging_u8[0], N, Sz, Sz, e->staging[0], S(stream));
   u8hwc_to_nchw(e->staging_u8[1], N, Sz, Sz, e->staging[1], S(stream));
+  CGB_API_END
+}
+
+int cgb_engine_set_image_pool(cgb_engine_t* e, int pool_size) {
+  CGB_API_BEGIN
+  CGB_CHECK(e && !e->bound, "cgb_engine_set_image_pool must be called before cgb_engine_bind");
+  CGB_CHECK(pool_size >= 0 && pool_size <= 4096, "pool_size out of range");
+  e->pool_size = pool_size;
+  Arena A;  // re-plan the workspace
+  e->layout(A);
+  e->workspace_bytes = A.off;
+  CGB_API_END
+}
+
+int cgb_set_pool_decisions(cgb_engine_t* e, const int* decisions, void* stream) {
+  CGB_API_BEGIN
+  CGB_CHECK(e && e->bound && decisions, "bad argument / engine not bound");
+  CGB_CHECK(e->pool_size > 0, "the image pool is not enabled (cgb_engine_set_image_pool)");
+  CGB_CUDA(cudaMemcpyAsync(e->pool_dec, decisions, (size_t)2 * e->cfg.batch * 2 * sizeof(int), cudaMemcpyDefault, S(stream)));
   CGB_API_END
 }
 

@@ -178,10 +178,10 @@ void cgb_engine::layout(Arena& A) {
     P.stats = static_cast<float2*>(A.alloc(P.stats_bytes));
     P.bstats = static_cast<float2*>(A.alloc(P.stats_bytes));
   }
-  dis.resize(5);
+  dis.resize(7);
   for (size_t di = 0; di < dis.size(); ++di) {
     DisPass& D = dis[di];
-    const int N = (di == 4 || !infer_only) ? cfg.batch : 0;
+    const int N = di >= 5 ? ((pool_size > 0 && !infer_only) ? cfg.batch : 0) : (di == 4 || !infer_only) ? cfg.batch : 0;
     D.l0 = A.tensor(N, H2, H2, 64, 0);
     D.y1 = A.tensor(N, H4, H4, 128, 0);
     D.a1 = A.tensor(N, H4, H4, 128, 0);
@@ -242,6 +242,13 @@ void cgb_engine::layout(Arena& A) {
     d.dpre0 = A.tensor(N, H2, H2, 64, 0);
     d.colbuf_elems = (size_t)N * H2 * H2 * 64;
     d.colbuf = static_cast<bf16*>(A.alloc(d.colbuf_elems * sizeof(bf16)));
+  }
+  if (pool_size > 0 && !infer_only) {
+    for (int i = 0; i < 2; ++i) {
+      pool_img[i] = A.tensor(pool_size, S, S, 16, 0);
+      pool_din[i] = A.tensor(cfg.batch, S, S, 16, 0);
+    }
+    pool_dec = static_cast<int*>(A.alloc((size_t)2 * cfg.batch * 2 * sizeof(int)));
   }
   A.alloc(1024);  // tail guard
 }
@@ -898,6 +905,21 @@ void cgb_engine::record_programs() {
     pr.cur_lane = 0;
     pr.mark("G phase end");
   }
+  // D-phase pass on the fakes.  Without a pool the G-phase forward of D on the fake is reused (D unchanged since).
+  // With the image history pool the discriminator sees pool.query(fake): exchange kernel, then a forward of its own.
+  auto emit_dis_fake_phase = [&](Program& pr, double* fl, int side) {
+    const int dnet = side == 0 ? CGB_NET_D_A : CGB_NET_D_B;
+    const int slot = side == 0 ? CGB_LOSS_D_A : CGB_LOSS_D_B;
+    if (pool_size > 0) {
+      const TensorDesc fk = side == 0 ? fake_B : fake_A, pl = pool_img[side], din = pool_din[side];
+      const int* dec = pool_dec + (size_t)side * cfg.batch * 2;
+      pr.add([fk, pl, dec, din](cudaStream_t s) { pool_exchange(fk, pl, dec, din, s); });
+      emit_dis_forward(pr, fl, dis[5 + side], dnet, pool_din[side]);
+      emit_dis_backward(pr, fl, dis[5 + side], ds[side], 0.f, 0.5f, slot, true, nullptr);
+    } else {
+      emit_dis_backward(pr, fl, dis[side], ds[side], 0.f, 0.5f, slot, true, nullptr);
+    }
+  };
   {  // ---- D phase: real passes are new; the fake passes reuse the G-phase forward (D unchanged since)
     Program& pr = prog_D;
     float* gD = G[CGB_GROUP_D];
@@ -908,11 +930,11 @@ void cgb_engine::record_programs() {
     pr.cur_lane = 0;
     emit_dis_forward(pr, flops, dis[2], CGB_NET_D_A, real_B);
     emit_dis_backward(pr, flops, dis[2], ds[0], 1.f, 0.5f, CGB_LOSS_D_A, true, nullptr);
-    emit_dis_backward(pr, flops, dis[0], ds[0], 0.f, 0.5f, CGB_LOSS_D_A, true, nullptr);
+    emit_dis_fake_phase(pr, flops, 0);
     pr.cur_lane = 1;
     emit_dis_forward(pr, flops, dis[3], CGB_NET_D_B, real_A);
     emit_dis_backward(pr, flops, dis[3], ds[1], 1.f, 0.5f, CGB_LOSS_D_B, true, nullptr);
-    emit_dis_backward(pr, flops, dis[1], ds[1], 0.f, 0.5f, CGB_LOSS_D_B, true, nullptr);
+    emit_dis_fake_phase(pr, flops, 1);
     pr.join();
     pr.cur_lane = 0;
     pr.mark("D phase end");
@@ -1037,7 +1059,7 @@ void cgb_engine::record_programs() {
       }
       emit_dis_forward(pr, &sink, dis[2 + side], dnet, real_in);
       emit_dis_backward(pr, &sink, dis[2 + side], ds[side], 1.f, 0.5f, side == 0 ? CGB_LOSS_D_A : CGB_LOSS_D_B, true, nullptr);
-      emit_dis_backward(pr, &sink, dis[side], ds[side], 0.f, 0.5f, side == 0 ? CGB_LOSS_D_A : CGB_LOSS_D_B, true, nullptr);
+      emit_dis_fake_phase(pr, &sink, side);
       pr.mark(side == 0 ? "D_A all done" : "D_B all done");
       return ev;
     };

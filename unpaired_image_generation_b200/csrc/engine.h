@@ -218,6 +218,9 @@ struct cgb_engine {
   int sm_count = 148;
   bool bound = false;
   bool infer_only = false;  // CGB_FLAG_INFERENCE: module forwards only
+  int pool_size = 0;        // image history pool (cgb_engine_set_image_pool): 0 = off (D sees the current fakes)
+  cgb::TensorDesc pool_img[2], pool_din[2];  // [0]: fake_B history (for D_A), [1]: fake_A history (for D_B)
+  int* pool_dec = nullptr;  // device [2][batch][2]: (store, ret) per image, written by cgb_set_pool_decisions
   float grad_scale = 1.f;
 
   std::vector<cgb::LayerParam> layers[4];
@@ -241,7 +244,7 @@ struct cgb_engine {
   int* adam_step[2] = {nullptr, nullptr};
   float* adam_hyper[2] = {nullptr, nullptr};
   std::vector<cgb::GenPass> gen;  // 6 training passes + 1 module-forward pass
-  std::vector<cgb::DisPass> dis;  // 4 training passes + 1 module-forward pass
+  std::vector<cgb::DisPass> dis;  // 4 training passes + 1 module-forward pass + 2 passes on the pool's output
   cgb::GenScratch gs[cgb::kPassLanes];
   cgb::DisScratch ds[2];
   cgb::TensorDesc dxp_img[2], dx_D0[2];  // gradients w.r.t. the fake images (from the cycle passes / from D)

@@ -982,6 +982,28 @@ __global__ void adam_prep_kernel(int* step, float* hyper, float beta1, float bet
   hyper[1] = (float)(1.0 / sqrt(1.0 - pow((double)beta2, (double)t)));
 }
 
+// Image history pool (canonical ImagePool.query with the decisions made on the host): per image n, in batch
+// order, d_in[n] = ret >= 0 ? pool[ret] : fake[n]; then pool[store] = fake[n] when store >= 0.  A thread owns one
+// 8-channel vector of a pixel and walks the batch sequentially, so two images that pick the same slot behave as in
+// the sequential stand-in.  dec = [N][2] = (store, ret).
+__global__ void pool_exchange_kernel(DevTensor fake, DevTensor pool, const int* __restrict__ dec, DevTensor d_in) {
+  const int C8 = fake.C / 8;
+  const long long total = (long long)fake.H * fake.W * C8;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c0 = (int)(idx % C8) * 8;
+  const long long p = idx / C8;
+  const int w = (int)(p % fake.W), h = (int)(p / fake.W);
+  for (int n = 0; n < fake.N; ++n) {
+    const int store = dec[2 * n], ret = dec[2 * n + 1];
+    const uint4 v = *reinterpret_cast<const uint4*>(fake.p + n * fake.sN + h * fake.sH + w * fake.sW + c0);
+    uint4 r = v;
+    if (ret >= 0 && ret < pool.N) r = *reinterpret_cast<const uint4*>(pool.p + ret * pool.sN + h * pool.sH + w * pool.sW + c0);
+    *reinterpret_cast<uint4*>(d_in.p + n * d_in.sN + h * d_in.sH + w * d_in.sW + c0) = r;
+    if (store >= 0 && store < pool.N) *reinterpret_cast<uint4*>(pool.p + store * pool.sN + h * pool.sH + w * pool.sW + c0) = v;
+  }
+}
+
 __global__ void set_float_kernel(float* dst, float value) { *dst = value; }
 
 // uint8 interleaved RGB [N][H][W][3] -> fp32 planar [N][3][H][W] in [-1, 1]: x = u8 / 127.5 - 1
@@ -1277,6 +1299,15 @@ void adam_step(float* p, const float* g, float* m, float* v, long long n, float 
   adam_prep_kernel<<<1, 1, 0, st>>>(step_dev, hyper_dev, beta1, beta2);
   CGB_CUDA(cudaGetLastError());
   adam_kernel<<<blocks_for((n + 3) / 4, 256), 256, 0, st>>>(p, g, m, v, n, beta1, beta2, eps, hyper_dev, grad_scale);
+  CGB_CUDA(cudaGetLastError());
+}
+
+void pool_exchange(const TensorDesc& fake, const TensorDesc& pool, const int* dec, const TensorDesc& d_in, cudaStream_t st) {
+  CGB_CHECK(fake.C == pool.C && fake.C == d_in.C && fake.H == pool.H && fake.W == pool.W && d_in.N == fake.N &&
+                d_in.H == fake.H && d_in.W == fake.W && fake.C % 8 == 0,
+            "pool_exchange: shape mismatch");
+  const long long total = (long long)fake.H * fake.W * (fake.C / 8);
+  pool_exchange_kernel<<<blocks_for(total, 256), 256, 0, st>>>(dev(fake), dev(pool), dec, dev(d_in));
   CGB_CUDA(cudaGetLastError());
 }
 

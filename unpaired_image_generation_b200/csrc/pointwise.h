@@ -74,6 +74,9 @@ void pack_weights(const float* master, const PackEntry* entries_dev, int n_entri
 void adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                float eps, int* step_dev, float* hyper_dev, float grad_scale, cudaStream_t st);
 
+// Image history pool exchange: d_in[n] = dec[n].ret >= 0 ? pool[ret] : fake[n]; pool[dec[n].store] = fake[n]
+// (batch order; dec = [N][2] ints (store, ret) on the device, -1 = none)
+void pool_exchange(const TensorDesc& fake, const TensorDesc& pool, const int* dec, const TensorDesc& d_in, cudaStream_t st);
 // one-element store on the stream (graph- and stream-ordered scalar updates: the learning rate)
 void set_device_float(float* dst, float value, cudaStream_t st);
 // uint8 interleaved RGB [N][H][W][3] -> fp32 planar [N][3][H][W], x = u8 / 127.5 - 1

@@ -13,7 +13,8 @@ from . import _lib
 
 NET_G_AB, NET_G_BA, NET_D_A, NET_D_B = 0, 1, 2, 3
 GROUP_G, GROUP_D = 0, 1
-IMAGE_IDS = OrderedDict(fake_B=0, rec_A=1, fake_A=2, rec_B=3, idt_A=4, idt_B=5, real_A=6, real_B=7)
+IMAGE_IDS = OrderedDict(fake_B=0, rec_A=1, fake_A=2, rec_B=3, idt_A=4, idt_B=5, real_A=6, real_B=7,
+                        pool_fake_B=8, pool_fake_A=9)
 LOSS_KEYS = ("loss_G", "loss_G_A", "loss_G_B", "loss_cycle_A", "loss_cycle_B", "loss_idt_A", "loss_idt_B",
              "loss_D_A", "loss_D_B")
 
@@ -74,7 +75,7 @@ def describe(batch: int, size: int, n_blocks: int = 9) -> Dict[int, List[ParamIn
 class StepEngine:
     def __init__(self, batch: int, size: int, n_blocks: int = 9, lambda_A: float = 10.0, lambda_B: float = 10.0,
                  lambda_idt: float = 0.5, lr: float = 2e-4, betas=(0.5, 0.999), eps: float = 1e-8, device=None,
-                 inference: bool = False):
+                 inference: bool = False, pool_size: int = 0):
         if not torch.cuda.is_available():
             raise RuntimeError("unpaired_image_generation_b200 needs a CUDA device (B200, sm_100a); "
                                "there is no CPU fallback")
@@ -86,6 +87,9 @@ class StepEngine:
         # inference=True: module forwards only (CGB_FLAG_INFERENCE): the workspace holds one forward pass
         self.inference = bool(inference)
         _lib.check(self.lib.cgb_engine_create_ex(ctypes.byref(cfg), 1 if inference else 0, ctypes.byref(self._h)))
+        self.pool_size = int(pool_size)
+        if self.pool_size > 0:  # image history pool: re-plans the workspace, must precede the bind
+            _lib.check(self.lib.cgb_engine_set_image_pool(self._h, self.pool_size))
         self.infos: Dict[int, List[ParamInfo]] = {}
         for net in range(4):
             lst = []
@@ -179,6 +183,13 @@ class StepEngine:
                 raise ValueError(f"expected contiguous uint8 [{self.batch}, {self.size}, {self.size}, 3], got {t.dtype} {tuple(t.shape)}")
         _lib.check(self.lib.cgb_stage_inputs_u8(self._h, _ptr(real_A), _ptr(real_B), _stream()))
         self._keep = (real_A, real_B)
+
+    def set_pool_decisions(self, decisions: torch.Tensor):
+        """int32 [2, batch, 2] (store, ret) pairs of this step's image-pool queries (device or pinned host)"""
+        if decisions.dtype != torch.int32 or tuple(decisions.shape) != (2, self.batch, 2) or not decisions.is_contiguous():
+            raise ValueError(f"expected contiguous int32 [2, {self.batch}, 2]")
+        _lib.check(self.lib.cgb_set_pool_decisions(self._h, _ptr(decisions), _stream()))
+        self._keep_dec = decisions
 
     def set_lr(self, lr: float, group: int = -1):
         """learning rate of one parameter group (0 generators, 1 discriminators) or of both (-1); stream-ordered,

@@ -16,17 +16,40 @@ from .modules import Discriminator, Generator
 from .parallel import GradSync
 
 
+class _PoolDecisions:
+    """Host side of the image history pool: the random decisions of the canonical ImagePool.query, one (store, ret)
+    pair per image (restated from the stand-in's PoolDecisions, oracle/cyclegan_standin.py; the images themselves
+    live in the engine's workspace and are exchanged by a kernel)."""
+
+    def __init__(self, pool_size: int, seed: int):
+        import random
+        self.size, self.count, self.rng = int(pool_size), 0, random.Random(seed)
+
+    def next(self):
+        if self.size <= 0:
+            return -1, -1
+        if self.count < self.size:
+            self.count += 1
+            return self.count - 1, -1
+        if self.rng.uniform(0.0, 1.0) > 0.5:
+            i = self.rng.randint(0, self.size - 1)
+            return i, i
+        return -1, -1
+
+
 class CycleGANTrainer:
     LOSS_KEYS = _engine.LOSS_KEYS
 
     def __init__(self, G_AB: Generator, G_BA: Generator, D_A: Discriminator, D_B: Discriminator,
                  lambda_A: float = 10.0, lambda_B: float = 10.0, lambda_idt: float = 0.5, lr: float = 2e-4,
-                 betas=(0.5, 0.999), eps: float = 1e-8, process_group=None):
+                 betas=(0.5, 0.999), eps: float = 1e-8, process_group=None, pool_size: int = 0, pool_seed: int = 0):
         self.G_AB, self.G_BA, self.D_A, self.D_B = G_AB, G_BA, D_A, D_B
         if G_AB.n_blocks != G_BA.n_blocks:
             raise ValueError("both generators must have the same number of residual blocks")
         self._hyper = dict(lambda_A=lambda_A, lambda_B=lambda_B, lambda_idt=lambda_idt, lr=lr, betas=betas, eps=eps)
         self.sync = GradSync(process_group)
+        self.pool_size = int(pool_size)
+        self._pools = (_PoolDecisions(pool_size, pool_seed), _PoolDecisions(pool_size, pool_seed + 1))  # fake_B, fake_A
         self.engine: Optional[_engine.StepEngine] = None
         self.stream: Optional[torch.cuda.Stream] = None
         self.comm_stream: Optional[torch.cuda.Stream] = None
@@ -42,7 +65,7 @@ class CycleGANTrainer:
                 raise ValueError("the trainer is bound to input shape "
                                  f"{(self.engine.batch, 3, self.engine.size, self.engine.size)}")
             return self.engine
-        eng = _engine.StepEngine(batch, h, self.G_AB.n_blocks, **self._hyper)
+        eng = _engine.StepEngine(batch, h, self.G_AB.n_blocks, pool_size=self.pool_size, **self._hyper)
         for net, mod in enumerate((self.G_AB, self.G_BA, self.D_A, self.D_B)):
             mod._attach(eng, net)
         eng.refresh_weights(0)
@@ -54,6 +77,19 @@ class CycleGANTrainer:
         if getattr(self, "_lr", None) is not None:  # set_lr() before the first step
             eng.set_lr(self._lr)
         return eng
+
+    def _pool_step(self, eng) -> None:
+        """this step's image-pool decisions (one per image and pool), sent ahead of the D phase"""
+        if self.pool_size <= 0:
+            return
+        dec = torch.empty(2, eng.batch, 2, dtype=torch.int32)
+        for side in range(2):
+            for n in range(eng.batch):
+                store, ret = self._pools[side].next()
+                dec[side, n, 0], dec[side, n, 1] = store, ret
+        dec = dec.pin_memory()
+        with torch.cuda.stream(self.stream):
+            eng.set_pool_decisions(dec)
 
     def _enter(self):
         self.stream.wait_stream(torch.cuda.current_stream())
@@ -75,6 +111,7 @@ class CycleGANTrainer:
     def backward_only(self, real_A: torch.Tensor, real_B: torch.Tensor) -> Dict[str, float]:
         """forward + both backward phases, no optimiser step; gradients are left in `grads(name)`"""
         eng = self._ensure_engine(real_A)
+        self._pool_step(eng)
         with self._enter():
             eng.set_inputs(real_A, real_B)
             eng.phase_generators()
@@ -95,6 +132,7 @@ class CycleGANTrainer:
         if real_A.dtype == torch.uint8:
             return self._train_step_u8(real_A, real_B)
         eng = self._ensure_engine(real_A)
+        self._pool_step(eng)
         if self.sync.world_size == 1:
             if real_A.device.type == "cpu":
                 with self._enter():
@@ -116,6 +154,7 @@ class CycleGANTrainer:
         n, h, w, c = real_A.shape
         probe = torch.empty(n, c, h, w, device="meta")
         eng = self._ensure_engine(probe)
+        self._pool_step(eng)
         with self._enter():
             eng.stage_inputs_u8(real_A.contiguous(), real_B.contiguous())
             eng.train_step()
