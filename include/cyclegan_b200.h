@@ -104,6 +104,9 @@ int cgb_discriminator_forward(cgb_engine_t* e, int net, const float* x, float* l
 int cgb_set_inputs(cgb_engine_t* e, const float* real_A, const float* real_B, void* stream);
 int cgb_forward_cycle(cgb_engine_t* e, void* stream);              /* the six generator passes */
 int cgb_get_image(cgb_engine_t* e, int which, float* out, void* stream);
+/* the same image as uint8 interleaved RGB [batch][size][size][3]: u8 = clamp(rint((x + 1) * 127.5), 0, 255) -- the
+ * stand-in's to_uint8 (oracle/cyclegan_standin.py), inverse of cgb_stage_inputs_u8's normalisation */
+int cgb_get_image_u8(cgb_engine_t* e, int which, unsigned char* out, void* stream);
 /* forward + G-phase backward: grads_G = d loss_G / d(G_AB, G_BA); zeroes grads_G first */
 int cgb_phase_generators(cgb_engine_t* e, void* stream);
 /* D-phase forward/backward on real images and the pre-update fakes: grads_D; zeroes grads_D first */

@@ -221,6 +221,11 @@ def from_uint8(img_u8_hwc: torch.Tensor) -> torch.Tensor:
     return (img_u8_hwc.permute(0, 3, 1, 2).to(torch.float32) * (1.0 / 127.5) - 1.0).contiguous()
 
 
+def to_uint8(img: torch.Tensor) -> torch.Tensor:
+    """float [N, 3, H, W] in [-1, 1] -> uint8 interleaved RGB [N, H, W, 3]: clamp(round((x + 1) * 127.5), 0, 255)."""
+    return ((img.to(torch.float32) + 1.0) * 127.5).round().clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+
+
 def linear_decay_lr(base_lr: float, epoch: int, n_epochs: int = 100, n_epochs_decay: int = 100) -> float:
     """Constant for `n_epochs`, then linear decay to zero over `n_epochs_decay` (the canonical 'linear' policy):
     lr = base_lr * (1 - max(0, epoch + 1 - n_epochs) / (n_epochs_decay + 1)), epoch counted from 0."""

@@ -166,6 +166,10 @@ def test_uint8_inputs_match_float_inputs():
         tol = 5e-2 if k in ("loss_G_A", "loss_G_B", "loss_D_A", "loss_D_B") else 1e-2
         assert abs(lu[k] - lf[k]) / abs(lf[k]) < tol, (k, lu[k], lf[k])
         assert abs(lh[k] - lf[k]) / abs(lf[k]) < tol, (k, lh[k], lf[k])
+    # ... and back: uint8 read-out of a generated image equals the stand-in's to_uint8 of the fp32 read-out
+    fake = tr_u.engine.get_image("fake_B").cpu()
+    assert torch.equal(tr_u.engine.get_image_u8("fake_B").cpu(), ref.to_uint8(fake))
+    assert torch.equal(tr_u.engine.get_image_u8("real_A").cpu(), ref.to_uint8(ref.from_uint8(a8).to(torch.bfloat16).float()))
     real = tr_u.engine.get_image("real_A").cpu()
     assert float((real - ref.from_uint8(a8).to(torch.bfloat16).float()).abs().max()) == 0.0  # bit-exact bf16 image
 

@@ -49,6 +49,7 @@ SIGNATURES = {
     "cgb_set_inputs": (c_int, [_P, _P, _P, _P]),
     "cgb_forward_cycle": (c_int, [_P, _P]),
     "cgb_get_image": (c_int, [_P, c_int, _P, _P]),
+    "cgb_get_image_u8": (c_int, [_P, c_int, _P, _P]),
     "cgb_phase_generators": (c_int, [_P, _P]),
     "cgb_phase_discriminators": (c_int, [_P, _P]),
     "cgb_adam": (c_int, [_P, c_int, _P]),

@@ -183,6 +183,19 @@ int cgb_get_image(cgb_engine_t* e, int which, float* out, void* stream) {
   CGB_API_END
 }
 
+int cgb_get_image_u8(cgb_engine_t* e, int which, unsigned char* out, void* stream) {
+  CGB_API_BEGIN
+  CGB_CHECK(e && e->bound && which >= 0 && which < 10 && out, "bad argument / engine not bound");
+  CGB_CHECK(!e->infer_only, "inference-only engine: training entry points are unavailable");
+  if (which >= CGB_IMG_POOL_FAKE_B) {
+    CGB_CHECK(e->pool_size > 0, "the image pool is not enabled (cgb_engine_set_image_pool)");
+    nhwc_to_u8hwc(e->pool_din[which - CGB_IMG_POOL_FAKE_B], 3, out, S(stream));
+  } else {
+    nhwc_to_u8hwc(e->img[which], 3, out, S(stream));
+  }
+  CGB_API_END
+}
+
 int cgb_phase_generators(cgb_engine_t* e, void* stream) {
   CGB_API_BEGIN
   CGB_CHECK(e && e->bound, "engine not bound");

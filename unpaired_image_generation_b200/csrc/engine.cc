@@ -112,9 +112,10 @@ void cgb_engine::layout(Arena& A) {
     v.N = n;
     return v;
   };
-  // measured on B200 (batch 1: 5.39 ms unpaired vs 5.68 ms paired; batch 8: equal): the paired schedule does 20 %
-  // less kernel work but puts the identity passes on the critical chain, so it is opt-in (CGB_PAIR=1)
-  pair = std::getenv("CGB_PAIR") && std::atoi(std::getenv("CGB_PAIR")) != 0;
+  // The paired schedule does 20 % less kernel work but puts the identity passes on the critical chain.  Measured
+  // on B200 with the final kernels: batch 1: 4.74 ms paired vs 4.65 ms unpaired; batch 8: 25.7 ms paired vs 27.2 ms
+  // unpaired.  Default: paired from 4 image pairs per GPU up; CGB_PAIR=0 / 1 overrides.
+  pair = std::getenv("CGB_PAIR") ? std::atoi(std::getenv("CGB_PAIR")) != 0 : cfg.batch >= 4;
   if (pair) {
     reals3 = A.tensor(3 * N, S, S, 16, 3);
     pair_out[0] = A.tensor(2 * N, S, S, 16, 3);  // [fake_B; idt_A]

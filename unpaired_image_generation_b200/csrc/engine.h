@@ -249,7 +249,7 @@ struct cgb_engine {
   cgb::DisScratch ds[2];
   cgb::TensorDesc dxp_img[2], dx_D0[2];  // gradients w.r.t. the fake images (from the cycle passes / from D)
   cgb::TensorDesc xcol[4];               // im2col4 (7x7 taps x 4 channels -> 256 columns) of real_A, real_B, fake_B, fake_A
-  // paired schedule (switch CGB_PAIR=1, default off): the two passes that share a generator AND
+  // paired schedule (default: on from batch 4 up; CGB_PAIR=0 / 1 overrides): the two passes that share a generator AND
   // only need the real images -- fake_B = G_AB(real_A) with idt_A = G_AB(real_B), fake_A = G_BA(real_B) with
   // idt_B = G_BA(real_A) -- run as ONE pass of batch 2N.  [0] = G_AB pair, [1] = G_BA pair.
   bool pair = false;

@@ -1004,6 +1004,22 @@ __global__ void pool_exchange_kernel(DevTensor fake, DevTensor pool, const int* 
   }
 }
 
+// bf16 NHWC image (16 stored channels, C real) -> uint8 interleaved [N][H][W][C]: u8 = clamp(rint((x + 1) * 127.5))
+// (the inverse of u8hwc_to_nchw; the stand-in's to_uint8)
+__global__ void nhwc_to_u8hwc_kernel(DevTensor src, int C, unsigned char* __restrict__ dst) {
+  const long long total = (long long)src.N * src.H * src.W;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int w = idx % src.W;
+  const int h = (idx / src.W) % src.H;
+  const int n = idx / ((long long)src.W * src.H);
+  const bf16* p = src.p + n * src.sN + h * src.sH + w * src.sW;
+  for (int c = 0; c < C; ++c) {
+    const float v = __fmul_rn(__fadd_rn(__bfloat162float(p[c]), 1.f), 127.5f);
+    dst[idx * C + c] = (unsigned char)min(255, max(0, __float2int_rn(v)));
+  }
+}
+
 __global__ void set_float_kernel(float* dst, float value) { *dst = value; }
 
 // uint8 interleaved RGB [N][H][W][3] -> fp32 planar [N][3][H][W] in [-1, 1]: x = u8 / 127.5 - 1
@@ -1308,6 +1324,12 @@ void pool_exchange(const TensorDesc& fake, const TensorDesc& pool, const int* de
             "pool_exchange: shape mismatch");
   const long long total = (long long)fake.H * fake.W * (fake.C / 8);
   pool_exchange_kernel<<<blocks_for(total, 256), 256, 0, st>>>(dev(fake), dev(pool), dec, dev(d_in));
+  CGB_CUDA(cudaGetLastError());
+}
+
+void nhwc_to_u8hwc(const TensorDesc& src, int C, unsigned char* dst, cudaStream_t st) {
+  const long long total = (long long)src.N * src.H * src.W;
+  nhwc_to_u8hwc_kernel<<<blocks_for(total, 256), 256, 0, st>>>(dev(src), C, dst);
   CGB_CUDA(cudaGetLastError());
 }
 

@@ -79,6 +79,8 @@ void adam_step(float* p, const float* g, float* m, float* v, long long n, float 
 void pool_exchange(const TensorDesc& fake, const TensorDesc& pool, const int* dec, const TensorDesc& d_in, cudaStream_t st);
 // one-element store on the stream (graph- and stream-ordered scalar updates: the learning rate)
 void set_device_float(float* dst, float value, cudaStream_t st);
+// bf16 NHWC image -> uint8 interleaved [N][H][W][C], u8 = clamp(rint((x + 1) * 127.5), 0, 255)
+void nhwc_to_u8hwc(const TensorDesc& src, int C, unsigned char* dst, cudaStream_t st);
 // uint8 interleaved RGB [N][H][W][3] -> fp32 planar [N][3][H][W], x = u8 / 127.5 - 1
 void u8hwc_to_nchw(const unsigned char* src, int N, int H, int W, float* dst, cudaStream_t st);
 

@@ -209,6 +209,12 @@ class StepEngine:
         _lib.check(self.lib.cgb_get_image(self._h, IMAGE_IDS[name], _ptr(out), _stream()))
         return out
 
+    def get_image_u8(self, name: str) -> torch.Tensor:
+        """the image as uint8 interleaved RGB [N, H, W, 3] (stand-in: to_uint8)"""
+        out = torch.empty(self.batch, self.size, self.size, 3, dtype=torch.uint8, device=self.device)
+        _lib.check(self.lib.cgb_get_image_u8(self._h, IMAGE_IDS[name], _ptr(out), _stream()))
+        return out
+
     def phase_generators(self):
         _lib.check(self.lib.cgb_phase_generators(self._h, _stream()))
 
