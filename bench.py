@@ -313,7 +313,9 @@ def run_b200(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"CycleGAN {size}x{size} ResNet-9blk + 70x70 PatchGAN, batch {batch} per GPU, bf16 "
-                                   "storage / fp32 accumulate, full train step (BASELINE.json configs[1])",
+                                   "storage / fp32 accumulate, full train step (BASELINE.json "
+                                   + ("configs[1])" if (batch, size) == (1, 256) else
+                                      "configs[3] geometry)" if size == 512 else "configs[2] geometry)"),
                        "batch_per_gpu": batch, "global_batch": batch * world, "size": size,
                        "parallelism": f"dp{world}",
                        "l2": f"per-step working set {eng.workspace_bytes / 2**20:.0f} MiB >> 126 MB L2 (no explicit flush)"},
