@@ -302,7 +302,7 @@ def run_b200(args):
         }
         # ---- cpu_baseline: the stand-in on this box's host cores, bounded sample
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # rank 0 at N = 1 only (the other ranks would idle in the barrier)
             times, cores = time_standin(1, size, 2, 1)
             sec = min(times)
             cpu = {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": "port",
