@@ -5,10 +5,10 @@
  * public surface of the committed stand-in, oracle/cyclegan_standin.py:
  *   Generator.forward            (oracle/cyclegan_standin.py:144)  -> cgb_generator_forward
  *   Discriminator.forward        (oracle/cyclegan_standin.py:186)  -> cgb_discriminator_forward
- *   CycleGANTrainer.forward_only (oracle/cyclegan_standin.py:243)  -> cgb_forward_cycle + cgb_get_image
- *   CycleGANTrainer.train_step   (oracle/cyclegan_standin.py:303)  -> cgb_phase_generators, cgb_adam,
+ *   CycleGANTrainer.forward_only (oracle/cyclegan_standin.py:312)  -> cgb_forward_cycle + cgb_get_image
+ *   CycleGANTrainer.train_step   (oracle/cyclegan_standin.py:374)  -> cgb_phase_generators, cgb_adam,
  *                                                                     cgb_phase_discriminators, cgb_get_losses
- *   CycleGANTrainer.backward_only(oracle/cyclegan_standin.py:283)  -> the two phase calls without cgb_adam
+ *   CycleGANTrainer.backward_only(oracle/cyclegan_standin.py:352)  -> the two phase calls without cgb_adam
  *   module.state_dict()/load_state_dict()                          -> cgb_param_info + caller-owned flat buffers
  *
  * Conventions: every function returns 0 on success and a non-zero code on failure, in which case

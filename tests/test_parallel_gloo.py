@@ -1,5 +1,5 @@
 """world_size-2 gloo tests (CPU) of the data-parallel host logic: GradSync all-reduce + 1/world scale
-reproduces the single-process step on the concatenated batch (oracle/cyclegan_standin.py:283)."""
+reproduces the single-process step on the concatenated batch (oracle/cyclegan_standin.py:352)."""
 import os
 
 import pytest

@@ -1,6 +1,6 @@
 // The CycleGAN step engine: parameter inventory, HBM workspace layout, convolution plans and the
 // recorded launch programs for the generator / discriminator phases.
-// Mirrors CycleGANTrainer in the stand-in (oracle/cyclegan_standin.py:218-330).
+// Mirrors CycleGANTrainer in the stand-in (oracle/cyclegan_standin.py:278-400).
 #pragma once
 #include <deque>
 #include <functional>

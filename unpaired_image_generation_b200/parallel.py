@@ -5,7 +5,7 @@ sum-allreduce of the two flat gradient buffers (generators: 22.8 M floats, discr
 followed by a 1/world scale folded into the Adam kernel.  This module is device-agnostic on
 purpose: the same code runs over NCCL on B200s and over gloo in the CPU test-suite.
 Stand-in counterpart: a single-process step on the concatenated batch
-(oracle/cyclegan_standin.py:303 train_step) -- see tests/test_parallel_gloo.py.
+(oracle/cyclegan_standin.py:374 train_step) -- see tests/test_parallel_gloo.py.
 """
 from __future__ import annotations
 

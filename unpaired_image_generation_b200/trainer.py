@@ -1,4 +1,4 @@
-"""CycleGANTrainer with the stand-in's API (oracle/cyclegan_standin.py:218): same constructor
+"""CycleGANTrainer with the stand-in's API (oracle/cyclegan_standin.py:278): same constructor
 arguments, `train_step(real_A, real_B) -> dict`, `forward_only`, `backward_only`.  One process per
 GPU; with torch.distributed initialised the two flat gradient buffers are all-reduced on a side
 stream, overlapped with the discriminator phase."""
