@@ -142,3 +142,24 @@ def test_paired_schedule_workspace(monkeypatch):
         out[pair] = lib.cgb_workspace_bytes(h)
         lib.cgb_engine_destroy(h)
     assert 0.8 * out["0"] < out["1"] < 1.35 * out["0"], out
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """bench.py --impl reference: ONE JSON line on stdout with the contract's keys (the stand-in timed on the host)"""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1", "--size", "64"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-500:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    assert "workload" in d["config"] and "model" not in d["config"]
