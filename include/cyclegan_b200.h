@@ -68,7 +68,11 @@ int cgb_engine_create(const cgb_config_t* cfg, cgb_engine_t** out);
 /* flags: CGB_FLAG_INFERENCE = engine for Generator.forward / Discriminator.forward only (BASELINE.json configs[4],
  * the generator-only inference sweep): the workspace holds the packed weights and ONE forward pass, none of
  * the training passes; every training entry point fails with "inference-only engine". */
-enum { CGB_FLAG_INFERENCE = 1 };
+/*        CGB_FLAG_FP32_VALIDATE = the fp32 VALIDATION MODE of north_star ("1e-5 for an fp32 validation mode"): the
+ * same engine, programs and schedule with fp32 activations, fp64 accumulation and deterministic CUDA-core kernels
+ * (csrc/fp32_path.h); bit-identical run to run; about 30x slower than the bf16 product path.  It checks the
+ * orchestration against the fp32 stand-in (oracle/cyclegan_standin.py:374 train_step) below the bf16 noise floor. */
+enum { CGB_FLAG_INFERENCE = 1, CGB_FLAG_FP32_VALIDATE = 2 };
 int cgb_engine_create_ex(const cgb_config_t* cfg, int flags, cgb_engine_t** out);
 void cgb_engine_destroy(cgb_engine_t* e);
 int cgb_num_params(const cgb_engine_t* e, int net);                       /* tensors in a network */
@@ -92,7 +96,11 @@ int cgb_engine_bind(cgb_engine_t* e, float* params_G, float* grads_G, float* m_G
 /* re-derive the bf16 packed weights from the fp32 masters (after load_state_dict / Adam) */
 int cgb_refresh_weights(cgb_engine_t* e, int group, void* stream);
 int cgb_set_grad_scale(cgb_engine_t* e, float scale); /* 1/world_size for data parallel */
+/* Adam step counters (the t of the bias corrections), for checkpoint / resume: together with the four flat buffers
+ * of a group (params, exp_avg, exp_avg_sq; grads are scratch) they are the whole optimiser state
+ * (stand-in: torch.optim.Adam.state_dict(), oracle/cyclegan_standin.py:300). */
 int cgb_set_step_count(cgb_engine_t* e, int group, int step);
+int cgb_get_step_count(cgb_engine_t* e, int group, int* step_out);
 
 /* ---- modules -------------------------------------------------------------------------------------------- */
 /* x, y: fp32 NCHW [batch][3][size][size] device tensors */
@@ -133,6 +141,15 @@ enum { CGB_SEG_STEP = 0, CGB_SEG_G = 1, CGB_SEG_D = 2, CGB_SEG_ADAM_G = 3, CGB_S
                                  optimiser: grads_G and grads_D are complete afterwards (data parallel) */,
        CGB_NUM_SEGMENTS = 7 };
 int cgb_run_segment(cgb_engine_t* e, int segment, void* stream);
+/* Data parallel, gradient all-reduce overlapped with the backward pass: while CGB_SEG_STEP_NOOPT is still running,
+ * ranges of the flat gradient buffers become final bucket by bucket (discriminators first, then the generators from
+ * the head towards the stem; CGB_DP_BUCKETS, default 3 per generator).  Buckets are listed in the order they become
+ * ready.  cgb_wait_grad_bucket makes `stream` (the caller's communication stream) wait until bucket `index` of the
+ * most recently launched CGB_SEG_STEP_NOOPT is final -- call it AFTER cgb_run_segment -- then all-reduce
+ * grads[group][offset : offset + numel] on that stream.  The optimiser segments must wait for the collectives. */
+int cgb_num_grad_buckets(const cgb_engine_t* e);
+int cgb_grad_bucket_info(const cgb_engine_t* e, int index, int* group, long long* offset, long long* numel);
+int cgb_wait_grad_bucket(cgb_engine_t* e, int index, void* stream);
 /* copies the CGB_NUM_LOSSES loss values to host memory (synchronises the stream) */
 int cgb_get_losses_host(cgb_engine_t* e, float* losses_host, void* stream);
 /* end-to-end convenience: pinned/pageable HOST inputs in, losses out (H2D + step + D2H, synchronous) */
@@ -163,10 +180,16 @@ int cgb_conv_layer_test(int n, int h, int w, int cin, int cout, int k, int strid
                         int transposed, int act, const float* x, const float* weight, const float* bias,
                         const float* dy, float* y, float* dx, float* dw, float* db);
 /* InstanceNorm(+act, +residual) forward and backward on NCHW fp32 tensors through the bf16 NHWC kernels.
- * act: 0 none, 3 ReLU, 1 LeakyReLU.  out_halo > 0 also checks the reflect-halo writer (out is still NCHW
- * interior).  da: gradient w.r.t. out; dy_out: gradient w.r.t. y. */
+ * act: 0 none, 3 ReLU, 1 LeakyReLU.  The output is produced into a tensor with a 1-pixel reflect halo (exercising
+ * the halo writer); `out` receives its interior.  da: gradient w.r.t. out; dy_out: gradient w.r.t. y. */
 int cgb_instnorm_test(int n, int c, int h, int w, int act, const float* y, const float* residual, const float* da,
                       float* out, float* dy_out);
+/* The same two harnesses through the fp32 validation kernels (csrc/fp32_path.h). */
+int cgb_conv_layer_test_f32(int n, int h, int w, int cin, int cout, int k, int stride, int pad, int reflect,
+                            int transposed, int act, const float* x, const float* weight, const float* bias,
+                            const float* dy, float* y, float* dx, float* dw, float* db);
+int cgb_instnorm_test_f32(int n, int c, int h, int w, int act, const float* y, const float* residual, const float* da,
+                          float* out, float* dy_out);
 
 #ifdef __cplusplus
 }

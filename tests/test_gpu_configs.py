@@ -68,6 +68,21 @@ def test_train_step_512_vs_golden(large):
     _check_losses(step, case["losses_steps"][0])
 
 
+@pytest.mark.parametrize("case", ["fp32_256_b8", "fp32_512_b4"])
+def test_full_size_configs_losses_vs_golden(case):
+    """BASELINE.json configs[2] (256x256, batch 8 per GPU: paired schedule) and configs[3] (512x512, batch 4 per GPU)
+    at their FULL per-GPU sizes: step-0 losses against the stand-in (tests/golden/standin_golden_full.json)"""
+    _need_gpu()
+    with open(os.path.join(GOLD, "standin_golden_full.json")) as f:
+        g = json.load(f)["cases"][case]
+    tr, _ = _trainer()
+    real_A, real_B = ref.synthetic_pair(g["batch"], g["size"], seed=1234)
+    losses = tr.backward_only(real_A.cuda(), real_B.cuda())
+    _check_losses(losses, g["losses_step0"])
+    step = tr.train_step(real_A.cuda(), real_B.cuda())  # the merged (paired) step graph sees the same forward
+    _check_losses(step, g["losses_step0"])
+
+
 def test_batch2_256_vs_golden(large):
     """BASELINE.json configs[2] geometry: more than one pair per GPU"""
     _need_gpu()

@@ -127,12 +127,16 @@ def test_conv_is_exactly_linear_in_power_of_two_scaling():
     assert torch.equal(outs[1], outs[0] * 2)
 
 
-@pytest.mark.parametrize("act,residual", [(3, False), (1, False), (0, True)])
-def test_instance_norm_forward_backward(act, residual):
+# shapes: the small register-kernel case, then the shapes of the real step -- 1 x 64 x 256 x 256 (stem / up2 maps:
+# the cp.async streaming variants), 8 x 256 x 64 x 64 (residual stream at batch 8), C = 128 and C = 512 (31 x 31, ragged)
+@pytest.mark.parametrize("act,residual,shape", [
+    (3, False, (2, 64, 24)), (1, False, (2, 64, 24)), (0, True, (2, 64, 24)),
+    (3, False, (1, 64, 256)), (0, True, (8, 256, 64)), (3, False, (2, 128, 128)), (1, False, (1, 512, 31))])
+def test_instance_norm_forward_backward(act, residual, shape):
     _need_gpu()
     lib = _lib.load()
     g = torch.Generator().manual_seed(5)
-    n, c, h = 2, 64, 24
+    n, c, h = shape
     y = bf(torch.randn(n, c, h, h, generator=g) * 2 + 0.5).requires_grad_(True)
     r = bf(torch.randn(n, c, h, h, generator=g)) if residual else None
     da = bf(torch.randn(n, c, h, h, generator=g))
@@ -308,6 +312,76 @@ def test_adam_matches_torch_on_identical_gradients():
         assert rel(eng.params[grp], ts[grp]) < 1e-6
         err = float((eng.params[grp].cpu() - ts[grp].detach()).abs().max())
         assert err < 1e-6, err
+
+
+def test_full_step_256_images_gradients_weights_vs_standin():
+    """BASELINE.json configs[1] at full size against the LIVE stand-in: the six images within the bf16 noise floor,
+    every weight gradient by direction and norm against the bf16-emulated stand-in, weights after one Adam step
+    within the north_star tolerance of 2e-2."""
+    _need_gpu()
+    torch.set_num_threads(os.cpu_count() or 1)
+    onets = ref.build_models(seed=0)
+    real_A, real_B = ref.synthetic_pair(1, 256, seed=1234)
+    mods = (cgb.Generator(), cgb.Generator(), cgb.Discriminator(), cgb.Discriminator())
+    for m, o in zip(mods, onets):
+        m.load_state_dict(o.state_dict())
+    tr = cgb.CycleGANTrainer(*mods)
+    imgs = tr.forward_only(real_A.cuda(), real_B.cuda())
+    f32 = ref.CycleGANTrainer(*onets).forward_only(real_A, real_B)
+    emu = ref.CycleGANTrainer(*ref.build_models(seed=0), emulate_bf16=True).forward_only(real_A, real_B)
+    for k in imgs:
+        floor = rel(emu[k], f32[k])
+        assert rel(imgs[k], f32[k]) < 1.5 * floor + 1e-3, (k, rel(imgs[k], f32[k]), floor)
+    tr.backward_only(real_A.cuda(), real_B.cuda())
+    enets = ref.build_models(seed=0)
+    ref.CycleGANTrainer(*enets, emulate_bf16=True).backward_only(real_A, real_B)
+    dead = set(ref.dead_bias_names_generator() + ref.dead_bias_names_discriminator())
+    for name, enet in zip(("G_AB", "G_BA", "D_A", "D_B"), enets):
+        grads = tr.grads(name)
+        for n, p in enet.named_parameters():
+            if n in dead:
+                continue
+            a, b = grads[n].detach().float().cpu(), p.grad
+            cos = float((a * b).sum() / (a.norm() * b.norm() + 1e-30))
+            assert cos > 0.9, (name, n, cos)
+            if a.numel() >= 1000:
+                assert 0.85 < float(a.norm() / b.norm()) < 1.15, (name, n, float(a.norm() / b.norm()))
+    otr = ref.CycleGANTrainer(*onets)
+    otr.train_step(real_A, real_B)
+    tr.train_step(real_A.cuda(), real_B.cuda())
+    for m, o in zip(mods, onets):
+        for (n, p), (_, q) in zip(m.named_parameters(), o.named_parameters()):
+            if n in dead:
+                continue
+            if n.endswith("bias"):
+                assert float((p.detach().cpu() - q.detach()).abs().max()) <= 2 * 2e-4 + 1e-7, n
+            else:
+                assert rel(p, q) < 2e-2, (n, rel(p, q))
+
+
+def test_private_inference_engines_follow_the_weights():
+    """Generator.forward at a shape other than the trainer's runs on a private inference engine; it must see the
+    weights of the latest optimiser step, not those of the step it was created at"""
+    _need_gpu()
+    real_A, real_B = ref.synthetic_pair(1, 64, seed=5)
+    mods = (cgb.Generator(seed=1), cgb.Generator(seed=2), cgb.Discriminator(seed=3), cgb.Discriminator(seed=4))
+    tr = cgb.CycleGANTrainer(*mods)
+    x2 = ref.synthetic_pair(2, 64, seed=6)[0].cuda()
+    tr.train_step(real_A.cuda(), real_B.cuda())
+    y_before = mods[0](x2).clone()
+    for _ in range(2):
+        tr.train_step(real_A.cuda(), real_B.cuda())
+    y_after = mods[0](x2).clone()
+    fresh = cgb.Generator()
+    fresh.load_state_dict(mods[0].state_dict())
+    y_fresh = fresh(x2)
+    assert rel(y_after, y_fresh) < 1e-6, rel(y_after, y_fresh)
+    assert rel(y_before, y_fresh) > 1e-3  # two Adam steps at lr 2e-4 move the output visibly
+    # an in-place write through parameters() is seen as well
+    with torch.no_grad():
+        next(iter(mods[0].parameters())).mul_(0.5)
+    fresh.load_state_dict(mods[0].state_dict())
+    assert rel(mods[0](x2), fresh(x2)) < 1e-6
 
 
 def test_losses_vs_fp32_golden_at_256(golden):

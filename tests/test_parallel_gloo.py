@@ -23,10 +23,15 @@ def _worker(rank, world, port, tmp):
         from oracle import cyclegan_standin as ref
         sync = GradSync()
         assert sync.world_size == world and sync.rank == rank and sync.grad_scale == 1.0 / world
-        # 1. plain all-reduce of a flat buffer, bucketed
+        # 1. all-reduce of a flat buffer range by range (the trainer reduces each gradient bucket as the step graph
+        #    announces it), and broadcast of rank 0's state to ranks that were initialised differently
         flat = torch.arange(1000, dtype=torch.float32) * (rank + 1)
-        GradSync(bucket_elems=256).all_reduce_(flat)
+        for off, n in ((700, 300), (256, 444), (0, 256)):  # buckets arrive head-first, ranges are disjoint
+            sync.all_reduce_(flat[off:off + n])
         assert torch.equal(flat, torch.arange(1000, dtype=torch.float32) * 3)
+        state = torch.full((17,), float(rank + 5))  # "different seeds": every rank starts from its own values
+        sync.broadcast_(state)
+        assert torch.equal(state, torch.full((17,), 5.0))
         # 2. each rank: backward on its shard of a global batch of 2
         real_A, real_B = ref.synthetic_pair(2, 32, seed=7)
         sl = sync.shard_batch(2)

@@ -40,6 +40,7 @@ SIGNATURES = {
     "cgb_refresh_weights": (c_int, [_P, c_int, _P]),
     "cgb_set_grad_scale": (c_int, [_P, c_float]),
     "cgb_set_step_count": (c_int, [_P, c_int, c_int]),
+    "cgb_get_step_count": (c_int, [_P, c_int, POINTER(c_int)]),
     "cgb_set_lr": (c_int, [_P, c_int, c_float, _P]),
     "cgb_engine_set_image_pool": (c_int, [_P, c_int]),
     "cgb_set_pool_decisions": (c_int, [_P, _P, _P]),
@@ -56,6 +57,9 @@ SIGNATURES = {
     "cgb_train_step": (c_int, [_P, _P]),
     "cgb_stage_inputs": (c_int, [_P, _P, _P, _P]),
     "cgb_run_segment": (c_int, [_P, c_int, _P]),
+    "cgb_num_grad_buckets": (c_int, [_P]),
+    "cgb_grad_bucket_info": (c_int, [_P, c_int, POINTER(c_int), POINTER(c_longlong), POINTER(c_longlong)]),
+    "cgb_wait_grad_bucket": (c_int, [_P, c_int, _P]),
     "cgb_get_losses_host": (c_int, [_P, POINTER(c_float), _P]),
     "cgb_train_step_host": (c_int, [_P, _P, _P, POINTER(c_float), _P]),
     "cgb_launches_per_step": (c_longlong, [_P]),
@@ -64,6 +68,8 @@ SIGNATURES = {
     "cgb_profile_timeline": (c_int, [_P, _P, c_char_p, c_int]),
     "cgb_conv_layer_test": (c_int, [c_int] * 11 + [_P] * 8),
     "cgb_instnorm_test": (c_int, [c_int] * 5 + [_P] * 5),
+    "cgb_conv_layer_test_f32": (c_int, [c_int] * 11 + [_P] * 8),
+    "cgb_instnorm_test_f32": (c_int, [c_int] * 5 + [_P] * 5),
 }
 
 _lib = None

@@ -42,6 +42,7 @@ int cgb_engine_create_ex(const cgb_config_t* cfg, int flags, cgb_engine_t** out)
   cgb_engine* e = new cgb_engine();
   e->cfg = *cfg;
   e->infer_only = (flags & CGB_FLAG_INFERENCE) != 0;
+  e->fp32 = (flags & CGB_FLAG_FP32_VALIDATE) != 0;
   e->build_inventory();
   Arena A;
   e->layout(A);
@@ -130,6 +131,14 @@ int cgb_set_step_count(cgb_engine_t* e, int group, int step) {
   CGB_API_BEGIN
   CGB_CHECK(e && e->bound && group >= 0 && group < 2, "bad argument / engine not bound");
   CGB_CUDA(cudaMemcpy(e->adam_step[group], &step, sizeof(int), cudaMemcpyHostToDevice));
+  CGB_API_END
+}
+
+int cgb_get_step_count(cgb_engine_t* e, int group, int* step_out) {
+  CGB_API_BEGIN
+  CGB_CHECK(e && e->bound && group >= 0 && group < 2 && step_out, "bad argument / engine not bound");
+  CGB_CUDA(cudaDeviceSynchronize());
+  CGB_CUDA(cudaMemcpy(step_out, e->adam_step[group], sizeof(int), cudaMemcpyDeviceToHost));
   CGB_API_END
 }
 
@@ -234,6 +243,25 @@ int cgb_run_segment(cgb_engine_t* e, int segment, void* stream) {
   CGB_CHECK(e && e->bound && segment >= 0 && segment < CGB_NUM_SEGMENTS, "bad argument / engine not bound");
   CGB_CHECK(!e->infer_only, "inference-only engine: training entry points are unavailable");
   e->run_segment(segment, S(stream));
+  CGB_API_END
+}
+
+int cgb_num_grad_buckets(const cgb_engine_t* e) { return (e && e->bound) ? (int)e->grad_buckets.size() : -1; }
+
+int cgb_grad_bucket_info(const cgb_engine_t* e, int index, int* group, long long* offset, long long* numel) {
+  CGB_API_BEGIN
+  CGB_CHECK(e && e->bound && index >= 0 && index < (int)e->grad_buckets.size() && group && offset && numel,
+            "bad argument / engine not bound");
+  *group = e->grad_buckets[index].group;
+  *offset = e->grad_buckets[index].offset;
+  *numel = e->grad_buckets[index].numel;
+  CGB_API_END
+}
+
+int cgb_wait_grad_bucket(cgb_engine_t* e, int index, void* stream) {
+  CGB_API_BEGIN
+  CGB_CHECK(e && e->bound && index >= 0 && index < (int)e->grad_buckets.size(), "bad argument / engine not bound");
+  CGB_CUDA(cudaStreamWaitEvent(S(stream), e->grad_events[index], 0));
   CGB_API_END
 }
 
@@ -375,10 +403,10 @@ struct Scratch {
     ptrs.push_back(p);
     return p;
   }
-  TensorDesc tensor(int N, int H, int W, int C, int halo) {
+  TensorDesc tensor(int N, int H, int W, int C, int halo, int esz = 2) {
     TensorDesc t;
-    t.N = N; t.H = H; t.W = W; t.C = C; t.halo = halo;
-    t.ptr = static_cast<bf16*>(alloc((size_t)t.elems() * sizeof(bf16)));
+    t.N = N; t.H = H; t.W = W; t.C = C; t.halo = halo; t.esz = esz;
+    t.ptr = static_cast<bf16*>(alloc(t.bytes()));
     return t;
   }
 };
@@ -546,6 +574,105 @@ int cgb_instnorm_test(int n, int c, int h, int w, int act, const float* y, const
     g.g1 = &DA;
     in_bwd_reduce(Y, stats, g, act, nullptr, bstats, 0);
     in_bwd_apply(Y, stats, bstats, g, act, DY, 0);
+    nhwc_to_nchw(DY, c, dy_out, 0);
+  }
+  CGB_CUDA(cudaDeviceSynchronize());
+  CGB_API_END
+}
+
+int cgb_conv_layer_test_f32(int n, int h, int w, int cin, int cout, int k, int stride, int pad, int reflect,
+                            int transposed, int act, const float* x, const float* weight, const float* bias,
+                            const float* dy, float* y, float* dx, float* dw, float* db) {
+  CGB_API_BEGIN
+  CGB_CHECK(x && weight, "x and weight are required");
+  ConvSpec s;
+  s.Cin = cin; s.Cout = cout;
+  s.CinS = cin % 64 == 0 ? cin : 16;
+  s.CoutS = cout % 64 == 0 ? cout : 16;
+  s.k = k; s.stride = stride; s.pad = pad; s.reflect = reflect != 0; s.transposed = transposed != 0;
+  CGB_CHECK(cin % 64 == 0 || cin <= 16, "cin must be a multiple of 64 or <= 16");
+  CGB_CHECK(cout % 64 == 0 || cout <= 16, "cout must be a multiple of 64 or <= 16");
+  const int T = k * k, ho = out_extent(s, h), wo = out_extent(s, w);
+  Scratch sc;
+  const int halo = s.reflect ? pad : 0;
+  TensorDesc X = sc.tensor(n, h, w, s.CinS, halo, 4);
+  TensorDesc Y = sc.tensor(n, ho, wo, s.CoutS, 0, 4);
+  nchw_to_nhwc(x, cin, X, 0);
+  const size_t wn = (size_t)cout * T * cin;
+  std::vector<float> wh(wn);
+  CGB_CUDA(cudaMemcpy(wh.data(), weight, wn * sizeof(float), cudaMemcpyDeviceToHost));
+  std::vector<float> wm = to_master(wh, cout, cin, k, s.transposed);
+  float* d_master = static_cast<float*>(sc.alloc(wn * sizeof(float)));
+  CGB_CUDA(cudaMemcpy(d_master, wm.data(), wn * sizeof(float), cudaMemcpyHostToDevice));
+  f32::conv_fprop(s, X, d_master, bias, act, Y, 0);
+  if (y) nhwc_to_nchw(Y, cout, y, 0);
+  if (dy) {
+    TensorDesc DY = sc.tensor(n, ho, wo, s.CoutS, 0, 4);
+    nchw_to_nhwc(dy, cout, DY, 0);
+    if (dx) {
+      TensorDesc DX = sc.tensor(n, h + 2 * halo, w + 2 * halo, s.CinS, 0, 4);
+      f32::conv_dgrad(s, DY, d_master, DX, 0);
+      if (halo == 0) {
+        nhwc_to_nchw(DX, cin, dx, 0);
+      } else {  // fold the padded-domain gradient on the host (the engine folds it inside the InstanceNorm backward)
+        std::vector<float> hb((size_t)DX.elems());
+        CGB_CUDA(cudaMemcpy(hb.data(), DX.ptr, hb.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        std::vector<double> out((size_t)n * cin * h * w, 0.0);
+        const int HP = h + 2 * halo, WP = w + 2 * halo;
+        auto refl = [](int i, int nn) { if (i < 0) i = -i; if (i >= nn) i = 2 * (nn - 1) - i; return i; };
+        for (int b = 0; b < n; ++b)
+          for (int hp = 0; hp < HP; ++hp)
+            for (int wp = 0; wp < WP; ++wp) {
+              const int hs = refl(hp - halo, h), ws = refl(wp - halo, w);
+              for (int c = 0; c < cin; ++c)
+                out[(((size_t)b * cin + c) * h + hs) * w + ws] += hb[(((size_t)b * HP + hp) * WP + wp) * s.CinS + c];
+            }
+        std::vector<float> outf(out.begin(), out.end());
+        CGB_CUDA(cudaMemcpy(dx, outf.data(), outf.size() * sizeof(float), cudaMemcpyHostToDevice));
+      }
+    }
+    if (dw) {
+      float* g = static_cast<float*>(sc.alloc(wn * sizeof(float)));
+      f32::conv_wgrad(s, X, DY, g, 0);
+      std::vector<float> gm(wn), gt(wn);
+      CGB_CUDA(cudaMemcpy(gm.data(), g, wn * sizeof(float), cudaMemcpyDeviceToHost));
+      for (int co = 0; co < cout; ++co)
+        for (int t = 0; t < T; ++t)
+          for (int ci = 0; ci < cin; ++ci) {
+            const size_t dst = s.transposed ? ((size_t)ci * cout + co) * T + t : ((size_t)co * cin + ci) * T + t;
+            gt[dst] = gm[((size_t)co * T + t) * cin + ci];
+          }
+      CGB_CUDA(cudaMemcpy(dw, gt.data(), wn * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    if (db) f32::bias_grad(DY, cout, db, 0);
+  }
+  CGB_CUDA(cudaDeviceSynchronize());
+  CGB_API_END
+}
+
+int cgb_instnorm_test_f32(int n, int c, int h, int w, int act, const float* y, const float* residual, const float* da,
+                          float* out, float* dy_out) {
+  CGB_API_BEGIN
+  CGB_CHECK(y && out, "y and out are required");
+  Scratch sc;
+  TensorDesc Y = sc.tensor(n, h, w, c, 0, 4);
+  TensorDesc O = sc.tensor(n, h, w, c, 1, 4);
+  float2* stats = static_cast<float2*>(sc.alloc((size_t)n * c * sizeof(float2)));
+  nchw_to_nhwc(y, c, Y, 0);
+  TensorDesc R;
+  if (residual) {
+    R = sc.tensor(n, h, w, c, 1, 4);
+    nchw_to_nhwc(residual, c, R, 0);
+  }
+  f32::in_forward(Y, stats, act, residual ? &R : nullptr, O, 0);
+  nhwc_to_nchw(O, c, out, 0);
+  if (da && dy_out) {
+    TensorDesc DA = sc.tensor(n, h, w, c, 0, 4);
+    TensorDesc DY = sc.tensor(n, h, w, c, 0, 4);
+    nchw_to_nhwc(da, c, DA, 0);
+    GradSrc g;
+    g.g1 = &DA;
+    f32::in_backward(Y, stats, g, act, nullptr, DY, 0);
     nhwc_to_nchw(DY, c, dy_out, 0);
   }
   CGB_CUDA(cudaDeviceSynchronize());

@@ -18,11 +18,23 @@ struct TensorDesc {
   bf16* ptr = nullptr;  // storage base: [N][H + 2*halo][W + 2*halo][C]
   int N = 0, H = 0, W = 0, C = 0;
   int halo = 0;
+  int esz = 2;          // bytes per element: 2 = bf16 (the product path), 4 = fp32 (validation mode, fp32_path.h);
+                        // strides below stay in ELEMENTS, `ptr` keeps its bf16* type and is re-cast by the fp32 kernels
   long long sW() const { return C; }
   long long sH() const { return (long long)(W + 2 * halo) * C; }
   long long sN() const { return (long long)(H + 2 * halo) * sH(); }
   long long elems() const { return (long long)N * sN(); }
-  bf16* interior() const { return ptr + halo * sH() + halo * sW(); }
+  // address of element offset `off` from the storage base (scaled by the element size)
+  bf16* at(long long off) const { return reinterpret_cast<bf16*>(reinterpret_cast<char*>(ptr) + off * esz); }
+  bf16* interior() const { return at(halo * sH() + halo * sW()); }
+  size_t bytes() const { return (size_t)elems() * esz; }
+  // view of n consecutive images starting at image `first`
+  TensorDesc images(int first, int n) const {
+    TensorDesc v = *this;
+    v.ptr = at((long long)first * sN());
+    v.N = n;
+    return v;
+  }
 };
 
 struct ConvSpec {

@@ -32,6 +32,7 @@ cgb_engine::~cgb_engine() {
   for (cudaEvent_t ev : events) cudaEventDestroy(ev);
   for (auto& v : seg_events)
     for (cudaEvent_t ev : v) cudaEventDestroy(ev);
+  for (cudaEvent_t ev : grad_events) cudaEventDestroy(ev);
   for (int l = 1; l < kLanes; ++l)
     if (lane_streams[l]) cudaStreamDestroy(lane_streams[l]);
   if (meta) cudaFree(meta);
@@ -105,17 +106,18 @@ void cgb_engine::layout(Arena& A) {
   // module-forward pass; every training tensor is allocated with batch 0
   const int N = infer_only ? 0 : cfg.batch, S = cfg.size, nb = cfg.n_blocks;
   const int H2 = S / 2, H4 = S / 4, H8 = S / 8;
+  A.esz = fp32 ? 4 : 2;
   for (int g = 0; g < 2; ++g) pack[g] = static_cast<bf16*>(A.alloc((size_t)pack_elems[g] * sizeof(bf16)));
-  auto images = [](const TensorDesc& t, int first, int n) {  // view of n consecutive images
-    TensorDesc v = t;
-    v.ptr = t.ptr + (long long)first * t.sN();
-    v.N = n;
-    return v;
-  };
+  auto images = [](const TensorDesc& t, int first, int n) { return t.images(first, n); };
   // The paired schedule does 20 % less kernel work but puts the identity passes on the critical chain.  Measured
   // on B200 with the final kernels: batch 1: 4.74 ms paired vs 4.65 ms unpaired; batch 8: 25.7 ms paired vs 27.2 ms
   // unpaired.  Default: paired from 4 image pairs per GPU up; CGB_PAIR=0 / 1 overrides.
   pair = std::getenv("CGB_PAIR") ? std::atoi(std::getenv("CGB_PAIR")) != 0 : cfg.batch >= 4;
+  if (fp32) pair = false;  // validation mode: one pass per image set, one gradient buffer per pass kind
+  if (fp32 && !infer_only) {
+    for (int k = 0; k < 3; ++k) gslot[0][k] = static_cast<float*>(A.alloc((size_t)group_numel[0] * sizeof(float)));
+    for (int k = 0; k < 2; ++k) gslot[1][k] = static_cast<float*>(A.alloc((size_t)group_numel[1] * sizeof(float)));
+  }
   if (pair) {
     reals3 = A.tensor(3 * N, S, S, 16, 3);
     pair_out[0] = A.tensor(2 * N, S, S, 16, 3);  // [fake_B; idt_A]
@@ -400,6 +402,16 @@ void cgb_engine::record_programs() {
   auto add_fprop = [E](Program& pr, double* fl, const LayerParam& L, const TensorDesc& x, const TensorDesc& y,
                        int act, float2* stats) {
     const float* bias = L.has_in ? nullptr : E->P[L.group] + L.b_off;
+    if (E->fp32) {
+      const ConvSpec sp = L.spec;
+      const float* w = E->P[L.group] + L.w_off;
+      const double f = 2.0 * x.N * (sp.transposed ? (double)x.H * x.W : (double)y.H * y.W) * sp.Cout * sp.Cin * sp.taps();
+      pr.cur_name = "fprop(fp32) " + L.name;
+      pr.add([sp, x, w, bias, act, y](cudaStream_t st) { f32::conv_fprop(sp, x, w, bias, act, y, st); }, 1, kOpIgemm, f);
+      pr.cur_name.clear();
+      *fl += f;
+      return;
+    }
     IgemmPlan p = plan_fprop(L.spec, x, E->pack[L.group] + L.wf_off, y, bias, act, E->sm_count);
     p.args.stats = reinterpret_cast<float*>(stats);
     p.args.kiters = static_cast<const KIter*>(E->meta_upload(p.kiters.data(), p.kiters.size() * sizeof(KIter)));
@@ -411,6 +423,16 @@ void cgb_engine::record_programs() {
     *fl += p.flops;
   };
   auto add_dgrad = [E](Program& pr, double* fl, const LayerParam& L, const TensorDesc& dy, const TensorDesc& dx) {
+    if (E->fp32) {
+      const ConvSpec sp = L.spec;
+      const float* w = E->P[L.group] + L.w_off;
+      const double f = 2.0 * dy.N * (sp.transposed ? (double)dx.H * dx.W : (double)dy.H * dy.W) * sp.Cout * sp.Cin * sp.taps();
+      pr.cur_name = "dgrad(fp32) " + L.name;
+      pr.add([sp, dy, w, dx](cudaStream_t st) { f32::conv_dgrad(sp, dy, w, dx, st); }, 1, kOpIgemm, f);
+      pr.cur_name.clear();
+      *fl += f;
+      return;
+    }
     IgemmPlan p = plan_dgrad(L.spec, dy, E->pack[L.group] + L.wt_off, dx, E->sm_count);
     p.args.kiters = static_cast<const KIter*>(E->meta_upload(p.kiters.data(), p.kiters.size() * sizeof(KIter)));
     E->igemm_plans.push_back(p);
@@ -420,9 +442,19 @@ void cgb_engine::record_programs() {
     pr.cur_name.clear();
     *fl += p.flops;
   };
+  // gbase: the flat gradient buffer of the layer's group this pass writes to (cgb_engine::grad_base)
   auto add_wgrad_on_lane = [E](Program& pr, double* fl, const LayerParam& L, const TensorDesc& x, const TensorDesc& dy,
-                               bf16* colbuf, size_t colbuf_elems, const TensorDesc* precol) {
-    float* g = E->G[L.group] + L.w_off;
+                               bf16* colbuf, size_t colbuf_elems, const TensorDesc* precol, float* gbase) {
+    float* g = gbase + L.w_off;
+    if (E->fp32) {
+      const ConvSpec sp = L.spec;
+      const double f = 2.0 * x.N * (sp.transposed ? (double)x.H * x.W : (double)dy.H * dy.W) * sp.Cout * sp.Cin * sp.taps();
+      pr.cur_name = "wgrad(fp32) " + L.name;
+      pr.add([sp, x, dy, g](cudaStream_t st) { f32::conv_wgrad(sp, x, dy, g, st); }, 1, kOpWgradTc, f);
+      pr.cur_name.clear();
+      *fl += f;
+      return;
+    }
     if (tc_supports_wgrad(L.spec)) {
       WgradPlan p = plan_wgrad(L.spec, x, dy, g, E->sm_count);
       p.args.taps = static_cast<const WTap*>(E->meta_upload(p.taps.data(), p.taps.size() * sizeof(WTap)));
@@ -443,13 +475,22 @@ void cgb_engine::record_programs() {
       E->small_wgrad_plans.push_back(p);
       const SmallWgradPlan* pp = &E->small_wgrad_plans.back();
       pr.cur_name = "wgrad(im2col) " + L.name;
-      pr.add([pp](cudaStream_t st) { run(*pp, st); }, 2, kOpWgradDirect, p.flops);
+      pr.add([pp](cudaStream_t st) { run(*pp, st); }, 2, kOpWgradSmall, p.flops);
       pr.cur_name.clear();
       *fl += p.flops;
     }
   };
-  auto add_norm = [](Program& pr, const TensorDesc& y, float2* stats, int act, const TensorDesc* residual,
-                     const TensorDesc& out) {
+  auto add_norm = [E](Program& pr, const TensorDesc& y, float2* stats, int act, const TensorDesc* residual,
+                      const TensorDesc& out) {
+    if (E->fp32) {  // statistics (mean, rstd) + apply in one deterministic kernel
+      pr.cur_name = "in_forward(fp32) C" + std::to_string(y.C) + " " + std::to_string(y.H) + "x" + std::to_string(y.W);
+      const bool has_res = residual != nullptr;
+      const TensorDesc r = has_res ? *residual : TensorDesc();
+      pr.add([y, stats, act, has_res, r, out](cudaStream_t st) { f32::in_forward(y, stats, act, has_res ? &r : nullptr, out, st); },
+             1, kOpNorm);
+      pr.cur_name.clear();
+      return;
+    }
     // statistics were accumulated by the producing conv's epilogue
     pr.cur_name = "in_apply C" + std::to_string(y.C) + " " + std::to_string(y.H) + "x" + std::to_string(y.W) +
                   " halo" + std::to_string(out.halo) + (residual ? " +res" : "");
@@ -462,8 +503,15 @@ void cgb_engine::record_programs() {
     pr.cur_name.clear();
   };
   // InstanceNorm + activation backward; da_store (engine-owned tensor) receives the assembled gradient
-  auto add_in_bwd_raw = [](Program& pr, const TensorDesc& y, const float2* stats, float2* bstats, GradSrc g, int act,
-                           const TensorDesc* da_store, const TensorDesc& dy) {
+  auto add_in_bwd_raw = [E](Program& pr, const TensorDesc& y, const float2* stats, float2* bstats, GradSrc g, int act,
+                            const TensorDesc* da_store, const TensorDesc& dy) {
+    if (E->fp32) {
+      pr.cur_name = "in_backward(fp32) C" + std::to_string(y.C) + " " + std::to_string(y.H) + "x" + std::to_string(y.W);
+      pr.add([y, stats, g, act, da_store, dy](cudaStream_t st) { f32::in_backward(y, stats, g, act, da_store, dy, st); }, 1,
+             kOpNorm);
+      pr.cur_name.clear();
+      return;
+    }
     const std::string shape = " C" + std::to_string(y.C) + " " + std::to_string(y.H) + "x" + std::to_string(y.W) +
                               (g.g1 ? " g1" : "") + (g.g2 ? " g2fold" + std::to_string(g.fold) : "") +
                               (da_store ? " +da" : "");
@@ -497,7 +545,7 @@ void cgb_engine::record_programs() {
     float2* st = P.stats;
     pr.add([st, bytes = P.stats_bytes](cudaStream_t s) { CGB_CUDA(cudaMemsetAsync(st, 0, bytes, s)); }, 0, kOpMemset);
     static const bool stem_gemm = std::getenv("CGB_STEM_GEMM") != nullptr;
-    if (xcol_in && stem_gemm) {
+    if (xcol_in && stem_gemm && !E->fp32) {
       // stem as a plain GEMM over the im2col4 matrix: K = 256 (49 taps x 4 channels, zero padded); superseded by the
       // 16-channel patch-resident conv (the im2col4 matrix still feeds the stem weight gradient)
       LayerParam Lx = L[0];
@@ -543,9 +591,10 @@ void cgb_engine::record_programs() {
   // second half by the L1 term against target2.
   auto emit_gen_backward = [&](Program& pr, double* fl, GenPass& P, GenScratch& S, const TensorDesc* target,
                                float l1_scale, int loss_slot, GradSrc gsrc, const TensorDesc* dxp_img_out,
-                               const TensorDesc* target2 = nullptr, float l1_scale2 = 0.f, int loss_slot2 = -1) {
+                               const TensorDesc* target2 = nullptr, float l1_scale2 = 0.f, int loss_slot2 = -1,
+                               const std::function<void(Program&, int)>* after_wgrad = nullptr) {
     const std::vector<LayerParam>& L = E->layers[P.net];
-    float* Gg = E->G[CGB_GROUP_G];
+    float* Gg = E->grad_base(CGB_GROUP_G, P.gslot);
     float2* st = P.stats;
     float2* bs = P.bstats;
     const int main_lane = pr.cur_lane, wlane = pr.cur_lane + kPassLanes;
@@ -555,8 +604,11 @@ void cgb_engine::record_programs() {
                          bf16* colbuf, size_t colbuf_elems, const TensorDesc* precol = nullptr) {
       pr_.dep(main_lane, wlane);
       pr_.cur_lane = wlane;
-      add_wgrad_on_lane(pr_, fl_, Lp, x, dy, colbuf, colbuf_elems, precol);
+      add_wgrad_on_lane(pr_, fl_, Lp, x, dy, colbuf, colbuf_elems, precol, Gg);
       wgrad_done.push_back(pr_.record(wlane));
+      // data-parallel hook (still on the weight-gradient lane): this layer's gradient is final once the other passes
+      // of the same generator are done too -- the callback adds those waits and the bucket's external event
+      if (after_wgrad) (*after_wgrad)(pr_, (int)(&Lp - L.data()));
       pr_.cur_lane = main_lane;
     };
     // A layer's dy buffer is read by its weight gradient on the side lane.  Consecutive layers never share a dy
@@ -571,12 +623,7 @@ void cgb_engine::record_programs() {
     const LayerParam& head = L[5 + 2 * nb];
     if (target2) {
       const int half = P.out.N / 2;
-      auto images = [](const TensorDesc& t, int first, int n) {
-        TensorDesc v = t;
-        v.ptr = t.ptr + (long long)first * t.sN();
-        v.N = n;
-        return v;
-      };
+      auto images = [](const TensorDesc& t, int first, int n) { return t.images(first, n); };
       const TensorDesc outA = images(P.out, 0, half), outB = images(P.out, half, half);
       const TensorDesc dpreA = images(S.dpre_head, 0, half), dpreB = images(S.dpre_head, half, half);
       const TensorDesc tg2 = *target2;
@@ -674,7 +721,7 @@ void cgb_engine::record_programs() {
   auto emit_dis_backward = [&](Program& pr, double* fl, DisPass& D, DisScratch& S, float target, float w,
                                int loss_slot, bool weight_grads, const TensorDesc* dx_img_out) {
     const std::vector<LayerParam>& L = E->layers[D.net];
-    float* Gd = E->G[CGB_GROUP_D];
+    float* Gd = E->grad_base(CGB_GROUP_D, D.gslot);
     float2* st = D.stats;
     float2* bs = D.bstats;
     const int main_lane = pr.cur_lane, wlane = pr.cur_lane + kPassLanes;
@@ -682,7 +729,7 @@ void cgb_engine::record_programs() {
                          bf16* colbuf, size_t colbuf_elems, const TensorDesc* precol = nullptr) {
       pr_.dep(main_lane, wlane);
       pr_.cur_lane = wlane;
-      add_wgrad_on_lane(pr_, fl_, Lp, x, dy, colbuf, colbuf_elems, precol);
+      add_wgrad_on_lane(pr_, fl_, Lp, x, dy, colbuf, colbuf_elems, precol, Gd);
       pr_.cur_lane = main_lane;
     };
     auto add_in_bwd = [&](Program& pr_, const TensorDesc& y, const float2* stats, float2* bstats, GradSrc g, int act,
@@ -770,6 +817,19 @@ void cgb_engine::record_programs() {
     prog_adam[g].add([p, tb, cnt, mx, arena](cudaStream_t s) { pack_weights(p, tb, cnt, mx, arena, s); });
   }
   if (!infer_only) {
+  // fp32 validation mode: per-pass gradient buffers (generators: fake / rec / idt pass; discriminators: real / fake)
+  gen[0].gslot = gen[2].gslot = 0;
+  gen[1].gslot = gen[3].gslot = 1;
+  gen[4].gslot = gen[5].gslot = 2;
+  dis[2].gslot = dis[3].gslot = 0;
+  dis[0].gslot = dis[1].gslot = dis[5].gslot = dis[6].gslot = 1;
+  auto add_sum_slots = [E](Program& pr, int group) {
+    if (!E->fp32) return;
+    float* dst = E->G[group];
+    const float *s0 = E->gslot[group][0], *s1 = E->gslot[group][1], *s2 = group == CGB_GROUP_G ? E->gslot[group][2] : nullptr;
+    const long long n = E->group_numel[group];
+    pr.add([dst, s0, s1, s2, n](cudaStream_t st) { f32::sum_slots(dst, s0, s1, s2, n, st); });
+  };
   // ---------------------------------------------------------------- step programs
   const TensorDesc &fake_B = img[CGB_IMG_FAKE_B], &rec_A = img[CGB_IMG_REC_A], &fake_A = img[CGB_IMG_FAKE_A],
                    &rec_B = img[CGB_IMG_REC_B], &idt_A = img[CGB_IMG_IDT_A], &idt_B = img[CGB_IMG_IDT_B],
@@ -786,9 +846,7 @@ void cgb_engine::record_programs() {
     prog_set_inputs_lite.add([sb, rb](cudaStream_t s) { nchw_to_nhwc(sb, 3, rb, s); });
     if (pair) {
       // [real_A; real_B; real_A]: images 0..2N feed G_AB, images N..3N feed G_BA; one im2col over all three
-      TensorDesc ra2 = reals3;
-      ra2.ptr = reals3.ptr + (long long)2 * N * reals3.sN();
-      ra2.N = N;
+      const TensorDesc ra2 = reals3.images(2 * N, N);
       prog_set_inputs.add([sa, ra2](cudaStream_t s) { nchw_to_nhwc(sa, 3, ra2, s); });
       prog_set_inputs_lite.add([sa, ra2](cudaStream_t s) { nchw_to_nhwc(sa, 3, ra2, s); });
       const TensorDesc r3 = reals3, x3 = xcol3;
@@ -904,6 +962,7 @@ void cgb_engine::record_programs() {
     pr.mark("bwd fake_A done");
     pr.join();
     pr.cur_lane = 0;
+    add_sum_slots(pr, CGB_GROUP_G);
     pr.mark("G phase end");
   }
   // D-phase pass on the fakes.  Without a pool the G-phase forward of D on the fake is reused (D unchanged since).
@@ -938,6 +997,7 @@ void cgb_engine::record_programs() {
     emit_dis_fake_phase(pr, flops, 1);
     pr.join();
     pr.cur_lane = 0;
+    add_sum_slots(pr, CGB_GROUP_D);
     pr.mark("D phase end");
   }
   // ---- the whole step as one schedule, recorded twice: with Adam(D) in the shadow of the generator backward
@@ -951,6 +1011,35 @@ void cgb_engine::record_programs() {
     float* gD = G[CGB_GROUP_D];
     const size_t gGb = (size_t)group_numel[CGB_GROUP_G] * sizeof(float), gDb = (size_t)group_numel[CGB_GROUP_D] * sizeof(float);
     float* ls = losses;
+    // Data-parallel program (no optimiser inside): gradient ranges become final while the step is still running and
+    // are announced through external events (cgb_engine::grad_buckets), so the caller's all-reduce of a bucket
+    // overlaps the rest of the backward pass.  A generator's gradient gets contributions from three passes (fake,
+    // rec, idt); the fake pass is the last one, its weight gradients run head -> stem on the weight-gradient lane.
+    const bool dp = !with_adam_d;
+    int ev_rec_done[2] = {-1, -1};  // [g]: the rec pass through generator g (G_AB: rec_B, G_BA: rec_A) is complete
+    int ev_idt_done[2] = {-1, -1};  // [g]: the identity pass through generator g is complete
+    static const int n_dp_buckets = std::getenv("CGB_DP_BUCKETS") ? std::max(1, std::atoi(std::getenv("CGB_DP_BUCKETS"))) : 3;
+    auto bucket_hook = [&](int gnet) {
+      return std::function<void(Program&, int)>([&, gnet](Program& p, int layer) {
+        if (!dp || fp32 || n_dp_buckets <= 1) return;  // (validation mode: gradients are final after the slot sum)
+        const std::vector<LayerParam>& L = layers[gnet];
+        // bucket j covers layers [lo_j, lo_{j-1}); lo_0 = end, residual blocks split evenly, the last bucket ends at the stem
+        int lo = -1, hi = (int)L.size();
+        for (int j = 1; j <= n_dp_buckets; ++j) {
+          const int l = j == n_dp_buckets ? 0 : 3 + 2 * (nb - nb * j / n_dp_buckets);
+          if (l == layer) lo = l;
+          if (lo < 0) hi = l;
+          if (lo >= 0) break;
+        }
+        if (lo < 0 || lo >= hi) return;
+        if (ev_rec_done[gnet] >= 0) p.wait(p.cur_lane, ev_rec_done[gnet]);
+        if (ev_idt_done[gnet] >= 0) p.wait(p.cur_lane, ev_idt_done[gnet]);
+        const long long net_end = gnet == 0 ? layers[1][0].w_off : group_numel[CGB_GROUP_G];
+        const long long off = L[lo].w_off, end = hi < (int)L.size() ? L[hi].w_off : net_end;
+        grad_buckets.push_back({CGB_GROUP_G, off, end - off});
+        p.ext_event((int)grad_buckets.size() - 1);
+      });
+    };
     pr.cur_lane = 0;
     pr.mark("step begin");
     pr.add([gG, gGb](cudaStream_t s) { CGB_CUDA(cudaMemsetAsync(gG, 0, gGb, s)); }, 0, kOpMemset);
@@ -1009,10 +1098,12 @@ void cgb_engine::record_programs() {
     pr.cur_lane = 0;
     emit_gen_forward(pr, &sink, gen[1], CGB_NET_G_BA, fake_B, img[CGB_IMG_REC_A], false, &xcol[2], nullptr);
     emit_gen_backward(pr, &sink, gen[1], gs[0], &real_A, cfg.lambda_A / numel_img, CGB_LOSS_CYCLE_A, GradSrc(), &dxp_img[0]);
+    if (dp) ev_rec_done[CGB_NET_G_BA] = pr.record(0);
     pr.mark("rec_A fwd+bwd done");
     pr.cur_lane = 1;
     emit_gen_forward(pr, &sink, gen[3], CGB_NET_G_AB, fake_A, img[CGB_IMG_REC_B], false, &xcol[3], nullptr);
     emit_gen_backward(pr, &sink, gen[3], gs[1], &real_B, cfg.lambda_B / numel_img, CGB_LOSS_CYCLE_B, GradSrc(), &dxp_img[1]);
+    if (dp) ev_rec_done[CGB_NET_G_AB] = pr.record(1);
     pr.mark("rec_B fwd+bwd done");
     // Lanes 2 / 3: the identity pass of one generator, the adversarial term on the fake (D frozen: input gradient
     // only, needed by the fake's backward on lane 0 / 1) and the whole D phase of one discriminator.
@@ -1034,6 +1125,7 @@ void cgb_engine::record_programs() {
       auto idt_bwd = [&]() {
         if (!pair) {
           emit_gen_backward(pr, &sink, GP, GS, &real_in, idt_scale, idt_slot, GradSrc(), nullptr);
+          if (dp) ev_idt_done[gnet] = pr.record(lane);
           pr.mark(side == 0 ? "idt_A fwd+bwd done" : "idt_B fwd+bwd done");
         }
       };
@@ -1070,6 +1162,11 @@ void cgb_engine::record_programs() {
     // backward chains (nothing later in the step reads the discriminator weights)
     pr.dep(3, 2);
     pr.cur_lane = 2;
+    add_sum_slots(pr, CGB_GROUP_D);
+    if (dp) {  // the discriminator gradients are final: first bucket
+      grad_buckets.push_back({CGB_GROUP_D, 0, group_numel[CGB_GROUP_D]});
+      pr.ext_event((int)grad_buckets.size() - 1);
+    }
     if (with_adam_d) {
       const long long before = pr.launches;
       for (size_t i = 0; i < prog_adam[CGB_GROUP_D].ops.size(); ++i)
@@ -1084,11 +1181,12 @@ void cgb_engine::record_programs() {
     g.g2 = &dxp_img[0];
     pr.cur_lane = 0;
     pr.wait(0, ev_dD_A);
+    const std::function<void(Program&, int)> hook_AB = bucket_hook(CGB_NET_G_AB), hook_BA = bucket_hook(CGB_NET_G_BA);
     if (pair)
       emit_gen_backward(pr, &sink, gen[0], gs[2], nullptr, 0.f, -1, g, nullptr, &real_B,
-                        cfg.lambda_B * cfg.lambda_idt / numel_img, CGB_LOSS_IDT_A);
+                        cfg.lambda_B * cfg.lambda_idt / numel_img, CGB_LOSS_IDT_A, &hook_AB);
     else
-      emit_gen_backward(pr, &sink, gen[0], gs[0], nullptr, 0.f, -1, g, nullptr);
+      emit_gen_backward(pr, &sink, gen[0], gs[0], nullptr, 0.f, -1, g, nullptr, nullptr, 0.f, -1, &hook_AB);
     pr.mark("bwd fake_B done");
     g.g1 = &dx_D0[1];
     g.g2 = &dxp_img[1];
@@ -1096,16 +1194,24 @@ void cgb_engine::record_programs() {
     pr.wait(1, ev_dD_B);
     if (pair)
       emit_gen_backward(pr, &sink, gen[2], gs[3], nullptr, 0.f, -1, g, nullptr, &real_A,
-                        cfg.lambda_A * cfg.lambda_idt / numel_img, CGB_LOSS_IDT_B);
+                        cfg.lambda_A * cfg.lambda_idt / numel_img, CGB_LOSS_IDT_B, &hook_BA);
     else
-      emit_gen_backward(pr, &sink, gen[2], gs[1], nullptr, 0.f, -1, g, nullptr);
+      emit_gen_backward(pr, &sink, gen[2], gs[1], nullptr, 0.f, -1, g, nullptr, nullptr, 0.f, -1, &hook_BA);
     pr.mark("bwd fake_A done");
     pr.join();
     pr.cur_lane = 0;
+    add_sum_slots(pr, CGB_GROUP_G);
+    if (dp && (fp32 || n_dp_buckets <= 1)) {  // one bucket: the whole generator group, at the end
+      grad_buckets.push_back({CGB_GROUP_G, 0, group_numel[CGB_GROUP_G]});
+      pr.ext_event((int)grad_buckets.size() - 1);
+    }
     pr.mark("step end (before Adam)");
   };
   record_step(prog_step, true);
   record_step(prog_step_dp, false);
+  grad_events.resize(grad_buckets.size());
+  for (cudaEvent_t& ev : grad_events) CGB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  prog_step_dp.ext_events = grad_events.data();
   }  // !infer_only
   {  // both optimisers side by side
     Program& pr = prog_adams;

@@ -10,6 +10,7 @@
 
 #include "../../include/cyclegan_b200.h"
 #include "conv_plan.h"
+#include "fp32_path.h"
 #include "pointwise.h"
 #include "small_wgrad.h"
 
@@ -26,7 +27,7 @@ struct LayerParam {
 };
 
 typedef std::function<void(cudaStream_t)> Op;
-enum OpKind { kOpOther = 0, kOpIgemm = 1, kOpWgradTc = 2, kOpWgradDirect = 3, kOpNorm = 4, kOpMemset = 5, kOpDep = 6, kOpMarker = 7, kOpRecord = 8, kOpWait = 9, kNumOpKinds = 10 };
+enum OpKind { kOpOther = 0, kOpIgemm = 1, kOpWgradTc = 2, kOpWgradSmall = 3, kOpNorm = 4, kOpMemset = 5, kOpDep = 6, kOpMarker = 7, kOpRecord = 8, kOpWait = 9, kOpExtEvent = 10, kNumOpKinds = 11 };
 constexpr int kLanes = 8;  // parallel graph branches: lanes 0-3 carry independent passes, lane l+4 the weight
                            // gradients of the pass on lane l (wgrad runs beside the dgrad of the same layer)
 constexpr int kPassLanes = 4;
@@ -90,6 +91,18 @@ struct Program {
     flops.push_back(0.0);
     names.push_back("");
   }
+  // external event: recorded on the current lane at this point of the program; streams OUTSIDE the program (the
+  // data-parallel communication stream) wait on it while the rest of the program keeps running.  In a captured graph
+  // it becomes an event-record node (cudaEventRecordExternal), in eager mode a plain cudaEventRecord.
+  cudaEvent_t* ext_events = nullptr;  // owned by the engine
+  void ext_event(int id) {
+    ops.push_back(Op());
+    kinds.push_back(kOpExtEvent);
+    lanes.push_back(cur_lane);
+    dep_from.push_back(id);
+    flops.push_back(0.0);
+    names.push_back("");
+  }
   void fork(int n = kLanes) {
     for (int l = 1; l < n; ++l) dep(0, l);
   }
@@ -97,8 +110,10 @@ struct Program {
     for (int l = 1; l < n; ++l) dep(l, 0);
   }
   void run(cudaStream_t st) const {
-    for (size_t i = 0; i < ops.size(); ++i)
+    for (size_t i = 0; i < ops.size(); ++i) {
       if (kinds[i] < kOpDep) ops[i](st);
+      else if (kinds[i] == kOpExtEvent && ext_events) CGB_CUDA(cudaEventRecord(ext_events[dep_from[i]], st));
+    }
   }
   // lanes[l] are distinct streams (lane 0 = the caller's); events: one per dep op, created by the caller
   struct Mark {
@@ -122,6 +137,9 @@ struct Program {
         } else {
           CGB_CUDA(cudaStreamWaitEvent(lane_streams[lanes[i]], rec[dep_from[i]], 0));
         }
+      } else if (kinds[i] == kOpExtEvent) {
+        if (ext_events)
+          CGB_CUDA(cudaEventRecordWithFlags(ext_events[dep_from[i]], lane_streams[lanes[i]], cudaEventRecordExternal));
       } else if (kinds[i] == kOpMarker) {
         if (timeline) {
           Mark m;
@@ -160,6 +178,7 @@ struct Program {
 struct Arena {
   uint8_t* base = nullptr;
   size_t off = 0;
+  int esz = 2;  // element size of the activation tensors carved from this arena (4: fp32 validation mode)
   void* alloc(size_t bytes) {
     off = (off + 1023) & ~size_t(1023);
     void* p = reinterpret_cast<void*>(reinterpret_cast<uintptr_t>(base) + off);
@@ -173,13 +192,15 @@ struct Arena {
     t.W = W;
     t.C = C;
     t.halo = halo;
-    t.ptr = static_cast<bf16*>(alloc((size_t)t.elems() * sizeof(bf16)));
+    t.esz = esz;
+    t.ptr = static_cast<bf16*>(alloc(t.bytes()));
     return t;
   }
 };
 
 struct GenPass {  // activations of one generator forward pass, kept for its backward
   int net = 0;
+  int gslot = 0;  // fp32 validation mode: which per-pass weight-gradient buffer this pass writes (cgb_engine::gslot)
   TensorDesc in, out;  // image tensors (not owned)
   const TensorDesc* xcol = nullptr;  // shared im2col4 matrix of `in` (stem fprop / wgrad as GEMMs), or null
   TensorDesc y_stem, a_stem, y_d1, a_d1, y_d2, y_u1, a_u1, y_u2, a_u2p;
@@ -192,6 +213,7 @@ struct GenPass {  // activations of one generator forward pass, kept for its bac
 
 struct DisPass {
   int net = 0;
+  int gslot = 0;
   TensorDesc in;  // image (not owned)
   TensorDesc l0, y1, a1, y2, a2, y3, a3, logits;
   float2* stats = nullptr;
@@ -218,6 +240,13 @@ struct cgb_engine {
   int sm_count = 148;
   bool bound = false;
   bool infer_only = false;  // CGB_FLAG_INFERENCE: module forwards only
+  // CGB_FLAG_FP32_VALIDATE: fp32 activations, fp64 accumulation, deterministic kernels (fp32_path.h); same programs.
+  // Weight gradients are WRITTEN into one flat buffer per pass kind (generators: fake / rec / idt pass; discriminators:
+  // real / fake pass) and summed in a fixed order at the end of each phase, so no float accumulation order depends
+  // on how the lanes interleave.
+  bool fp32 = false;
+  float* gslot[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+  float* grad_base(int group, int slot) const { return fp32 ? gslot[group][slot] : G[group]; }
   int pool_size = 0;        // image history pool (cgb_engine_set_image_pool): 0 = off (D sees the current fakes)
   cgb::TensorDesc pool_img[2], pool_din[2];  // [0]: fake_B history (for D_A), [1]: fake_A history (for D_B)
   int* pool_dec = nullptr;  // device [2][batch][2]: (store, ret) per image, written by cgb_set_pool_decisions
@@ -274,6 +303,14 @@ struct cgb_engine {
   cgb::Program prog_mod_gen[2], prog_mod_dis[2];
   double conv_flops = 0;  // accumulated while recording prog_cycle/prog_G/prog_D
 
+  // Data parallel: the gradient buffers become final bucket by bucket while the merged step (prog_step_dp) is still
+  // running; each bucket has an external event the caller's communication stream waits on (cgb_wait_grad_bucket).
+  struct GradBucket {
+    int group;
+    long long offset, numel;  // range of the group's flat gradient buffer
+  };
+  std::vector<GradBucket> grad_buckets;  // in the order they become ready
+  std::vector<cudaEvent_t> grad_events;  // one per bucket
   cudaStream_t lane_streams[cgb::kLanes] = {};  // [0] = caller's stream
   std::vector<cudaEvent_t> events;
   std::vector<cudaEvent_t> seg_events[CGB_NUM_SEGMENTS];

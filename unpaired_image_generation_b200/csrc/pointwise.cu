@@ -2,6 +2,7 @@
 // the channel count a multiple of 8, so every thread moves 16-byte vectors.
 #include "pointwise.h"
 
+#include "fp32_path.h"
 #include "ptx.cuh"
 
 #include <cstdlib>
@@ -25,6 +26,7 @@ struct DevTensor {
 };
 
 DevTensor dev(const TensorDesc& t) {
+  CGB_CHECK(t.esz == 2, "bf16 kernel called on an fp32 (validation mode) tensor");
   DevTensor d;
   d.p = t.interior();
   d.sN = t.sN();
@@ -35,6 +37,21 @@ DevTensor dev(const TensorDesc& t) {
   d.W = t.W;
   d.C = t.C;
   d.halo = t.halo;
+  return d;
+}
+// pure copy kernels (halo fill, pool exchange) also serve the fp32 validation mode: an fp32 tensor [.., C] is
+// viewed as a bf16 tensor [.., 2C] (strides are in bf16 elements; the base pointer is already byte-exact)
+DevTensor dev_bytes(const TensorDesc& t) {
+  TensorDesc b = t;
+  b.esz = 2;
+  DevTensor d = dev(b);
+  d.p = t.interior();
+  if (t.esz == 4) {
+    d.sN *= 2;
+    d.sH *= 2;
+    d.sW *= 2;
+    d.C *= 2;
+  }
   return d;
 }
 DevTensor dev_null() {
@@ -1095,39 +1112,11 @@ __global__ void im2col4_kernel(DevTensor src, int k, int stride, int sgn, int of
   *reinterpret_cast<uint2*>(dst.p + n * dst.sN + h * dst.sH + w * dst.sW + t * 4) = v;
 }
 
-// ------------------------------------------------------------------------------------------ direct wgrad
-// grid (pixel blocks, taps); thread <-> (cout, cin) pair(s); fp32 atomics into g[Cout][T][Cin].
-__global__ void wgrad_direct_kernel(DevTensor x, DevTensor dy, int Cin, int Cout, int k, int stride, int pad,
-                                    int reflect, int pix_per_block, float* __restrict__ g) {
-  const int T = k * k;
-  const int t = blockIdx.y;
-  const int r = t / k, c = t % k;
-  const long long total = (long long)dy.N * dy.H * dy.W;
-  const long long p0 = (long long)blockIdx.x * pix_per_block;
-  const long long p1 = min(total, p0 + pix_per_block);
-  const int pairs = Cin * Cout;
-  for (int pair = threadIdx.x; pair < pairs; pair += blockDim.x) {
-    const int co = pair / Cin, ci = pair % Cin;
-    float acc = 0.f;
-    for (long long p = p0; p < p1; ++p) {
-      const int ow = p % dy.W;
-      const int oh = (p / dy.W) % dy.H;
-      const int n = p / ((long long)dy.W * dy.H);
-      int ih = oh * stride + r - pad, iw = ow * stride + c - pad;
-      if (!reflect && (ih < 0 || ih >= x.H || iw < 0 || iw >= x.W)) continue;
-      // reflect: the halo of x already holds the mirrored pixels (ih in [-pad, H+pad))
-      const float d = __bfloat162float(dy.p[n * dy.sN + oh * dy.sH + ow * dy.sW + co]);
-      const float xv = __bfloat162float(x.p[n * x.sN + ih * x.sH + iw * x.sW + ci]);
-      acc += d * xv;
-    }
-    atomicAdd(g + ((long long)co * T + t) * Cin + ci, acc);
-  }
-}
-
 }  // namespace
 
 // ================================================================================================ host API
 void nchw_to_nhwc(const float* src, int C, const TensorDesc& dst, cudaStream_t st) {
+  if (dst.esz == 4) return f32::nchw_to_nhwc(src, C, dst, st);
   CGB_CHECK(dst.C % 8 == 0 && C <= dst.C, "nchw_to_nhwc: bad channel counts");
   const long long total = (long long)dst.N * (dst.H + 2 * dst.halo) * (dst.W + 2 * dst.halo);
   nchw_to_nhwc_kernel<<<blocks_for(total, 256), 256, 0, st>>>(src, C, dev(dst));
@@ -1135,6 +1124,7 @@ void nchw_to_nhwc(const float* src, int C, const TensorDesc& dst, cudaStream_t s
 }
 
 void nhwc_to_nchw(const TensorDesc& src, int C, float* dst, cudaStream_t st) {
+  if (src.esz == 4) return f32::nhwc_to_nchw(src, C, dst, st);
   const long long total = (long long)src.N * src.H * src.W;
   nhwc_to_nchw_kernel<<<blocks_for(total, 256), 256, 0, st>>>(dev(src), C, dst);
   CGB_CUDA(cudaGetLastError());
@@ -1142,8 +1132,9 @@ void nhwc_to_nchw(const TensorDesc& src, int C, float* dst, cudaStream_t st) {
 
 void fill_reflect_halo(const TensorDesc& t, cudaStream_t st) {
   if (t.halo == 0) return;
-  const long long total = (long long)t.N * (t.H + 2 * t.halo) * (t.W + 2 * t.halo) * (t.C / 8);
-  launch_pdl(fill_halo_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, st, dev(t));
+  const DevTensor d = dev_bytes(t);
+  const long long total = (long long)t.N * (t.H + 2 * t.halo) * (t.W + 2 * t.halo) * (d.C / 8);
+  launch_pdl(fill_halo_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, st, d);
 }
 
 void in_stats(const TensorDesc& y, float2* stats, cudaStream_t st) {
@@ -1155,6 +1146,7 @@ void in_stats(const TensorDesc& y, float2* stats, cudaStream_t st) {
 }
 
 void bias_grad(const TensorDesc& dy, int C, float* gbias, cudaStream_t st) {
+  if (dy.esz == 4) return f32::bias_grad(dy, C, gbias, st);  // validation mode: STORES the sum (one buffer per pass)
   const int HW = dy.H * dy.W;
   // every block ends with one scalar atomic per channel on the SAME few addresses (all images share the bias):
   // ~148 blocks over the whole batch (512 per image made the 3-channel head bias gradient 73 us at batch 8)
@@ -1273,6 +1265,7 @@ void in_bwd_apply(const TensorDesc& y, const float2* stats, const float2* bstats
 
 void tanh_bwd(const TensorDesc& out, const TensorDesc* target, float l1_scale, const GradSrc& g, int C,
               const TensorDesc& dpre, float* loss_slot, cudaStream_t st) {
+  if (out.esz == 4) return f32::tanh_bwd(out, target, l1_scale, g, C, dpre, loss_slot, st);
   CGB_CHECK(out.C == 16 && dpre.C == 16 && C <= 8, "tanh_bwd expects 16-channel image tensors");
   if (g.g1 || g.g2) check_grad(out, g);
   const long long total = (long long)out.N * out.H * out.W;
@@ -1281,12 +1274,14 @@ void tanh_bwd(const TensorDesc& out, const TensorDesc* target, float l1_scale, c
 }
 
 void l1_loss(const TensorDesc& a, const TensorDesc& b, int C, float scale, float* loss_slot, cudaStream_t st) {
+  if (a.esz == 4) return f32::l1_loss(a, b, C, scale, loss_slot, st);
   const long long total = (long long)a.N * a.H * a.W;
   l1_loss_kernel<<<blocks_for(total, 256), 256, 0, st>>>(dev(a), dev(b), C, scale, loss_slot);
   CGB_CUDA(cudaGetLastError());
 }
 
 void leaky_bwd(const TensorDesc& a, const TensorDesc& g, const TensorDesc& dpre, cudaStream_t st) {
+  if (a.esz == 4) return f32::leaky_bwd(a, g, dpre, st);
   const long long total = (long long)a.N * a.H * a.W * (a.C / 8);
   leaky_bwd_kernel<<<blocks_for(total, 256), 256, 0, st>>>(dev(a), dev(g), dev(dpre));
   CGB_CUDA(cudaGetLastError());
@@ -1294,6 +1289,7 @@ void leaky_bwd(const TensorDesc& a, const TensorDesc& g, const TensorDesc& dpre,
 
 void mse_loss(const TensorDesc& logits, float target, float w, float* loss_slot, const TensorDesc* dlogits,
               cudaStream_t st) {
+  if (logits.esz == 4) return f32::mse_loss(logits, target, w, loss_slot, dlogits, st);
   const long long total = (long long)logits.N * logits.H * logits.W;
   mse_loss_kernel<<<blocks_for(total, 256), 256, 0, st>>>(dev(logits), target, w, loss_slot,
                                                           dlogits ? dev(*dlogits) : dev_null());
@@ -1322,12 +1318,14 @@ void pool_exchange(const TensorDesc& fake, const TensorDesc& pool, const int* de
   CGB_CHECK(fake.C == pool.C && fake.C == d_in.C && fake.H == pool.H && fake.W == pool.W && d_in.N == fake.N &&
                 d_in.H == fake.H && d_in.W == fake.W && fake.C % 8 == 0,
             "pool_exchange: shape mismatch");
-  const long long total = (long long)fake.H * fake.W * (fake.C / 8);
-  pool_exchange_kernel<<<blocks_for(total, 256), 256, 0, st>>>(dev(fake), dev(pool), dec, dev(d_in));
+  const DevTensor f = dev_bytes(fake);
+  const long long total = (long long)fake.H * fake.W * (f.C / 8);
+  pool_exchange_kernel<<<blocks_for(total, 256), 256, 0, st>>>(f, dev_bytes(pool), dec, dev_bytes(d_in));
   CGB_CUDA(cudaGetLastError());
 }
 
 void nhwc_to_u8hwc(const TensorDesc& src, int C, unsigned char* dst, cudaStream_t st) {
+  if (src.esz == 4) return f32::nhwc_to_u8hwc(src, C, dst, st);
   const long long total = (long long)src.N * src.H * src.W;
   nhwc_to_u8hwc_kernel<<<blocks_for(total, 256), 256, 0, st>>>(dev(src), C, dst);
   CGB_CUDA(cudaGetLastError());
@@ -1346,21 +1344,11 @@ void u8hwc_to_nchw(const unsigned char* src, int N, int H, int W, float* dst, cu
 
 void im2col4(const TensorDesc& src, int k, int stride, int sgn, int off, bool use_halo, const TensorDesc& dst,
              cudaStream_t st) {
+  if (src.esz == 4) return;  // validation mode: the 3-channel weight gradients are computed directly (f32::conv_wgrad)
   CGB_CHECK(src.C >= 4 && dst.C >= 4 * k * k && dst.halo == 0, "im2col4: bad source / destination");
   const long long total = (long long)dst.N * dst.H * dst.W * k * k;
   launch_pdl(im2col4_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, st, dev(src), k, stride, sgn, off, use_halo ? 1 : 0,
              dev(dst));
-}
-
-void wgrad_direct(const ConvSpec& s, const TensorDesc& x, const TensorDesc& dy, float* g, cudaStream_t st) {
-  CGB_CHECK(!s.transposed, "wgrad_direct: transposed convs use the tensor-core path");
-  if (s.reflect) CGB_CHECK(x.halo == s.pad, "wgrad_direct: reflect conv input must carry a halo");
-  const long long total = (long long)dy.N * dy.H * dy.W;
-  const int ppb = total >= 65536 ? 1024 : (total >= 8192 ? 256 : 64);
-  dim3 grid((unsigned)((total + ppb - 1) / ppb), s.taps());
-  wgrad_direct_kernel<<<grid, 256, 0, st>>>(dev(x), dev(dy), s.Cin, s.Cout, s.k, s.stride, s.pad, s.reflect ? 1 : 0,
-                                            ppb, g);
-  CGB_CUDA(cudaGetLastError());
 }
 
 }  // namespace cgb

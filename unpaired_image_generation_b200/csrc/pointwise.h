@@ -92,8 +92,4 @@ void u8hwc_to_nchw(const unsigned char* src, int N, int H, int W, float* dst, cu
 void im2col4(const TensorDesc& src, int k, int stride, int sgn, int off, bool use_halo, const TensorDesc& dst,
              cudaStream_t st);
 
-// ---- CUDA-core convolution passes for the 3-channel / 1-channel layers ------------------------
-// g[Cout][T][Cin] += sum_pixels dy * x   (x may carry a reflect halo == pad; zero padding otherwise)
-void wgrad_direct(const ConvSpec& s, const TensorDesc& x, const TensorDesc& dy, float* g, cudaStream_t st);
-
 }  // namespace cgb

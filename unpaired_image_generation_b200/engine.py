@@ -75,7 +75,7 @@ def describe(batch: int, size: int, n_blocks: int = 9) -> Dict[int, List[ParamIn
 class StepEngine:
     def __init__(self, batch: int, size: int, n_blocks: int = 9, lambda_A: float = 10.0, lambda_B: float = 10.0,
                  lambda_idt: float = 0.5, lr: float = 2e-4, betas=(0.5, 0.999), eps: float = 1e-8, device=None,
-                 inference: bool = False, pool_size: int = 0):
+                 inference: bool = False, pool_size: int = 0, precision: str = "bf16"):
         if not torch.cuda.is_available():
             raise RuntimeError("unpaired_image_generation_b200 needs a CUDA device (B200, sm_100a); "
                                "there is no CPU fallback")
@@ -85,8 +85,13 @@ class StepEngine:
         cfg = _lib.CgbConfig(batch, size, n_blocks, lambda_A, lambda_B, lambda_idt, lr, betas[0], betas[1], eps)
         self._h = ctypes.c_void_p()
         # inference=True: module forwards only (CGB_FLAG_INFERENCE): the workspace holds one forward pass
+        # precision="fp32": the deterministic fp32 validation mode (CGB_FLAG_FP32_VALIDATE), same programs / schedule
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' (product path) or 'fp32' (validation mode)")
         self.inference = bool(inference)
-        _lib.check(self.lib.cgb_engine_create_ex(ctypes.byref(cfg), 1 if inference else 0, ctypes.byref(self._h)))
+        self.precision = precision
+        flags = (1 if inference else 0) | (2 if precision == "fp32" else 0)
+        _lib.check(self.lib.cgb_engine_create_ex(ctypes.byref(cfg), flags, ctypes.byref(self._h)))
         self.pool_size = int(pool_size)
         if self.pool_size > 0:  # image history pool: re-plans the workspace, must precede the bind
             _lib.check(self.lib.cgb_engine_set_image_pool(self._h, self.pool_size))
@@ -102,9 +107,14 @@ class StepEngine:
             numel = [self.lib.cgb_group_numel(self._h, g) for g in range(2)]
             mk = lambda n: torch.zeros(n, dtype=torch.float32, device=self.device)
             self.params = [mk(numel[0]), mk(numel[1])]
-            self.grads = [mk(numel[0]), mk(numel[1])]
-            self.exp_avg = [mk(numel[0]), mk(numel[1])]
-            self.exp_avg_sq = [mk(numel[0]), mk(numel[1])]
+            if self.inference:
+                # module forwards never touch gradients or Adam moments: bind one small dummy instead of 3 x 113 MB
+                dummy = mk(4)
+                self.grads = self.exp_avg = self.exp_avg_sq = [dummy, dummy]
+            else:
+                self.grads = [mk(numel[0]), mk(numel[1])]
+                self.exp_avg = [mk(numel[0]), mk(numel[1])]
+                self.exp_avg_sq = [mk(numel[0]), mk(numel[1])]
             ws_bytes = self.lib.cgb_workspace_bytes(self._h)
             self._ws_raw = torch.empty(ws_bytes + 1024, dtype=torch.uint8, device=self.device)
             off = (-self._ws_raw.data_ptr()) % 1024
@@ -143,6 +153,27 @@ class StepEngine:
 
     def set_grad_scale(self, scale: float):
         _lib.check(self.lib.cgb_set_grad_scale(self._h, scale))
+
+    # ---- optimiser state (checkpoint / resume) ----------------------------------------------------
+    def step_count(self, group: int) -> int:
+        out = ctypes.c_int()
+        _lib.check(self.lib.cgb_get_step_count(self._h, group, ctypes.byref(out)))
+        return int(out.value)
+
+    def set_step_count(self, group: int, step: int):
+        _lib.check(self.lib.cgb_set_step_count(self._h, group, int(step)))
+
+    def optimizer_state(self) -> Dict[str, object]:
+        """flat Adam state of both groups (stand-in: opt_G.state_dict() / opt_D.state_dict()): moments + step"""
+        return {"exp_avg": [t.detach().clone() for t in self.exp_avg],
+                "exp_avg_sq": [t.detach().clone() for t in self.exp_avg_sq],
+                "step": [self.step_count(0), self.step_count(1)]}
+
+    def load_optimizer_state(self, state: Dict[str, object]):
+        for g in range(2):
+            self.exp_avg[g].copy_(state["exp_avg"][g])
+            self.exp_avg_sq[g].copy_(state["exp_avg_sq"][g])
+            self.set_step_count(g, state["step"][g])
 
     # ---- modules --------------------------------------------------------------------------------
     def _check_img(self, x: torch.Tensor) -> torch.Tensor:
@@ -200,6 +231,20 @@ class StepEngine:
     def run_segment(self, segment: int):
         """graph-replayed part of the step: 0 whole step, 1 G phase (incl. forwards), 2 D phase, 3/4 Adam G/D"""
         _lib.check(self.lib.cgb_run_segment(self._h, segment, _stream()))
+
+    def grad_buckets(self) -> List[tuple]:
+        """(group, offset, numel) ranges of the flat gradient buffers in the order the data-parallel step
+        (segment 6) announces them as final"""
+        out = []
+        for i in range(max(0, self.lib.cgb_num_grad_buckets(self._h))):
+            g, off, n = ctypes.c_int(), ctypes.c_longlong(), ctypes.c_longlong()
+            _lib.check(self.lib.cgb_grad_bucket_info(self._h, i, ctypes.byref(g), ctypes.byref(off), ctypes.byref(n)))
+            out.append((int(g.value), int(off.value), int(n.value)))
+        return out
+
+    def wait_grad_bucket(self, index: int):
+        """the current stream waits until bucket `index` of the most recently launched segment 6 is final"""
+        _lib.check(self.lib.cgb_wait_grad_bucket(self._h, index, _stream()))
 
     def forward_cycle(self):
         _lib.check(self.lib.cgb_forward_cycle(self._h, _stream()))

@@ -32,7 +32,18 @@ class _NetModule:
             self._params[info.name] = t.to(self._device)
         self._engine: Optional[_engine.StepEngine] = None  # set by CycleGANTrainer
         self._net: Optional[int] = None
-        self._private: Dict[Tuple[int, int], _engine.StepEngine] = {}
+        # inference-only engines for input shapes other than the trainer's, newest last; each remembers the weight
+        # version it was packed from and is re-synchronised when the weights moved on (training steps, in-place writes)
+        self._private: "OrderedDict[Tuple[int, int], _engine.StepEngine]" = OrderedDict()
+        self._private_version: Dict[Tuple[int, int], Tuple[int, int]] = {}
+        self._trained_steps = 0  # bumped by CycleGANTrainer after every optimiser step (raw-pointer writes)
+
+    _MAX_PRIVATE = 2  # private inference engines kept alive per module (each holds one forward pass of workspace)
+
+    def _weights_version(self) -> Tuple[int, int]:
+        """changes whenever the parameters may have changed: optimiser steps of the attached trainer, plus torch's
+        in-place version counters (writes through parameters() / named_parameters() views)"""
+        return self._trained_steps, sum(int(p._version) for p in self._params.values())
 
     # ---- nn.Module-like surface -------------------------------------------------------------------
     def named_parameters(self) -> Iterator[Tuple[str, torch.Tensor]]:
@@ -56,7 +67,6 @@ class _NetModule:
             dst.copy_(src.to(device=dst.device, dtype=torch.float32))
         if self._engine is not None:
             self._engine.refresh_weights(0 if self._KIND == "G" else 1)
-        self._private.clear()
 
     # ---- engine plumbing --------------------------------------------------------------------------
     def _attach(self, eng: _engine.StepEngine, net: int) -> None:
@@ -67,6 +77,7 @@ class _NetModule:
         self._engine, self._net = eng, net
         self._device = eng.device
         self._private.clear()
+        self._private_version.clear()
 
     def _engine_for(self, x: torch.Tensor):
         batch, _, h, w = x.shape
@@ -75,14 +86,21 @@ class _NetModule:
         if self._engine is not None and (self._engine.batch, self._engine.size) == (batch, h):
             return self._engine, self._net
         key = (batch, h)
+        net = 0 if self._KIND == "G" else 2
         if key not in self._private:
-            eng = _engine.StepEngine(batch, h, self.n_blocks, inference=True)
-            net = 0 if self._KIND == "G" else 2
+            while len(self._private) >= self._MAX_PRIVATE:  # evict the least recently used engine
+                old, _ = self._private.popitem(last=False)
+                self._private_version.pop(old, None)
+            self._private[key] = _engine.StepEngine(batch, h, self.n_blocks, inference=True)
+        self._private.move_to_end(key)
+        eng = self._private[key]
+        version = self._weights_version()
+        if self._private_version.get(key) != version:  # first use, or the weights changed since it was packed
             for k, v in eng.param_views(net).items():
                 v.copy_(self._params[k].to(v.device))
             eng.refresh_weights(0 if self._KIND == "G" else 1)
-            self._private[key] = eng
-        return self._private[key], (0 if self._KIND == "G" else 2)
+            self._private_version[key] = self._weights_version()
+        return eng, net
 
     def __call__(self, x: torch.Tensor) -> torch.Tensor:
         return self.forward(x)
