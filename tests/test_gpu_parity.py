@@ -375,13 +375,19 @@ def test_private_inference_engines_follow_the_weights():
     fresh = cgb.Generator()
     fresh.load_state_dict(mods[0].state_dict())
     y_fresh = fresh(x2)
-    assert rel(y_after, y_fresh) < 1e-6, rel(y_after, y_fresh)
-    assert rel(y_before, y_fresh) > 1e-3  # two Adam steps at lr 2e-4 move the output visibly
+    # (two bf16 forwards of the same weights differ at the noise level: the InstanceNorm statistics accumulate with
+    # fp32 atomics in a run-dependent order)
+    same, moved = rel(y_after, y_fresh), rel(y_before, y_fresh)
+    assert same < 3e-2, same
+    assert moved > 4 * same, (moved, same)  # two Adam steps at lr 2e-4 move the output far beyond that noise
     # an in-place write through parameters() is seen as well
     with torch.no_grad():
         next(iter(mods[0].parameters())).mul_(0.5)
+    y_stale = y_after
     fresh.load_state_dict(mods[0].state_dict())
-    assert rel(mods[0](x2), fresh(x2)) < 1e-6
+    y_new = mods[0](x2)
+    assert rel(y_new, fresh(x2)) < 3e-2
+    assert rel(y_stale, y_new) > 4 * rel(y_new, fresh(x2))
 
 
 def test_losses_vs_fp32_golden_at_256(golden):

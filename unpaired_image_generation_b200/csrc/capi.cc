@@ -572,8 +572,10 @@ int cgb_instnorm_test(int n, int c, int h, int w, int act, const float* y, const
     nchw_to_nhwc(da, c, DA, 0);
     GradSrc g;
     g.g1 = &DA;
-    in_bwd_reduce(Y, stats, g, act, nullptr, bstats, 0);
-    in_bwd_apply(Y, stats, bstats, g, act, DY, 0);
+    if (!in_bwd_fused(Y, stats, g, act, nullptr, DY, 0)) {  // the engine makes the same choice (engine.cc add_in_bwd_raw)
+      in_bwd_reduce(Y, stats, g, act, nullptr, bstats, 0);
+      in_bwd_apply(Y, stats, bstats, g, act, DY, 0);
+    }
     nhwc_to_nchw(DY, c, dy_out, 0);
   }
   CGB_CUDA(cudaDeviceSynchronize());

@@ -515,6 +515,14 @@ void cgb_engine::record_programs() {
     const std::string shape = " C" + std::to_string(y.C) + " " + std::to_string(y.H) + "x" + std::to_string(y.W) +
                               (g.g1 ? " g1" : "") + (g.g2 ? " g2fold" + std::to_string(g.fold) : "") +
                               (da_store ? " +da" : "");
+    if (in_bwd_fused_supported(y)) {  // one cluster kernel: reductions + apply from shared memory
+      pr.cur_name = "in_bwd_fused" + shape;
+      pr.add([y, stats, g, act, da_store, dy](cudaStream_t st) {
+               CGB_CHECK(in_bwd_fused(y, stats, g, act, da_store, dy, st), "fused InstanceNorm backward refused a planned shape");
+             }, 1, kOpNorm);
+      pr.cur_name.clear();
+      return;
+    }
     pr.cur_name = "in_bwd_reduce" + shape;
     pr.add([y, stats, bstats, g, act, da_store](cudaStream_t st) { in_bwd_reduce(y, stats, g, act, da_store, bstats, st); },
            1, kOpNorm);

@@ -35,6 +35,12 @@ struct GradSrc {
 // bstats[n][c] += (sum dz, sum dz*xhat); optionally stores the assembled (bf16-rounded) gradient.
 void in_bwd_reduce(const TensorDesc& y, const float2* stats, const GradSrc& g, int act, const TensorDesc* da_out,
                    float2* bstats, cudaStream_t st);
+// Both steps in ONE kernel (thread-block clusters; the map's per-image slice of 32 or 16 channels stays in the
+// cluster's shared memory): same results as in_bwd_reduce + in_bwd_apply but deterministic (no atomics).  Returns false
+// without launching anything when the map is too large for it (or CGB_IN_FUSED=0): the caller then uses the two kernels.
+bool in_bwd_fused(const TensorDesc& y, const float2* stats, const GradSrc& g, int act, const TensorDesc* da_out,
+                  const TensorDesc& dy, cudaStream_t st);
+bool in_bwd_fused_supported(const TensorDesc& y);
 // dy = rstd * (dz - mean(dz) - xhat * mean(dz * xhat))
 void in_bwd_apply(const TensorDesc& y, const float2* stats, const float2* bstats, const GradSrc& g, int act,
                   const TensorDesc& dy, cudaStream_t st);
