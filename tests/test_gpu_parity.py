@@ -381,8 +381,8 @@ def test_private_inference_engines_follow_the_weights():
     assert same < 3e-2, same
     assert moved > 4 * same, (moved, same)  # two Adam steps at lr 2e-4 move the output far beyond that noise
     # an in-place write through parameters() is seen as well
-    with torch.no_grad():
-        next(iter(mods[0].parameters())).mul_(0.5)
+    with torch.no_grad():  # (the head: a scale on any conv that feeds an InstanceNorm would be normalised away)
+        dict(mods[0].named_parameters())["head.weight"].mul_(0.5)
     y_stale = y_after
     fresh.load_state_dict(mods[0].state_dict())
     y_new = mods[0](x2)

@@ -180,8 +180,9 @@ static bool try_patch(IgemmPlan& p, const TensorDesc& act, bool padded_view, con
   }
   const int tiles_w = (Wo + 7) / 8, tile_rows = (Ho + 15) / 16;
   const int prow = padded_rows(rows);
-  static const double frac = std::getenv("CGB_CTA_FRAC") ? std::atof(std::getenv("CGB_CTA_FRAC")) : 0.3;
-  const long long target = (long long)(sm_count * frac);
+  static const double frac_f = std::getenv("CGB_CTA_FRAC") ? std::atof(std::getenv("CGB_CTA_FRAC")) : 0.3;
+  static const double frac_d = std::getenv("CGB_CTA_FRAC_DGRAD") ? std::atof(std::getenv("CGB_CTA_FRAC_DGRAD")) : frac_f;
+  const long long target = (long long)(sm_count * (flip ? frac_d : frac_f));
   int forced_bn = 0, forced_mt = 0;
   if (const char* f = std::getenv("CGB_FORCE_BN")) forced_bn = std::atoi(f);
   if (const char* f = std::getenv("CGB_FORCE_MT")) forced_mt = std::atoi(f);

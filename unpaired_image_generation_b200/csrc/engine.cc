@@ -600,23 +600,33 @@ void cgb_engine::record_programs() {
   auto emit_gen_backward = [&](Program& pr, double* fl, GenPass& P, GenScratch& S, const TensorDesc* target,
                                float l1_scale, int loss_slot, GradSrc gsrc, const TensorDesc* dxp_img_out,
                                const TensorDesc* target2 = nullptr, float l1_scale2 = 0.f, int loss_slot2 = -1,
-                               const std::function<void(Program&, int)>* after_wgrad = nullptr) {
+                               const std::function<void(Program&, int, int)>* after_wgrad = nullptr) {
     const std::vector<LayerParam>& L = E->layers[P.net];
     float* Gg = E->grad_base(CGB_GROUP_G, P.gslot);
     float2* st = P.stats;
     float2* bs = P.bstats;
     const int main_lane = pr.cur_lane, wlane = pr.cur_lane + kPassLanes;
+    // Second weight-gradient lane (CGB_WGRAD_LANES=2): consecutive layers' weight gradients alternate between two side
+    // lanes and run concurrently.  At batch 1 a residual weight gradient (18 CTAs, ~29 us) takes longer than the
+    // chain spends on a layer once the InstanceNorm backward is one kernel (~27 us), so a single side lane would set
+    // the pace of the backward pass.
+    static const int n_wlanes = std::getenv("CGB_WGRAD_LANES") ? std::atoi(std::getenv("CGB_WGRAD_LANES")) : 2;
+    const int wlane2 = n_wlanes >= 2 ? pr.cur_lane + 2 * kPassLanes : wlane;
+    int n_wgrads = 0;
     // weight gradient on the side lane, beside the input gradient of the same layer
-    std::vector<int> wgrad_done;  // record ids on the side lane, one per weight gradient issued so far
+    std::vector<int> wgrad_done;  // record ids on the side lanes, one per weight gradient issued so far
     auto add_wgrad = [&](Program& pr_, double* fl_, const LayerParam& Lp, const TensorDesc& x, const TensorDesc& dy,
                          bf16* colbuf, size_t colbuf_elems, const TensorDesc* precol = nullptr) {
-      pr_.dep(main_lane, wlane);
-      pr_.cur_lane = wlane;
+      // (a gradient that reads a precomputed im2col matrix stays on the first side lane: that is the lane the
+      // matrix was built on / that waits for it, see record_step)
+      const int wl = ((n_wgrads++ & 1) && precol == nullptr) ? wlane2 : wlane, other = wl == wlane ? wlane2 : wlane;
+      pr_.dep(main_lane, wl);
+      pr_.cur_lane = wl;
       add_wgrad_on_lane(pr_, fl_, Lp, x, dy, colbuf, colbuf_elems, precol, Gg);
-      wgrad_done.push_back(pr_.record(wlane));
+      wgrad_done.push_back(pr_.record(wl));
       // data-parallel hook (still on the weight-gradient lane): this layer's gradient is final once the other passes
       // of the same generator are done too -- the callback adds those waits and the bucket's external event
-      if (after_wgrad) (*after_wgrad)(pr_, (int)(&Lp - L.data()));
+      if (after_wgrad) (*after_wgrad)(pr_, (int)(&Lp - L.data()), other != wl ? other : -1);
       pr_.cur_lane = main_lane;
     };
     // A layer's dy buffer is read by its weight gradient on the side lane.  Consecutive layers never share a dy
@@ -708,6 +718,7 @@ void cgb_engine::record_programs() {
     add_wgrad(pr, fl, L[0], P.in, S.dyF, S.colbuf, S.colbuf_elems, P.xcol);
     if (dxp_img_out) add_dgrad(pr, fl, L[0], S.dyF, *dxp_img_out);
     pr.dep(wlane, main_lane);
+    if (wlane2 != wlane) pr.dep(wlane2, main_lane);
   };
 
   // ---------------------------------------------------------------- discriminator
@@ -1028,7 +1039,7 @@ void cgb_engine::record_programs() {
     int ev_idt_done[2] = {-1, -1};  // [g]: the identity pass through generator g is complete
     static const int n_dp_buckets = std::getenv("CGB_DP_BUCKETS") ? std::max(1, std::atoi(std::getenv("CGB_DP_BUCKETS"))) : 3;
     auto bucket_hook = [&](int gnet) {
-      return std::function<void(Program&, int)>([&, gnet](Program& p, int layer) {
+      return std::function<void(Program&, int, int)>([&, gnet](Program& p, int layer, int other_wlane) {
         if (!dp || fp32 || n_dp_buckets <= 1) return;  // (validation mode: gradients are final after the slot sum)
         const std::vector<LayerParam>& L = layers[gnet];
         // bucket j covers layers [lo_j, lo_{j-1}); lo_0 = end, residual blocks split evenly, the last bucket ends at the stem
@@ -1040,6 +1051,7 @@ void cgb_engine::record_programs() {
           if (lo >= 0) break;
         }
         if (lo < 0 || lo >= hi) return;
+        if (other_wlane >= 0) p.dep(other_wlane, p.cur_lane);  // the previous layer's gradient ran on the other side lane
         if (ev_rec_done[gnet] >= 0) p.wait(p.cur_lane, ev_rec_done[gnet]);
         if (ev_idt_done[gnet] >= 0) p.wait(p.cur_lane, ev_idt_done[gnet]);
         const long long net_end = gnet == 0 ? layers[1][0].w_off : group_numel[CGB_GROUP_G];
@@ -1189,7 +1201,7 @@ void cgb_engine::record_programs() {
     g.g2 = &dxp_img[0];
     pr.cur_lane = 0;
     pr.wait(0, ev_dD_A);
-    const std::function<void(Program&, int)> hook_AB = bucket_hook(CGB_NET_G_AB), hook_BA = bucket_hook(CGB_NET_G_BA);
+    const std::function<void(Program&, int, int)> hook_AB = bucket_hook(CGB_NET_G_AB), hook_BA = bucket_hook(CGB_NET_G_BA);
     if (pair)
       emit_gen_backward(pr, &sink, gen[0], gs[2], nullptr, 0.f, -1, g, nullptr, &real_B,
                         cfg.lambda_B * cfg.lambda_idt / numel_img, CGB_LOSS_IDT_A, &hook_AB);

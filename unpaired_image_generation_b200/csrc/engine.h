@@ -28,7 +28,7 @@ struct LayerParam {
 
 typedef std::function<void(cudaStream_t)> Op;
 enum OpKind { kOpOther = 0, kOpIgemm = 1, kOpWgradTc = 2, kOpWgradSmall = 3, kOpNorm = 4, kOpMemset = 5, kOpDep = 6, kOpMarker = 7, kOpRecord = 8, kOpWait = 9, kOpExtEvent = 10, kNumOpKinds = 11 };
-constexpr int kLanes = 8;  // parallel graph branches: lanes 0-3 carry independent passes, lane l+4 the weight
+constexpr int kLanes = 12;  // parallel graph branches: lanes 0-3 carry independent passes, lanes l+4 and l+8 the weight
                            // gradients of the pass on lane l (wgrad runs beside the dgrad of the same layer)
 constexpr int kPassLanes = 4;
 

@@ -835,23 +835,20 @@ in_apply_async_kernel(DevTensor y, const float2* __restrict__ stats, int act, De
 }
 
 // ------------------------------------------------------------------------------------------ fused IN backward
-// One thread-block CLUSTER of kInCluster CTAs owns (image n, CG consecutive channels) of a map whose slice fits the
-// cluster's shared memory: every CTA keeps its pixels' (y, assembled gradient) in shared memory, the two reductions
-// (sum dz, sum dz * xhat) go per thread -> warp shuffles -> CTA -> cluster (partials read through distributed shared
-// memory in rank order), and the apply pass runs from shared memory.  Versus in_bwd_reduce + in_bwd_apply: one launch
-// instead of two on the backward chain, 6 instead of 10 bytes per element of HBM / L2 traffic, no atomics (the result
-// is deterministic).  Each thread owns the items (pixel, 8-channel vector) i * 256 + tid, so its channel vector is
-// fixed and the shared-memory slots are private to the thread.
+// One thread-block CLUSTER of kInCluster CTAs owns (image n, CG consecutive channels) of a map of at most 4096 pixels
+// (the residual stream at 256x256, the discriminator's inner layers): every thread keeps its ITEMS (pixel, 8-channel
+// vector) elements of y and of the assembled gradient in REGISTERS, the two reductions (sum dz, sum dz * xhat) go
+// thread -> warp shuffles -> CTA -> cluster (partials read through distributed shared memory in rank order), and the
+// apply pass runs from the registers.  Versus in_bwd_reduce + in_bwd_apply: one launch instead of two on the backward
+// chain, 6 instead of 10 bytes per element of traffic, all loads of a thread in flight at once, no atomics (the
+// result is deterministic).  A thread owns items i * 256 + tid, so its channel vector (tid % OCT) is fixed.
 constexpr int kInCluster = 8;
 
-template <int CG>
+template <int CG, int ITEMS>
 __global__ void __launch_bounds__(256)
 in_bwd_fused_kernel(DevTensor y, const float2* __restrict__ stats, DevGrad g, int act, DevTensor da, DevTensor dy,
-                    int pix_per_cta, int items) {
+                    int pix_per_cta) {
   constexpr int OCT = CG / 8;  // 8-channel vectors per pixel handled by this cluster
-  extern __shared__ uint4 fused_smem[];
-  uint4* ybuf = fused_smem;                                  // [items][256] raw bf16 x 8
-  float4* gbuf = reinterpret_cast<float4*>(fused_smem + (size_t)items * 256);  // [items][2][256] fp32 gradient
   __shared__ float warp_part[8][OCT][16];
   __shared__ float cta_part[2 * CG];
   __shared__ float total[2 * CG];
@@ -864,36 +861,83 @@ in_bwd_fused_kernel(DevTensor y, const float2* __restrict__ stats, DevGrad g, in
   const int HW = y.H * y.W;
   const float inv = 1.f / (float)HW;
   const int p_begin = (int)rank * pix_per_cta, p_end = min(HW, p_begin + pix_per_cta);
+  // ---- phase 1a: issue every load of this thread
+  uint4 yraw[ITEMS], g1raw[ITEMS], g2raw[ITEMS];
+  int ph[ITEMS], pw[ITEMS];
+  bool ok[ITEMS];
+#pragma unroll
+  for (int it = 0; it < ITEMS; ++it) {
+    const int p = p_begin + (it * 256 + tid) / OCT;
+    ok[it] = p < p_end;
+    ph[it] = p / y.W;
+    pw[it] = p - ph[it] * y.W;
+    if (ok[it]) {
+      yraw[it] = *reinterpret_cast<const uint4*>(y.p + n * y.sN + ph[it] * y.sH + pw[it] * y.sW + c0);
+      if (g.g1.p != nullptr)
+        g1raw[it] = *reinterpret_cast<const uint4*>(g.g1.p + n * g.g1.sN + ph[it] * g.g1.sH + pw[it] * g.g1.sW + c0);
+      if (g.g2.p != nullptr)
+        g2raw[it] = *reinterpret_cast<const uint4*>(g.g2.p + n * g.g2.sN + (ph[it] + g.fold) * g.g2.sH +
+                                                    (pw[it] + g.fold) * g.g2.sW + c0);
+    }
+  }
   float a[8], b[8];
   load_norm8(stats, (long long)n * y.C + c0, inv, a, b);
   float s1[8], s2[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
-  // ---- phase 1: gather, assemble the gradient, keep (y, gradient) in shared memory, partial sums
-#pragma unroll 2
-  for (int it = 0; it < items; ++it) {
-    const int p = p_begin + (it * 256 + tid) / OCT;
-    if (p < p_end) {
-      const int h = p / y.W, w = p - h * y.W;
-      const uint4 yraw = *reinterpret_cast<const uint4*>(y.p + n * y.sN + h * y.sH + w * y.sW + c0);
-      float gr[8], v[8];
-      load_grad8(g, n, h, w, c0, y.H, y.W, gr);
-      if (da.p != nullptr) {
+  // ---- phase 1b: assemble the gradient (mirrored halo contributions of a padded-domain source are rare), sums
+  float gr[ITEMS][8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) gr[i] = round_bf16(gr[i]);
-        store8(da.p + n * da.sN + h * da.sH + w * da.sW + c0, gr);
-      }
-      unpack8(yraw, v);
+  for (int it = 0; it < ITEMS; ++it) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float xh = fmaf(v[i], a[i], b[i]);
-        const float dz = gr[i] * act_grad(xh, act);
-        s1[i] += dz;
-        s2[i] = fmaf(dz, xh, s2[i]);
+    for (int i = 0; i < 8; ++i) gr[it][i] = 0.f;
+    if (!ok[it]) continue;
+    float v[8];
+    if (g.g1.p != nullptr) {
+      unpack8(g1raw[it], v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) gr[it][i] += v[i];
+    }
+    if (g.g2.p != nullptr) {
+      unpack8(g2raw[it], v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) gr[it][i] += v[i];
+      const int p = g.fold, h = ph[it], w = pw[it], H = y.H, W = y.W;
+      const bool hb = (h >= 1 && h <= p) || (h >= H - 1 - p && h <= H - 2);
+      const bool wb = (w >= 1 && w <= p) || (w >= W - 1 - p && w <= W - 2);
+      if (hb || wb) {
+        const int hm = (h >= 1 && h <= p) ? p - h : 2 * (H - 1) - h + p;
+        const int wm = (w >= 1 && w <= p) ? p - w : 2 * (W - 1) - w + p;
+        const bf16* base = g.g2.p + n * g.g2.sN + c0;
+        if (hb) {
+          load8(base + hm * g.g2.sH + (w + p) * g.g2.sW, v);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) gr[it][i] += v[i];
+        }
+        if (wb) {
+          load8(base + (h + p) * g.g2.sH + wm * g.g2.sW, v);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) gr[it][i] += v[i];
+        }
+        if (hb && wb) {
+          load8(base + hm * g.g2.sH + wm * g.g2.sW, v);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) gr[it][i] += v[i];
+        }
       }
-      ybuf[it * 256 + tid] = yraw;
-      gbuf[(it * 2) * 256 + tid] = make_float4(gr[0], gr[1], gr[2], gr[3]);
-      gbuf[(it * 2 + 1) * 256 + tid] = make_float4(gr[4], gr[5], gr[6], gr[7]);
+    }
+    if (da.p != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) gr[it][i] = round_bf16(gr[it][i]);
+      store8(da.p + n * da.sN + ph[it] * da.sH + pw[it] * da.sW + c0, gr[it]);
+    }
+    unpack8(yraw[it], v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float xh = fmaf(v[i], a[i], b[i]);
+      const float dz = gr[it][i] * act_grad(xh, act);
+      s1[i] += dz;
+      s2[i] = fmaf(dz, xh, s2[i]);
     }
   }
   // ---- reductions: lanes with the same channel vector (lane % OCT) inside a warp, the 8 warps, the cluster's CTAs
@@ -928,31 +972,25 @@ in_bwd_fused_kernel(DevTensor y, const float2* __restrict__ stats, DevGrad g, in
     total[tid] = t;
   }
   __syncthreads();
-  // ---- phase 2: dy = rstd * (dz - mean(dz) - xhat * mean(dz * xhat)) = a * dz - c - d * xhat, from shared memory
+  // ---- phase 2: dy = rstd * (dz - mean(dz) - xhat * mean(dz * xhat)) = a * dz - c - d * xhat, from the registers
   float c[8], d[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     c[i] = a[i] * total[oct * 8 + i] * inv;
     d[i] = a[i] * total[CG + oct * 8 + i] * inv;
   }
-#pragma unroll 2
-  for (int it = 0; it < items; ++it) {
-    const int p = p_begin + (it * 256 + tid) / OCT;
-    if (p < p_end) {
-      const int h = p / y.W, w = p - h * y.W;
-      float v[8], gr[8];
-      unpack8(ybuf[it * 256 + tid], v);
-      const float4 g0 = gbuf[(it * 2) * 256 + tid], g1 = gbuf[(it * 2 + 1) * 256 + tid];
-      gr[0] = g0.x; gr[1] = g0.y; gr[2] = g0.z; gr[3] = g0.w;
-      gr[4] = g1.x; gr[5] = g1.y; gr[6] = g1.z; gr[7] = g1.w;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float xh = fmaf(v[i], a[i], b[i]);
-        const float dz = gr[i] * act_grad(xh, act);
-        v[i] = fmaf(a[i], dz, -c[i]) - d[i] * xh;
-      }
-      store8(dy.p + n * dy.sN + h * dy.sH + w * dy.sW + c0, v);
+  for (int it = 0; it < ITEMS; ++it) {
+    if (!ok[it]) continue;
+    float v[8];
+    unpack8(yraw[it], v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float xh = fmaf(v[i], a[i], b[i]);
+      const float dz = gr[it][i] * act_grad(xh, act);
+      v[i] = fmaf(a[i], dz, -c[i]) - d[i] * xh;
     }
+    store8(dy.p + n * dy.sN + ph[it] * dy.sH + pw[it] * dy.sW + c0, v);
   }
   ptx::cluster_sync_all();  // no CTA may exit while a peer can still read its partial sums
 }
@@ -1341,46 +1379,35 @@ static bool in_fused_enabled() {
   return on;
 }
 
-// picks the channel-group width: 32 when the slice fits, else 16; 0: the map is too large for a cluster's shared memory
-static int in_fused_plan(const TensorDesc& y, int* pix_per_cta, int* items, int* smem) {
+// channel-group width (32, else 16) and register items per thread (1, 2 or 4); 0: the map has more than 4096 pixels
+// per image (or an odd channel count) and keeps the two-kernel path
+static int in_fused_plan(const TensorDesc& y, int* pix_per_cta, int* items) {
   const int HW = y.H * y.W;
   for (int cg : {32, 16}) {
     if (y.C % cg != 0) continue;
     const int ppc = (HW + kInCluster - 1) / kInCluster;
-    const int it = (ppc * (cg / 8) + 255) / 256;
-    const int bytes = it * 256 * 48;  // 16 B of y + 32 B of fp32 gradient per item
-    if (bytes <= 200 * 1024) {
-      *pix_per_cta = ppc;
-      *items = it;
-      *smem = bytes;
-      return cg;
-    }
+    int it = (ppc * (cg / 8) + 255) / 256;
+    if (it > 4) continue;
+    it = it <= 1 ? 1 : it <= 2 ? 2 : 4;
+    *pix_per_cta = ppc;
+    *items = it;
+    return cg;
   }
   return 0;
 }
 
 bool in_bwd_fused_supported(const TensorDesc& y) {
-  int ppc = 0, items = 0, smem = 0;
-  return in_fused_enabled() && y.esz == 2 && y.C % 8 == 0 && in_fused_plan(y, &ppc, &items, &smem) != 0;
+  int ppc = 0, items = 0;
+  return in_fused_enabled() && y.esz == 2 && y.C % 8 == 0 && in_fused_plan(y, &ppc, &items) != 0;
 }
 
-bool in_bwd_fused(const TensorDesc& y, const float2* stats, const GradSrc& g, int act, const TensorDesc* da_out,
-                  const TensorDesc& dy, cudaStream_t st) {
-  if (!in_fused_enabled() || y.esz != 2) return false;
-  int ppc = 0, items = 0, smem = 0;
-  const int cg = in_fused_plan(y, &ppc, &items, &smem);
-  if (cg == 0) return false;
-  check_grad(y, g);
-  auto kern = cg == 32 ? in_bwd_fused_kernel<32> : in_bwd_fused_kernel<16>;
-  static bool configured[2] = {false, false};
-  if (!configured[cg == 32]) {
-    CGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured[cg == 32] = true;
-  }
+template <int CG, int ITEMS>
+static void launch_in_bwd_fused(const TensorDesc& y, const float2* stats, const GradSrc& g, int act, const TensorDesc* da_out,
+                                const TensorDesc& dy, int ppc, cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(kInCluster * (y.C / cg)), (unsigned)y.N);
+  cfg.gridDim = dim3((unsigned)(kInCluster * (y.C / CG)), (unsigned)y.N);
   cfg.blockDim = dim3(256);
-  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.dynamicSmemBytes = 0;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1391,8 +1418,26 @@ bool in_bwd_fused(const TensorDesc& y, const float2* stats, const GradSrc& g, in
   attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  CGB_CUDA(cudaLaunchKernelEx(&cfg, kern, dev(y), stats, dev(g), act, da_out ? dev(*da_out) : dev_null(), dev(dy), ppc,
-                              items));
+  CGB_CUDA(cudaLaunchKernelEx(&cfg, in_bwd_fused_kernel<CG, ITEMS>, dev(y), stats, dev(g), act,
+                              da_out ? dev(*da_out) : dev_null(), dev(dy), ppc));
+}
+
+bool in_bwd_fused(const TensorDesc& y, const float2* stats, const GradSrc& g, int act, const TensorDesc* da_out,
+                  const TensorDesc& dy, cudaStream_t st) {
+  if (!in_fused_enabled() || y.esz != 2) return false;
+  int ppc = 0, items = 0;
+  const int cg = in_fused_plan(y, &ppc, &items);
+  if (cg == 0) return false;
+  check_grad(y, g);
+  switch (cg * 10 + items) {
+    case 321: launch_in_bwd_fused<32, 1>(y, stats, g, act, da_out, dy, ppc, st); break;
+    case 322: launch_in_bwd_fused<32, 2>(y, stats, g, act, da_out, dy, ppc, st); break;
+    case 324: launch_in_bwd_fused<32, 4>(y, stats, g, act, da_out, dy, ppc, st); break;
+    case 161: launch_in_bwd_fused<16, 1>(y, stats, g, act, da_out, dy, ppc, st); break;
+    case 162: launch_in_bwd_fused<16, 2>(y, stats, g, act, da_out, dy, ppc, st); break;
+    case 164: launch_in_bwd_fused<16, 4>(y, stats, g, act, da_out, dy, ppc, st); break;
+    default: return false;
+  }
   return true;
 }
 
