@@ -606,11 +606,12 @@ void cgb_engine::record_programs() {
     float2* st = P.stats;
     float2* bs = P.bstats;
     const int main_lane = pr.cur_lane, wlane = pr.cur_lane + kPassLanes;
-    // Second weight-gradient lane (CGB_WGRAD_LANES=2): consecutive layers' weight gradients alternate between two side
-    // lanes and run concurrently.  At batch 1 a residual weight gradient (18 CTAs, ~29 us) takes longer than the
-    // chain spends on a layer once the InstanceNorm backward is one kernel (~27 us), so a single side lane would set
-    // the pace of the backward pass.
-    static const int n_wlanes = std::getenv("CGB_WGRAD_LANES") ? std::atoi(std::getenv("CGB_WGRAD_LANES")) : 2;
+    // Second weight-gradient lane (CGB_WGRAD_LANES=2, off by default): consecutive layers' weight gradients alternate
+    // between two side lanes and run concurrently.  At batch 1 a residual weight gradient (18 CTAs, ~29 us) takes
+    // longer than the chain spends on a layer once the InstanceNorm backward is one kernel (~27 us); measured on B200
+    // (profiles/r02_d_sweep_b1.txt) the second lane changes nothing: 4.643 vs 4.650 ms at batch 1, 26.90 vs 26.81 ms at
+    // batch 8 -- the step is bound by SM time, not by this chain.
+    static const int n_wlanes = std::getenv("CGB_WGRAD_LANES") ? std::atoi(std::getenv("CGB_WGRAD_LANES")) : 1;
     const int wlane2 = n_wlanes >= 2 ? pr.cur_lane + 2 * kPassLanes : wlane;
     int n_wgrads = 0;
     // weight gradient on the side lane, beside the input gradient of the same layer

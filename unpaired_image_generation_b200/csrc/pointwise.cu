@@ -1389,6 +1389,11 @@ static int in_fused_plan(const TensorDesc& y, int* pix_per_cta, int* items) {
     int it = (ppc * (cg / 8) + 255) / 256;
     if (it > 4) continue;
     it = it <= 1 ? 1 : it <= 2 ? 2 : 4;
+    // Measured on B200 (profiles/r02_c_ops_b*.txt): the cluster kernel halves the InstanceNorm-backward time of a
+    // residual-stream tensor at batch 1 (16.5 -> 8-10 us) but its register-resident elements cap the occupancy, so
+    // on grids of several waves (batch >= 4) the two streaming kernels are faster (33 vs 47 us at batch 8).
+    static const int max_ctas = std::getenv("CGB_IN_FUSED_MAX_CTAS") ? std::atoi(std::getenv("CGB_IN_FUSED_MAX_CTAS")) : 2 * 148;
+    if ((long long)kInCluster * (y.C / cg) * y.N > max_ctas) return 0;
     *pix_per_cta = ppc;
     *items = it;
     return cg;
