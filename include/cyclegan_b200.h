@@ -121,6 +121,11 @@ int cgb_phase_generators(cgb_engine_t* e, void* stream);
 int cgb_phase_discriminators(cgb_engine_t* e, void* stream);
 /* Adam on a group (grads multiplied by grad_scale), then refreshes that group's bf16 weights */
 int cgb_adam(cgb_engine_t* e, int group, void* stream);
+/* Adam on the sub-range [offset, offset + numel) of a group (data parallel: step each gradient bucket right after its
+ * all-reduce, overlapped with the rest of the backward pass).  advance_step != 0 for the FIRST range of an optimiser
+ * step of that group (increments the step counter and refreshes the bias corrections).  Does not refresh the bf16
+ * weights: call cgb_refresh_weights(group) after the last range. */
+int cgb_adam_range(cgb_engine_t* e, int group, long long offset, long long numel, int advance_step, void* stream);
 /* whole step on one stream, replayed from a CUDA graph after the first call */
 int cgb_train_step(cgb_engine_t* e, void* stream);
 /* copies fp32 NCHW inputs (device or pinned host) into the engine's staging buffers, nothing else */

@@ -54,6 +54,7 @@ SIGNATURES = {
     "cgb_phase_generators": (c_int, [_P, _P]),
     "cgb_phase_discriminators": (c_int, [_P, _P]),
     "cgb_adam": (c_int, [_P, c_int, _P]),
+    "cgb_adam_range": (c_int, [_P, c_int, c_longlong, c_longlong, c_int, _P]),
     "cgb_train_step": (c_int, [_P, _P]),
     "cgb_stage_inputs": (c_int, [_P, _P, _P, _P]),
     "cgb_run_segment": (c_int, [_P, c_int, _P]),

@@ -230,6 +230,18 @@ int cgb_adam(cgb_engine_t* e, int group, void* stream) {
   CGB_API_END
 }
 
+int cgb_adam_range(cgb_engine_t* e, int group, long long offset, long long numel, int advance_step, void* stream) {
+  CGB_API_BEGIN
+  CGB_CHECK(e && e->bound && group >= 0 && group < 2, "bad argument / engine not bound");
+  CGB_CHECK(!e->infer_only, "inference-only engine: training entry points are unavailable");
+  CGB_CHECK(offset >= 0 && numel >= 0 && offset % 4 == 0 && offset + numel <= e->group_numel[group],
+            "range must lie inside the group and start at a multiple of 4 elements");
+  adam_range(e->P[group] + offset, e->G[group] + offset, e->M[group] + offset, e->V[group] + offset, numel, e->cfg.beta1,
+             e->cfg.beta2, e->cfg.eps, e->adam_step[group], e->adam_hyper[group], e->grad_scale, advance_step != 0,
+             S(stream));
+  CGB_API_END
+}
+
 int cgb_train_step(cgb_engine_t* e, void* stream) {
   CGB_API_BEGIN
   CGB_CHECK(e && e->bound, "engine not bound");

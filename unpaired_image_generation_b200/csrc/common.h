@@ -113,6 +113,8 @@ struct WgradArgs {
   const int* row_map;      // optional: GEMM row m -> row of g (row length Cin, T ignored); < 0 = skip
   const int* col_map;      // optional: GEMM column -> column of g (< 0 = skip); forces the scalar epilogue
   int ncols;               // GEMM N extent (0: same as Cin)
+  int a_virtual;           // 1: the dY-side tensor map is a virtual im2col with dims (32 channels, 8 row taps, w, h, n) and
+                           //    box (32, 2, TWk, THk, 1): 64-channel atom j of the M tile = row taps 2j and 2j + 1
 };
 
 // Launch with the programmatic-dependent-launch attribute (see ptx.cuh: pdl_wait / pdl_launch_dependents).

@@ -1273,6 +1273,25 @@ __global__ void im2col4_kernel(DevTensor src, int k, int stride, int sgn, int of
   *reinterpret_cast<uint2*>(dst.p + n * dst.sN + h * dst.sH + w * dst.sW + t * 4) = v;
 }
 
+// one thread per (pixel of dst, horizontal tap s < 8): an 8-byte load (channels 0..3) and an 8-byte store
+__global__ void expand_rows4_kernel(DevTensor src, int k, int sgn, int off, int row_off, DevTensor dst) {
+  ptx::pdl_wait();  // launched with programmatic stream serialization (see launch_pdl)
+  const long long total = (long long)dst.N * dst.H * dst.W * 8;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int s = idx & 7;
+  long long r = idx >> 3;
+  const int w = r % dst.W;
+  r /= dst.W;
+  const int hh = r % dst.H;
+  const int n = r / dst.H;
+  const int sh = hh + row_off, sw = w + sgn * s + off;
+  uint2 v = make_uint2(0u, 0u);
+  if (s < k && sh >= 0 && sh < src.H && sw >= 0 && sw < src.W)
+    v = *reinterpret_cast<const uint2*>(src.p + n * src.sN + sh * src.sH + sw * src.sW);
+  *reinterpret_cast<uint2*>(dst.p + n * dst.sN + hh * dst.sH + w * dst.sW + s * 4) = v;
+}
+
 }  // namespace
 
 // ================================================================================================ host API
@@ -1541,8 +1560,16 @@ void pack_weights(const float* master, const PackEntry* entries_dev, int n_entri
 void adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                float eps, int* step_dev, float* hyper_dev, float grad_scale, cudaStream_t st) {
   (void)lr;  // the live value is hyper_dev[2] (set_device_float), initialised with the configured rate at bind time
-  adam_prep_kernel<<<1, 1, 0, st>>>(step_dev, hyper_dev, beta1, beta2);
-  CGB_CUDA(cudaGetLastError());
+  adam_range(p, g, m, v, n, beta1, beta2, eps, step_dev, hyper_dev, grad_scale, true, st);
+}
+
+void adam_range(float* p, const float* g, float* m, float* v, long long n, float beta1, float beta2, float eps,
+                int* step_dev, float* hyper_dev, float grad_scale, bool advance_step, cudaStream_t st) {
+  if (advance_step) {
+    adam_prep_kernel<<<1, 1, 0, st>>>(step_dev, hyper_dev, beta1, beta2);
+    CGB_CUDA(cudaGetLastError());
+  }
+  if (n <= 0) return;
   adam_kernel<<<blocks_for((n + 3) / 4, 256), 256, 0, st>>>(p, g, m, v, n, beta1, beta2, eps, hyper_dev, grad_scale);
   CGB_CUDA(cudaGetLastError());
 }
@@ -1573,6 +1600,13 @@ void u8hwc_to_nchw(const unsigned char* src, int N, int H, int W, float* dst, cu
   const long long total = (long long)N * H * W;
   u8hwc_to_nchw_kernel<<<blocks_for(total, 256), 256, 0, st>>>(src, N, H, W, dst);
   CGB_CUDA(cudaGetLastError());
+}
+
+void expand_rows4(const TensorDesc& src, int k, int sgn, int off, const TensorDesc& dst, cudaStream_t st) {
+  CGB_CHECK(src.C >= 4 && dst.C == 32 && dst.halo == 0 && k <= 8 && src.N == dst.N, "expand_rows4: bad source / destination");
+  const long long total = (long long)dst.N * dst.H * dst.W * 8;
+  launch_pdl(expand_rows4_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, st, dev(src), k, sgn, off,
+             sgn > 0 ? off : off - (k - 1), dev(dst));
 }
 
 void im2col4(const TensorDesc& src, int k, int stride, int sgn, int off, bool use_halo, const TensorDesc& dst,

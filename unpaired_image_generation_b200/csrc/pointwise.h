@@ -80,6 +80,11 @@ void pack_weights(const float* master, const PackEntry* entries_dev, int n_entri
 void adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                float eps, int* step_dev, float* hyper_dev, float grad_scale, cudaStream_t st);
 
+// the same update on a sub-range (data parallel: each gradient bucket is stepped right after its all-reduce);
+// advance_step: first range of this optimiser step (increments the step counter, refreshes the bias corrections)
+void adam_range(float* p, const float* g, float* m, float* v, long long n, float beta1, float beta2, float eps,
+                int* step_dev, float* hyper_dev, float grad_scale, bool advance_step, cudaStream_t st);
+
 // Image history pool exchange: d_in[n] = dec[n].ret >= 0 ? pool[ret] : fake[n]; pool[dec[n].store] = fake[n]
 // (batch order; dec = [N][2] ints (store, ret) on the device, -1 = none)
 void pool_exchange(const TensorDesc& fake, const TensorDesc& pool, const int* dec, const TensorDesc& d_in, cudaStream_t st);
@@ -97,5 +102,12 @@ void u8hwc_to_nchw(const unsigned char* src, int N, int H, int W, float* dst, cu
 // dst.C >= 4*k*k stored channels; columns >= 4*k*k are never written (they must be zero-initialised once).
 void im2col4(const TensorDesc& src, int k, int stride, int sgn, int off, bool use_halo, const TensorDesc& dst,
              cudaStream_t st);
+
+// Row expansion of a 16-stored-channel tensor with <= 4 real channels: the k horizontal taps only,
+//   dst[n][hh][w][s*4 + c] = src[n][hh + (sgn > 0 ? off : off - (k - 1))][w + sgn*s + off][c],  s < k, c < 4
+// (zero outside src; dst.C == 32, columns >= 4k are written as zeros).  The k vertical taps are NOT materialised: a
+// tensor map with overlapping row strides reads dst rows hh .. hh + k - 1 as the im2col matrix (small_wgrad.cc), which
+// is 8x fewer bytes than im2col4 for the 7x7 layers.
+void expand_rows4(const TensorDesc& src, int k, int sgn, int off, const TensorDesc& dst, cudaStream_t st);
 
 }  // namespace cgb

@@ -2,7 +2,14 @@
 
 #include "pointwise.h"
 
+#include <cstdlib>
+
 namespace cgb {
+
+static bool virtual_rows_enabled() {
+  static const bool on = !(std::getenv("CGB_VIRTUAL_COL") && std::atoi(std::getenv("CGB_VIRTUAL_COL")) == 0);
+  return on;
+}
 
 int im2col4_width(int taps) { return taps * 4 <= 64 ? 64 : 256; }
 
@@ -60,15 +67,36 @@ SmallWgradPlan plan_wgrad_small(const ConvSpec& s, const TensorDesc& x, const Te
     s1.Cin = s.Cin; s1.CinS = s.CinS; s1.Cout = Kp; s1.CoutS = Kp;
     p.gemm = plan_wgrad(s1, x1, p.col, g, sm_count);
     p.row_map.assign(Kp, -1);
-    for (int j = 0; j < T * 4; ++j)
-      if (j % 4 < s.Cout) p.row_map[j] = (j % 4) * T + j / 4;
+    // 7x7 (5 <= k <= 8): VIRTUAL im2col.  Only the k horizontal taps are materialised (32 columns per pixel instead
+    // of 256); the k vertical taps are rows h .. h + k - 1 of that tensor, read through a tensor map whose row-tap
+    // dimension overlaps its height dimension.  GEMM row m = r' * 32 + s * 4 + co with r' = k - 1 - r (the expansion
+    // is shifted down by k - 1 rows so that every row tap is a non-negative offset).
+    if (virtual_rows_enabled() && Kp == 256 && s.k >= 5 && s.k <= 8 &&
+        (size_t)x1.N * (x1.H + 8) * x1.W * 32 <= colbuf_elems) {
+      p.virtual_rows = true;
+      p.col.H = x1.H + 8;  // k - 1 rows above, one spare row-tap below; all written by expand_rows4
+      p.col.C = 32;
+      const int TWk = 1 << p.gemm.args.tw_shift, THk = 64 >> p.gemm.args.tw_shift;
+      const long long dims[5] = {32, 8, x1.W, x1.H, x1.N};
+      const long long str[4] = {(long long)x1.W * 32, 32, (long long)x1.W * 32, (long long)p.col.H * x1.W * 32};
+      const int box[5] = {32, 2, TWk, THk, 1};
+      p.gemm.tmDY = make_tmap_raw5d(colbuf, dims, str, box, 128);
+      p.gemm.args.a_virtual = 1;
+      for (int rp = 0; rp < s.k; ++rp)
+        for (int sx = 0; sx < s.k; ++sx)
+          for (int co = 0; co < s.Cout; ++co) p.row_map[rp * 32 + sx * 4 + co] = co * T + (s.k - 1 - rp) * s.k + sx;
+    } else {
+      for (int j = 0; j < T * 4; ++j)
+        if (j % 4 < s.Cout) p.row_map[j] = (j % 4) * T + j / 4;
+    }
   }
   p.gemm.flops = p.flops;
   return p;
 }
 
 void run(const SmallWgradPlan& p, cudaStream_t stream) {
-  if (!p.col_is_precomputed) im2col4(p.src, p.k, p.stride, p.sgn, p.off, p.use_halo, p.col, stream);
+  if (p.virtual_rows) expand_rows4(p.src, p.k, p.sgn, p.off, p.col, stream);
+  else if (!p.col_is_precomputed) im2col4(p.src, p.k, p.stride, p.sgn, p.off, p.use_halo, p.col, stream);
   run(p.gemm, stream);
 }
 

@@ -18,6 +18,9 @@ struct SmallWgradPlan {
   int k = 0, stride = 1, sgn = 1, off = 0;
   bool use_halo = false;
   bool col_is_precomputed = false;  // the caller keeps `col` up to date (shared stem im2col)
+  // virtual im2col (7x7 head): `col` is the ROW-EXPANDED gradient [N][Hp + 8][Wp][32] (pointwise.h expand_rows4) and the
+  // GEMM's dY-side tensor map reads rows h .. h + 7 of it as the 256 im2col columns (overlapping strides)
+  bool virtual_rows = false;
   double flops = 0;
 };
 

@@ -269,6 +269,10 @@ class StepEngine:
     def adam(self, group: int):
         _lib.check(self.lib.cgb_adam(self._h, group, _stream()))
 
+    def adam_range(self, group: int, offset: int, numel: int, advance_step: bool):
+        """Adam on a sub-range of a group's flat buffers (no bf16 refresh); see cgb_adam_range"""
+        _lib.check(self.lib.cgb_adam_range(self._h, group, offset, numel, 1 if advance_step else 0, _stream()))
+
     def train_step(self):
         """whole step on the current stream from the staged inputs (CUDA graph after the first call)"""
         _lib.check(self.lib.cgb_train_step(self._h, _stream()))

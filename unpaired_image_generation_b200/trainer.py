@@ -2,8 +2,9 @@
 arguments, `train_step(real_A, real_B) -> dict`, `forward_only`, `backward_only`, `set_lr`.  One process per
 GPU.  With torch.distributed initialised the step is data parallel: the merged step graph announces gradient
 buckets as they become final (discriminators first, then each generator from the head towards the stem) and the
-all-reduce of a bucket runs on a communication stream while the rest of the backward pass is still executing;
-both Adam updates follow the last collective.  Initial parameters and optimiser state are broadcast from rank 0."""
+all-reduce of a bucket, followed by Adam on that range, runs on a communication stream while the rest of the backward
+pass is still executing; the bf16 weight refresh follows the step.  Initial parameters and optimiser state are
+broadcast from rank 0."""
 from __future__ import annotations
 
 import os
@@ -224,19 +225,30 @@ class CycleGANTrainer:
                 ev_G.record(main)
             with torch.cuda.stream(comm):
                 if self._dp_overlap:
+                    # bucket by bucket: wait until the range is final, all-reduce it, Adam on it -- all while the step
+                    # graph keeps running (nothing left in the step reads the fp32 masters of a finished bucket; the
+                    # bf16 packs the kernels do read are refreshed after the step)
+                    first = [True, True]
                     for i, (group, off, numel) in enumerate(self._buckets):
                         eng.wait_grad_bucket(i)
                         self.sync.all_reduce_(eng.grads[group][off:off + numel])
-                comm.wait_event(ev_G)  # the whole step (also orders the collectives after it when not overlapping)
-                if not self._dp_overlap:
+                        eng.adam_range(group, off, numel, first[group])
+                        first[group] = False
+                    comm.wait_event(ev_G)             # the whole step: the conv kernels are done with the old bf16 weights
+                    eng.refresh_weights(1)
+                    eng.refresh_weights(0)
+                    ev_done.record(comm)
+                else:
+                    comm.wait_event(ev_G)
                     self.sync.all_reduce_(eng.grads[1])   # discriminators first: small, lets Adam(D) start early
                     self.sync.all_reduce_(eng.grads[0])
-                ev_D.record(comm)
-                eng.run_segment(3)                    # Adam(G) * 1/world + bf16 weight refresh
-                ev_done.record(comm)
-            with torch.cuda.stream(main):
-                main.wait_event(ev_D)
-                eng.run_segment(4)                    # Adam(D) beside Adam(G)
+                    ev_D.record(comm)
+                    eng.run_segment(3)                # Adam(G) * 1/world + bf16 weight refresh
+                    ev_done.record(comm)
+            if not self._dp_overlap:
+                with torch.cuda.stream(main):
+                    main.wait_event(ev_D)
+                    eng.run_segment(4)                # Adam(D) beside Adam(G)
             main.wait_event(ev_done)
             return
         with torch.cuda.stream(main):
