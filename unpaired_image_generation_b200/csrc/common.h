@@ -113,8 +113,9 @@ struct WgradArgs {
   const int* row_map;      // optional: GEMM row m -> row of g (row length Cin, T ignored); < 0 = skip
   const int* col_map;      // optional: GEMM column -> column of g (< 0 = skip); forces the scalar epilogue
   int ncols;               // GEMM N extent (0: same as Cin)
-  int a_virtual;           // 1: the dY-side tensor map is a virtual im2col with dims (32 channels, 8 row taps, w, h, n) and
-                           //    box (32, 2, TWk, THk, 1): 64-channel atom j of the M tile = row taps 2j and 2j + 1
+  int a_virtual;           // 1: the dY-side tensor map is a virtual im2col over a row-expanded tensor: dims (64 channels, w,
+                           //    row pair, h, n); 64-channel atom a of the GEMM's M extent = row pair a (rows h + 2a, h + 2a + 1)
+  int b_virtual;           // the same for the X side (atoms of the GEMM's N extent)
 };
 
 // Launch with the programmatic-dependent-launch attribute (see ptx.cuh: pdl_wait / pdl_launch_dependents).

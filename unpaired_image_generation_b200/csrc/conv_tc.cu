@@ -300,16 +300,20 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
         mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          if (args.a_virtual)  // (channel 0, row-tap pair, w, h, n): the box's (32 channels x 2 taps) form the 128-byte rows
-            tma_load_5d(sa + j * Cfg::kAtomBytes, &tmDY, &full_bar[s], 0, (mblk * 128 + j * 64) >> 5, w0, h0, n);
+          if (args.a_virtual)  // (channel 0, w, row pair, h, n): atom = rows h + 2a and h + 2a + 1 of the expanded tensor
+            tma_load_5d(sa + j * Cfg::kAtomBytes, &tmDY, &full_bar[s], 0, w0, (mblk * 128 + j * 64) >> 6, h0, n);
           else
             tma_load_5d(sa + j * Cfg::kAtomBytes, &tmDY, &full_bar[s], tap.a_c + mblk * 128 + j * 64, w0 + tap.a_dx,
                         tap.a_par, h0 + tap.a_dy, n);
         }
 #pragma unroll
-        for (int j = 0; j < BNW / 64; ++j)
-          tma_load_5d(sb + j * Cfg::kAtomBytes, &tmX, &full_bar[s], tap.b_c + nblk * BNW + j * 64, w0 + tap.b_dx,
-                      tap.b_par, h0 + tap.b_dy, n);
+        for (int j = 0; j < BNW / 64; ++j) {
+          if (args.b_virtual)
+            tma_load_5d(sb + j * Cfg::kAtomBytes, &tmX, &full_bar[s], 0, w0, (nblk * BNW + j * 64) >> 6, h0, n);
+          else
+            tma_load_5d(sb + j * Cfg::kAtomBytes, &tmX, &full_bar[s], tap.b_c + nblk * BNW + j * 64, w0 + tap.b_dx,
+                        tap.b_par, h0 + tap.b_dy, n);
+        }
       }
       __syncwarp();
     }

@@ -7,15 +7,10 @@ namespace cgb {
 
 // 5-D activation view: dims (d0 channels, d1 width, d2 parity plane, d3 height, d4 image),
 // strides in ELEMENTS for d1..d4 (d0 is contiguous), box = (box_c, box_w, 1, box_h, 1).
-// swizzle_bytes must equal box_c * 2 (32, 64 or 128).
+// swizzle_bytes must equal box_c * 2 (32, 64 or 128).  Strides may OVERLAP (two dimensions walking the same rows): that is
+// how the weight gradient of the 7x7 head reads a row-expanded gradient tensor as a virtual im2col matrix (small_wgrad.cc).
 CUtensorMap make_tmap_act5d(const bf16* base, const int dims[5], const long long strides_elems[4], int box_c,
                             int box_w, int box_h, int swizzle_bytes);
-
-// Any 5-D view: dims / box per dimension, strides in ELEMENTS for d1..d4 (d0 contiguous).  Strides may overlap (two
-// dimensions walking the same rows): that is how the weight gradient of the 3-channel head reads a row-expanded
-// gradient tensor as a VIRTUAL im2col matrix (small_wgrad.cc).
-CUtensorMap make_tmap_raw5d(const bf16* base, const long long dims[5], const long long strides_elems[4], const int box[5],
-                            int swizzle_bytes);
 
 // 2-D K-major matrix [rows][cols] bf16 with row pitch `pitch_elems`; box = (box_cols, box_rows).
 CUtensorMap make_tmap_2d(const bf16* base, long long rows, long long cols, long long pitch_elems, int box_cols,

@@ -25,6 +25,17 @@ ConvSpec make_spec(int cin, int cout, int k, int stride, int pad, bool reflect, 
 
 long long align_up(long long v, long long a) { return (v + a - 1) / a * a; }
 
+// The stem's input-side im2col operand of one image set, shared by the stem weight gradients of every pass that reads
+// those images: the row-expanded form [N][S + 8][S][64] read as a virtual im2col matrix (small_wgrad.h), or -- with
+// CGB_VIRTUAL_COL=0 -- the materialised im2col4 matrix [N][S][S][256]
+TensorDesc stem_col(Arena& A, int N, int S) {
+  return small_wgrad_virtual_in(7) ? A.tensor(N, S + 8, S, 64, 0) : A.tensor(N, S, S, 256, 0);
+}
+void build_stem_col(const TensorDesc& image, const TensorDesc& xc, cudaStream_t s) {
+  if (xc.C == 64) expand_rows4(image, 7, +1, -3, true, xc, s);
+  else im2col4(image, 7, 1, +1, -3, true, xc, s);
+}
+
 }  // namespace
 
 cgb_engine::~cgb_engine() {
@@ -224,14 +235,14 @@ void cgb_engine::layout(Arena& A) {
     dx_D0[i] = A.tensor(N, S, S, 16, 0);
   }
   if (pair) {
-    xcol3 = A.tensor(3 * N, S, S, 256, 0);
+    xcol3 = stem_col(A, 3 * N, S);
     xcol[0] = images(xcol3, 0, N);
     xcol[1] = images(xcol3, N, N);
     pair_xcol[0] = images(xcol3, 0, 2 * N);
     pair_xcol[1] = images(xcol3, N, 2 * N);
-    for (int i = 2; i < 4; ++i) xcol[i] = A.tensor(N, S, S, 256, 0);
+    for (int i = 2; i < 4; ++i) xcol[i] = stem_col(A, N, S);
   } else {
-    for (int i = 0; i < 4; ++i) xcol[i] = A.tensor(N, S, S, 256, 0);
+    for (int i = 0; i < 4; ++i) xcol[i] = stem_col(A, N, S);
   }
   for (DisScratch& d : ds) {
     d.dlogits = A.tensor(N, H8 - 2, H8 - 2, 16, 0);
@@ -553,7 +564,7 @@ void cgb_engine::record_programs() {
     float2* st = P.stats;
     pr.add([st, bytes = P.stats_bytes](cudaStream_t s) { CGB_CUDA(cudaMemsetAsync(st, 0, bytes, s)); }, 0, kOpMemset);
     static const bool stem_gemm = std::getenv("CGB_STEM_GEMM") != nullptr;
-    if (xcol_in && stem_gemm && !E->fp32) {
+    if (xcol_in && stem_gemm && !E->fp32 && xcol_in->C == 256) {
       // stem as a plain GEMM over the im2col4 matrix: K = 256 (49 taps x 4 channels, zero padded); superseded by the
       // 16-channel patch-resident conv (the im2col4 matrix still feeds the stem weight gradient)
       LayerParam Lx = L[0];
@@ -588,7 +599,7 @@ void cgb_engine::record_programs() {
         pr.dep(main_lane, xcol_lane);
         pr.cur_lane = xcol_lane;
       }
-      pr.add([out, xc](cudaStream_t s) { im2col4(out, 7, 1, +1, -3, true, xc, s); }, 1, kOpNorm);
+      pr.add([out, xc](cudaStream_t s) { build_stem_col(out, xc, s); }, 1, kOpNorm);
       pr.cur_lane = main_lane;
     }
   };
@@ -870,17 +881,17 @@ void cgb_engine::record_programs() {
       prog_set_inputs.add([sa, ra2](cudaStream_t s) { nchw_to_nhwc(sa, 3, ra2, s); });
       prog_set_inputs_lite.add([sa, ra2](cudaStream_t s) { nchw_to_nhwc(sa, 3, ra2, s); });
       const TensorDesc r3 = reals3, x3 = xcol3;
-      prog_set_inputs.add([r3, x3](cudaStream_t s) { im2col4(r3, 7, 1, +1, -3, true, x3, s); }, 1, kOpNorm);
+      prog_set_inputs.add([r3, x3](cudaStream_t s) { build_stem_col(r3, x3, s); }, 1, kOpNorm);
     } else {
       // one im2col per distinct input image serves the stem forward and the stem weight gradient of every pass
       const TensorDesc xa = xcol[0], xb = xcol[1];
-      prog_set_inputs.add([ra, xa](cudaStream_t s) { im2col4(ra, 7, 1, +1, -3, true, xa, s); }, 1, kOpNorm);
-      prog_set_inputs.add([rb, xb](cudaStream_t s) { im2col4(rb, 7, 1, +1, -3, true, xb, s); }, 1, kOpNorm);
+      prog_set_inputs.add([ra, xa](cudaStream_t s) { build_stem_col(ra, xa, s); }, 1, kOpNorm);
+      prog_set_inputs.add([rb, xb](cudaStream_t s) { build_stem_col(rb, xb, s); }, 1, kOpNorm);
     }
   }
   // im2col4 of a generated image for the pass that consumes it (paired schedule: the fake half of the pair output)
   auto add_xcol = [](Program& pr, const TensorDesc& image, const TensorDesc& xc) {
-    pr.add([image, xc](cudaStream_t s) { im2col4(image, 7, 1, +1, -3, true, xc, s); }, 1, kOpNorm);
+    pr.add([image, xc](cudaStream_t s) { build_stem_col(image, xc, s); }, 1, kOpNorm);
   };
   // pass order: 0 fake_B = G_AB(real_A), 1 rec_A = G_BA(fake_B), 2 fake_A = G_BA(real_B),
   //             3 rec_B = G_AB(fake_A), 4 idt_A = G_AB(real_B), 5 idt_B = G_BA(real_A)

@@ -1273,23 +1273,23 @@ __global__ void im2col4_kernel(DevTensor src, int k, int stride, int sgn, int of
   *reinterpret_cast<uint2*>(dst.p + n * dst.sN + h * dst.sH + w * dst.sW + t * 4) = v;
 }
 
-// one thread per (pixel of dst, horizontal tap s < 8): an 8-byte load (channels 0..3) and an 8-byte store
-__global__ void expand_rows4_kernel(DevTensor src, int k, int sgn, int off, int row_off, DevTensor dst) {
+// one thread per (pixel of dst, half, horizontal tap s < 8): an 8-byte load (channels 0..3) and an 8-byte store
+__global__ void expand_rows4_kernel(DevTensor src, int k, int sgn, int off, int row_off, int lo, DevTensor dst) {
   ptx::pdl_wait();  // launched with programmatic stream serialization (see launch_pdl)
-  const long long total = (long long)dst.N * dst.H * dst.W * 8;
+  const long long total = (long long)dst.N * dst.H * dst.W * 16;
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int s = idx & 7;
-  long long r = idx >> 3;
+  const int s = idx & 7, half = (idx >> 3) & 1;
+  long long r = idx >> 4;
   const int w = r % dst.W;
   r /= dst.W;
   const int hh = r % dst.H;
   const int n = r / dst.H;
-  const int sh = hh + row_off, sw = w + sgn * s + off;
+  const int sh = hh + half + row_off, sw = w + sgn * s + off;
   uint2 v = make_uint2(0u, 0u);
-  if (s < k && sh >= 0 && sh < src.H && sw >= 0 && sw < src.W)
+  if (s < k && sh >= lo && sh < src.H - lo && sw >= lo && sw < src.W - lo)
     v = *reinterpret_cast<const uint2*>(src.p + n * src.sN + sh * src.sH + sw * src.sW);
-  *reinterpret_cast<uint2*>(dst.p + n * dst.sN + hh * dst.sH + w * dst.sW + s * 4) = v;
+  *reinterpret_cast<uint2*>(dst.p + n * dst.sN + hh * dst.sH + w * dst.sW + half * 32 + s * 4) = v;
 }
 
 }  // namespace
@@ -1602,11 +1602,12 @@ void u8hwc_to_nchw(const unsigned char* src, int N, int H, int W, float* dst, cu
   CGB_CUDA(cudaGetLastError());
 }
 
-void expand_rows4(const TensorDesc& src, int k, int sgn, int off, const TensorDesc& dst, cudaStream_t st) {
-  CGB_CHECK(src.C >= 4 && dst.C == 32 && dst.halo == 0 && k <= 8 && src.N == dst.N, "expand_rows4: bad source / destination");
-  const long long total = (long long)dst.N * dst.H * dst.W * 8;
+void expand_rows4(const TensorDesc& src, int k, int sgn, int off, bool use_halo, const TensorDesc& dst, cudaStream_t st) {
+  if (src.esz == 4) return;  // validation mode: the 3-channel weight gradients are computed directly (f32::conv_wgrad)
+  CGB_CHECK(src.C >= 4 && dst.C == 64 && dst.halo == 0 && k <= 8 && src.N == dst.N, "expand_rows4: bad source / destination");
+  const long long total = (long long)dst.N * dst.H * dst.W * 16;
   launch_pdl(expand_rows4_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, st, dev(src), k, sgn, off,
-             sgn > 0 ? off : off - (k - 1), dev(dst));
+             sgn > 0 ? off : off - (k - 1), use_halo ? -src.halo : 0, dev(dst));
 }
 
 void im2col4(const TensorDesc& src, int k, int stride, int sgn, int off, bool use_halo, const TensorDesc& dst,

@@ -103,11 +103,13 @@ void u8hwc_to_nchw(const unsigned char* src, int N, int H, int W, float* dst, cu
 void im2col4(const TensorDesc& src, int k, int stride, int sgn, int off, bool use_halo, const TensorDesc& dst,
              cudaStream_t st);
 
-// Row expansion of a 16-stored-channel tensor with <= 4 real channels: the k horizontal taps only,
-//   dst[n][hh][w][s*4 + c] = src[n][hh + (sgn > 0 ? off : off - (k - 1))][w + sgn*s + off][c],  s < k, c < 4
-// (zero outside src; dst.C == 32, columns >= 4k are written as zeros).  The k vertical taps are NOT materialised: a
-// tensor map with overlapping row strides reads dst rows hh .. hh + k - 1 as the im2col matrix (small_wgrad.cc), which
-// is 8x fewer bytes than im2col4 for the 7x7 layers.
-void expand_rows4(const TensorDesc& src, int k, int sgn, int off, const TensorDesc& dst, cudaStream_t st);
+// Row expansion of a 16-stored-channel tensor with <= 4 real channels: the k horizontal taps of a row AND of the row
+// below it,
+//   dst[n][hh][w][half*32 + s*4 + c] = src[n][hh + half + (sgn > 0 ? off : off - (k - 1))][w + sgn*s + off][c]
+// for half < 2, s < k, c < 4 (zero outside src -- with use_halo the reflect halo of src counts as inside; dst.C == 64,
+// columns with s >= k are written as zeros).  The k vertical taps are NOT materialised: a tensor map whose row-pair
+// dimension (stride two rows) overlaps its height dimension reads rows hh, hh + 2, hh + 4, hh + 6 of dst as the four
+// 64-column atoms of the im2col matrix (small_wgrad.cc): 4x fewer bytes than im2col4 for the 7x7 layers.
+void expand_rows4(const TensorDesc& src, int k, int sgn, int off, bool use_halo, const TensorDesc& dst, cudaStream_t st);
 
 }  // namespace cgb

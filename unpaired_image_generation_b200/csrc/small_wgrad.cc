@@ -12,6 +12,11 @@ static bool virtual_rows_enabled() {
 }
 
 int im2col4_width(int taps) { return taps * 4 <= 64 ? 64 : 256; }
+bool small_wgrad_virtual(int k) { return virtual_rows_enabled() && k >= 5 && k <= 8; }
+bool small_wgrad_virtual_in(int k) {
+  static const bool on = !(std::getenv("CGB_VIRTUAL_COL_IN") && std::atoi(std::getenv("CGB_VIRTUAL_COL_IN")) == 0);
+  return on && small_wgrad_virtual(k);
+}
 
 size_t small_wgrad_col_elems(const ConvSpec& s, const TensorDesc& x, const TensorDesc& dy) {
   const int Kp = im2col4_width(s.taps());
@@ -36,23 +41,45 @@ SmallWgradPlan plan_wgrad_small(const ConvSpec& s, const TensorDesc& x, const Te
   p.k = s.k;
   if (s.Cin <= 4) {
     // im2col on the input side: g[co][(t, ci)] = sum_px dy[px][co] * col[px][t*4 + ci]
+    // 7x7 stem: VIRTUAL im2col -- col is the row-expanded input [N][H + 8][W][64] (expand_rows4, reflect halo
+    // included) and the GEMM's X-side tensor map reads rows h, h + 2, h + 4, h + 6 of it as the four 64-column atoms;
+    // GEMM column j = r * 32 + s * 4 + ci.
+    const bool virt = small_wgrad_virtual_in(s.k) && Kp == 256 && s.stride == 1;
     if (precomputed_col) {
       p.col = *precomputed_col;
       p.col_is_precomputed = true;
-      CGB_CHECK(p.col.N == dy.N && p.col.H == dy.H && p.col.W == dy.W && p.col.C == Kp, "precomputed im2col shape");
+      if (virt)
+        CGB_CHECK(p.col.N == dy.N && p.col.H == dy.H + 8 && p.col.W == dy.W && p.col.C == 64, "precomputed row-expanded shape");
+      else
+        CGB_CHECK(p.col.N == dy.N && p.col.H == dy.H && p.col.W == dy.W && p.col.C == Kp, "precomputed im2col shape");
     } else {
-      CGB_CHECK(small_wgrad_col_elems(s, x, dy) <= colbuf_elems, "im2col scratch too small");
       p.col.ptr = colbuf; p.col.halo = 0;
-      p.col.N = dy.N; p.col.H = dy.H; p.col.W = dy.W; p.col.C = Kp;
+      p.col.N = dy.N; p.col.H = virt ? dy.H + 8 : dy.H; p.col.W = dy.W; p.col.C = virt ? 64 : Kp;
+      CGB_CHECK((size_t)p.col.elems() <= colbuf_elems, "im2col scratch too small");
     }
     p.src = x; p.stride = s.stride; p.sgn = +1; p.off = -s.pad; p.use_halo = s.reflect;
     s1.Cin = Kp; s1.CinS = Kp; s1.Cout = s.Cout; s1.CoutS = s.CoutS;
-    p.gemm = plan_wgrad(s1, p.col, dy, g, sm_count);
+    TensorDesc colx = p.col;  // what the GEMM sees: [N][dy.H][dy.W][Kp]
+    colx.H = dy.H;
+    colx.C = Kp;
+    p.gemm = plan_wgrad(s1, colx, dy, g, sm_count);
     p.gemm.args.Cin = T * s.Cin;  // row length of g
     p.gemm.args.ncols = Kp;
     p.col_map.assign(Kp, -1);
-    for (int j = 0; j < T * 4; ++j)
-      if (j % 4 < s.Cin) p.col_map[j] = (j / 4) * s.Cin + j % 4;
+    if (virt) {
+      p.virtual_rows = true;
+      const int TWk = 1 << p.gemm.args.tw_shift, THk = 64 >> p.gemm.args.tw_shift;
+      const int dims[5] = {64, dy.W, 4, dy.H, dy.N};
+      const long long str[4] = {64, 2LL * dy.W * 64, (long long)dy.W * 64, (long long)p.col.H * dy.W * 64};
+      p.gemm.tmX = make_tmap_act5d(p.col.ptr, dims, str, 64, TWk, THk, 128);
+      p.gemm.args.b_virtual = 1;
+      for (int r = 0; r < s.k; ++r)
+        for (int sx = 0; sx < s.k; ++sx)
+          for (int ci = 0; ci < s.Cin; ++ci) p.col_map[r * 32 + sx * 4 + ci] = (r * s.k + sx) * s.Cin + ci;
+    } else {
+      for (int j = 0; j < T * 4; ++j)
+        if (j % 4 < s.Cin) p.col_map[j] = (j / 4) * s.Cin + j % 4;
+    }
   } else {
     // im2col on the output-gradient side: g[(t, co)][ci] = sum_px col[px][t*4 + co] * x[px][ci]
     CGB_CHECK(s.stride == 1, "strided skinny-output conv");
@@ -72,15 +99,14 @@ SmallWgradPlan plan_wgrad_small(const ConvSpec& s, const TensorDesc& x, const Te
     // dimension overlaps its height dimension.  GEMM row m = r' * 32 + s * 4 + co with r' = k - 1 - r (the expansion
     // is shifted down by k - 1 rows so that every row tap is a non-negative offset).
     if (virtual_rows_enabled() && Kp == 256 && s.k >= 5 && s.k <= 8 &&
-        (size_t)x1.N * (x1.H + 8) * x1.W * 32 <= colbuf_elems) {
+        (size_t)x1.N * (x1.H + 8) * x1.W * 64 <= colbuf_elems) {
       p.virtual_rows = true;
-      p.col.H = x1.H + 8;  // k - 1 rows above, one spare row-tap below; all written by expand_rows4
-      p.col.C = 32;
+      p.col.H = x1.H + 8;  // k - 1 rows above, spare rows below; every element is written by expand_rows4
+      p.col.C = 64;        // per pixel: the 32 expanded columns of its row and of the row below
       const int TWk = 1 << p.gemm.args.tw_shift, THk = 64 >> p.gemm.args.tw_shift;
-      const long long dims[5] = {32, 8, x1.W, x1.H, x1.N};
-      const long long str[4] = {(long long)x1.W * 32, 32, (long long)x1.W * 32, (long long)p.col.H * x1.W * 32};
-      const int box[5] = {32, 2, TWk, THk, 1};
-      p.gemm.tmDY = make_tmap_raw5d(colbuf, dims, str, box, 128);
+      const int dims[5] = {64, x1.W, 4, x1.H, x1.N};
+      const long long str[4] = {64, 2LL * x1.W * 64, (long long)x1.W * 64, (long long)p.col.H * x1.W * 64};
+      p.gemm.tmDY = make_tmap_act5d(colbuf, dims, str, 64, TWk, THk, 128);
       p.gemm.args.a_virtual = 1;
       for (int rp = 0; rp < s.k; ++rp)
         for (int sx = 0; sx < s.k; ++sx)
@@ -95,8 +121,8 @@ SmallWgradPlan plan_wgrad_small(const ConvSpec& s, const TensorDesc& x, const Te
 }
 
 void run(const SmallWgradPlan& p, cudaStream_t stream) {
-  if (p.virtual_rows) expand_rows4(p.src, p.k, p.sgn, p.off, p.col, stream);
-  else if (!p.col_is_precomputed) im2col4(p.src, p.k, p.stride, p.sgn, p.off, p.use_halo, p.col, stream);
+  if (p.virtual_rows && !p.col_is_precomputed) expand_rows4(p.src, p.k, p.sgn, p.off, p.use_halo, p.col, stream);
+  else if (!p.virtual_rows && !p.col_is_precomputed) im2col4(p.src, p.k, p.stride, p.sgn, p.off, p.use_halo, p.col, stream);
   run(p.gemm, stream);
 }
 

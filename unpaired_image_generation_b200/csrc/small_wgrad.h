@@ -18,8 +18,8 @@ struct SmallWgradPlan {
   int k = 0, stride = 1, sgn = 1, off = 0;
   bool use_halo = false;
   bool col_is_precomputed = false;  // the caller keeps `col` up to date (shared stem im2col)
-  // virtual im2col (7x7 head): `col` is the ROW-EXPANDED gradient [N][Hp + 8][Wp][32] (pointwise.h expand_rows4) and the
-  // GEMM's dY-side tensor map reads rows h .. h + 7 of it as the 256 im2col columns (overlapping strides)
+  // virtual im2col (7x7 head and stem): `col` is the ROW-EXPANDED gradient [N][Hp + 8][Wp][64] (pointwise.h expand_rows4) and the
+  // GEMM's dY-side tensor map reads rows h, h + 2, h + 4, h + 6 of it as the four 64-column atoms (overlapping strides)
   bool virtual_rows = false;
   double flops = 0;
 };
@@ -29,6 +29,10 @@ size_t small_wgrad_col_elems(const ConvSpec& s, const TensorDesc& x, const Tenso
 SmallWgradPlan plan_wgrad_small(const ConvSpec& s, const TensorDesc& x, const TensorDesc& dy, float* g, bf16* colbuf,
                                 size_t colbuf_elems, int sm_count, const TensorDesc* precomputed_col = nullptr);
 int im2col4_width(int taps);  // stored columns of an im2col4 matrix: 64 or 256
+// true: k x k layers with <= 4 channels on one side use the virtual im2col (row-expanded tensor [N][H + 8][W][64] read
+// through an overlapping-stride tensor map) instead of a materialised im2col4 matrix; CGB_VIRTUAL_COL=0 disables
+bool small_wgrad_virtual(int k);
+bool small_wgrad_virtual_in(int k);  // ... on the input side (the stem: CGB_VIRTUAL_COL_IN=0 keeps its im2col4 matrix)
 void run(const SmallWgradPlan& p, cudaStream_t stream);
 
 }  // namespace cgb

@@ -58,29 +58,6 @@ CUtensorMap make_tmap_act5d(const bf16* base, const int dims[5], const long long
   return m;
 }
 
-CUtensorMap make_tmap_raw5d(const bf16* base, const long long dims[5], const long long strides_elems[4], const int box[5],
-                            int swizzle_bytes) {
-  CGB_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor base must be 16-byte aligned");
-  CGB_CHECK(box[0] * 2 <= swizzle_bytes && (box[0] * 2) % 16 == 0, "inner box extent must be a multiple of 16 bytes within the swizzle span");
-  CUtensorMap m;
-  cuuint64_t gdim[5], gstr[4];
-  cuuint32_t bx[5], estr[5] = {1, 1, 1, 1, 1};
-  for (int i = 0; i < 5; ++i) {
-    CGB_CHECK(dims[i] > 0 && box[i] > 0 && box[i] <= 256, "tensor-map dim / box out of range");
-    gdim[i] = (cuuint64_t)dims[i];
-    bx[i] = (cuuint32_t)box[i];
-  }
-  for (int i = 0; i < 4; ++i) {
-    gstr[i] = (cuuint64_t)strides_elems[i] * 2;
-    CGB_CHECK(gstr[i] % 16 == 0, "tensor-map stride must be a multiple of 16 bytes");
-  }
-  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<bf16*>(base), gdim, gstr, bx, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, swz(swizzle_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  CGB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(raw 5d) failed with code " + std::to_string((int)r));
-  return m;
-}
-
 CUtensorMap make_tmap_2d(const bf16* base, long long rows, long long cols, long long pitch_elems, int box_cols,
                          int box_rows, int swizzle_bytes) {
   CGB_CHECK(box_cols * 2 == swizzle_bytes, "box_cols must span exactly one swizzle row");
