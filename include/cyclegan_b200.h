@@ -155,6 +155,13 @@ int cgb_run_segment(cgb_engine_t* e, int segment, void* stream);
 int cgb_num_grad_buckets(const cgb_engine_t* e);
 int cgb_grad_bucket_info(const cgb_engine_t* e, int index, int* group, long long* offset, long long* numel);
 int cgb_wait_grad_bucket(cgb_engine_t* e, int index, void* stream);
+/* which layers [layer_lo, layer_hi) of which network a bucket covers (net < 0: a whole parameter group) and its place
+ * in the order the buckets become final (the two generators' buckets alternate: their chains run side by side) */
+int cgb_grad_bucket_layers(const cgb_engine_t* e, int index, int* net, int* layer_lo, int* layer_hi, int* order);
+/* bf16 weight refresh of the layers [layer_lo, layer_hi) of one network only (cgb_refresh_weights does a whole group).
+ * Data parallel: the layers of generator bucket j may be refreshed as soon as bucket j + 1 of the SAME generator is
+ * final (every kernel of the step that reads them has completed by then); the last bucket after the step. */
+int cgb_refresh_weights_layers(cgb_engine_t* e, int net, int layer_lo, int layer_hi, void* stream);
 /* copies the CGB_NUM_LOSSES loss values to host memory (synchronises the stream) */
 int cgb_get_losses_host(cgb_engine_t* e, float* losses_host, void* stream);
 /* end-to-end convenience: pinned/pageable HOST inputs in, losses out (H2D + step + D2H, synchronous) */

@@ -82,7 +82,7 @@ def main():
             same = same and bool(torch.equal(lo, hi))
         ref0 = cgb.Generator(seed=100)  # rank 0's initial G_AB: training must have started from it on every rank
         if rank == 0:
-            print(f"[{precision}] buckets {eng.grad_buckets()}", flush=True)
+            print(f"[{precision}] buckets {[(b['group'], b['net'], b['layer_lo'], b['layer_hi'], b['numel']) for b in eng.grad_bucket_plan()]}", flush=True)
             print(f"[{precision}] weights and Adam state identical across {world} differently seeded ranks after 3 "
                   f"overlapped DP steps: {same}; losses {losses}", flush=True)
         assert same

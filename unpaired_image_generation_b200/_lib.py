@@ -61,6 +61,8 @@ SIGNATURES = {
     "cgb_num_grad_buckets": (c_int, [_P]),
     "cgb_grad_bucket_info": (c_int, [_P, c_int, POINTER(c_int), POINTER(c_longlong), POINTER(c_longlong)]),
     "cgb_wait_grad_bucket": (c_int, [_P, c_int, _P]),
+    "cgb_grad_bucket_layers": (c_int, [_P, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "cgb_refresh_weights_layers": (c_int, [_P, c_int, c_int, c_int, _P]),
     "cgb_get_losses_host": (c_int, [_P, POINTER(c_float), _P]),
     "cgb_train_step_host": (c_int, [_P, _P, _P, POINTER(c_float), _P]),
     "cgb_launches_per_step": (c_longlong, [_P]),

@@ -270,6 +270,28 @@ int cgb_grad_bucket_info(const cgb_engine_t* e, int index, int* group, long long
   CGB_API_END
 }
 
+int cgb_grad_bucket_layers(const cgb_engine_t* e, int index, int* net, int* layer_lo, int* layer_hi, int* order) {
+  CGB_API_BEGIN
+  CGB_CHECK(e && e->bound && index >= 0 && index < (int)e->grad_buckets.size() && net && layer_lo && layer_hi && order,
+            "bad argument / engine not bound");
+  *net = e->grad_buckets[index].net;
+  *layer_lo = e->grad_buckets[index].layer_lo;
+  *layer_hi = e->grad_buckets[index].layer_hi;
+  *order = e->grad_buckets[index].order;
+  CGB_API_END
+}
+
+int cgb_refresh_weights_layers(cgb_engine_t* e, int net, int layer_lo, int layer_hi, void* stream) {
+  CGB_API_BEGIN
+  CGB_CHECK(e && e->bound && net >= 0 && net < 4, "bad argument / engine not bound");
+  const int nl = (int)e->layers[net].size();
+  CGB_CHECK(layer_lo >= 0 && layer_lo <= layer_hi && layer_hi <= nl, "layer range out of bounds");
+  const int g = net < 2 ? CGB_GROUP_G : CGB_GROUP_D;
+  const int first = (net - 2 * g) * nl + layer_lo, count = layer_hi - layer_lo;
+  if (count > 0) pack_weights(e->P[g], e->pack_table[g] + first, count, e->pack_max[g], e->pack[g], S(stream));
+  CGB_API_END
+}
+
 int cgb_wait_grad_bucket(cgb_engine_t* e, int index, void* stream) {
   CGB_API_BEGIN
   CGB_CHECK(e && e->bound && index >= 0 && index < (int)e->grad_buckets.size(), "bad argument / engine not bound");

@@ -1049,7 +1049,7 @@ void cgb_engine::record_programs() {
     const bool dp = !with_adam_d;
     int ev_rec_done[2] = {-1, -1};  // [g]: the rec pass through generator g (G_AB: rec_B, G_BA: rec_A) is complete
     int ev_idt_done[2] = {-1, -1};  // [g]: the identity pass through generator g is complete
-    static const int n_dp_buckets = std::getenv("CGB_DP_BUCKETS") ? std::max(1, std::atoi(std::getenv("CGB_DP_BUCKETS"))) : 3;
+    static const int n_dp_buckets = std::getenv("CGB_DP_BUCKETS") ? std::max(1, std::atoi(std::getenv("CGB_DP_BUCKETS"))) : 4;
     auto bucket_hook = [&](int gnet) {
       return std::function<void(Program&, int, int)>([&, gnet](Program& p, int layer, int other_wlane) {
         if (!dp || fp32 || n_dp_buckets <= 1) return;  // (validation mode: gradients are final after the slot sum)
@@ -1057,7 +1057,9 @@ void cgb_engine::record_programs() {
         // bucket j covers layers [lo_j, lo_{j-1}); lo_0 = end, residual blocks split evenly, the last bucket ends at the stem
         int lo = -1, hi = (int)L.size();
         for (int j = 1; j <= n_dp_buckets; ++j) {
-          const int l = j == n_dp_buckets ? 0 : 3 + 2 * (nb - nb * j / n_dp_buckets);
+          // (boundaries on residual-block starts, spaced so that the LAST bucket -- whose all-reduce cannot overlap
+          // anything -- is the smallest: 4 buckets of a 9-block generator hold 3.9 / 2.4 / 3.5 / 1.6 M parameters)
+          const int l = j == n_dp_buckets ? 0 : 3 + 2 * std::max(0, nb - (j * (nb + 1) + n_dp_buckets / 2) / n_dp_buckets);
           if (l == layer) lo = l;
           if (lo < 0) hi = l;
           if (lo >= 0) break;
@@ -1068,7 +1070,14 @@ void cgb_engine::record_programs() {
         if (ev_idt_done[gnet] >= 0) p.wait(p.cur_lane, ev_idt_done[gnet]);
         const long long net_end = gnet == 0 ? layers[1][0].w_off : group_numel[CGB_GROUP_G];
         const long long off = L[lo].w_off, end = hi < (int)L.size() ? L[hi].w_off : net_end;
-        grad_buckets.push_back({CGB_GROUP_G, off, end - off});
+        int nth = 0;  // how many buckets of this generator came before
+        for (const GradBucket& b : grad_buckets) nth += b.net == gnet;
+        GradBucket gb{CGB_GROUP_G, off, end - off};
+        gb.net = gnet;
+        gb.layer_lo = lo;
+        gb.layer_hi = hi;
+        gb.order = 1 + 2 * nth + gnet;
+        grad_buckets.push_back(gb);
         p.ext_event((int)grad_buckets.size() - 1);
       });
     };
@@ -1234,7 +1243,9 @@ void cgb_engine::record_programs() {
     pr.cur_lane = 0;
     add_sum_slots(pr, CGB_GROUP_G);
     if (dp && (fp32 || n_dp_buckets <= 1)) {  // one bucket: the whole generator group, at the end
-      grad_buckets.push_back({CGB_GROUP_G, 0, group_numel[CGB_GROUP_G]});
+      GradBucket gb{CGB_GROUP_G, 0, group_numel[CGB_GROUP_G]};
+      gb.order = 1;
+      grad_buckets.push_back(gb);
       pr.ext_event((int)grad_buckets.size() - 1);
     }
     pr.mark("step end (before Adam)");

@@ -308,6 +308,8 @@ struct cgb_engine {
   struct GradBucket {
     int group;
     long long offset, numel;  // range of the group's flat gradient buffer
+    int net = -1, layer_lo = 0, layer_hi = 0;  // the layers [lo, hi) of one network it covers (net < 0: the whole group)
+    int order = 0;            // sort key: buckets of the two generators alternate (their backward chains run side by side)
   };
   std::vector<GradBucket> grad_buckets;  // in the order they become ready
   std::vector<cudaEvent_t> grad_events;  // one per bucket

@@ -233,14 +233,30 @@ class StepEngine:
         _lib.check(self.lib.cgb_run_segment(self._h, segment, _stream()))
 
     def grad_buckets(self) -> List[tuple]:
-        """(group, offset, numel) ranges of the flat gradient buffers in the order the data-parallel step
-        (segment 6) announces them as final"""
+        """(group, offset, numel) ranges of the flat gradient buffers announced by the data-parallel step (segment 6),
+        indexed as the C ABI indexes them"""
         out = []
         for i in range(max(0, self.lib.cgb_num_grad_buckets(self._h))):
             g, off, n = ctypes.c_int(), ctypes.c_longlong(), ctypes.c_longlong()
             _lib.check(self.lib.cgb_grad_bucket_info(self._h, i, ctypes.byref(g), ctypes.byref(off), ctypes.byref(n)))
             out.append((int(g.value), int(off.value), int(n.value)))
         return out
+
+    def grad_bucket_plan(self) -> List[dict]:
+        """the buckets in the order they become final, each with the layer range it covers:
+        dict(index, group, offset, numel, net, layer_lo, layer_hi)"""
+        plan = []
+        for i, (g, off, n) in enumerate(self.grad_buckets()):
+            net, lo, hi, order = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+            _lib.check(self.lib.cgb_grad_bucket_layers(self._h, i, ctypes.byref(net), ctypes.byref(lo), ctypes.byref(hi),
+                                                       ctypes.byref(order)))
+            plan.append(dict(index=i, group=g, offset=off, numel=n, net=int(net.value), layer_lo=int(lo.value),
+                             layer_hi=int(hi.value), order=int(order.value)))
+        plan.sort(key=lambda b: b["order"])
+        return plan
+
+    def refresh_weights_layers(self, net: int, layer_lo: int, layer_hi: int):
+        _lib.check(self.lib.cgb_refresh_weights_layers(self._h, net, layer_lo, layer_hi, _stream()))
 
     def wait_grad_bucket(self, index: int):
         """the current stream waits until bucket `index` of the most recently launched segment 6 is final"""

@@ -63,7 +63,7 @@ class CycleGANTrainer:
         self.comm_stream: Optional[torch.cuda.Stream] = None
         self._dp_segmented = bool(os.environ.get("CGB_DP_SEGMENTED"))  # the round-1 segmented data-parallel step
         self._dp_overlap = os.environ.get("CGB_DP_OVERLAP", "1") != "0"
-        self._buckets: List[Tuple[int, int, int]] = []  # (group, offset, numel) in ready order
+        self._buckets: List[dict] = []  # engine.grad_bucket_plan(): gradient ranges in the order they become final
         self._dec_ring: List[Tuple[torch.Tensor, Optional[torch.cuda.Event]]] = []
         self._dec_next = 0
 
@@ -96,7 +96,7 @@ class CycleGANTrainer:
         self.engine = eng
         self.stream = torch.cuda.Stream(device=eng.device)
         self.comm_stream = torch.cuda.Stream(device=eng.device)
-        self._buckets = eng.grad_buckets()
+        self._buckets = eng.grad_bucket_plan()
         if self.pool_size > 0:
             self._dec_ring = [(torch.empty(2, batch, 2, dtype=torch.int32).pin_memory(), None)
                               for _ in range(self._DEC_RING)]
@@ -228,15 +228,29 @@ class CycleGANTrainer:
                     # bucket by bucket: wait until the range is final, all-reduce it, Adam on it -- all while the step
                     # graph keeps running (nothing left in the step reads the fp32 masters of a finished bucket; the
                     # bf16 packs the kernels do read are refreshed after the step)
+                    # The bf16 packs of a generator bucket are refreshed once the NEXT bucket of the same generator is
+                    # final (the chain has then left those layers; the discriminators' right away: nothing reads them
+                    # after their phase); the last bucket of each generator after the whole step.
                     first = [True, True]
-                    for i, (group, off, numel) in enumerate(self._buckets):
-                        eng.wait_grad_bucket(i)
-                        self.sync.all_reduce_(eng.grads[group][off:off + numel])
-                        eng.adam_range(group, off, numel, first[group])
-                        first[group] = False
+                    pending = {}  # net -> bucket whose packs wait for the next bucket of that network
+                    for b in self._buckets:
+                        eng.wait_grad_bucket(b["index"])
+                        prev = pending.pop(b["net"], None)
+                        if prev is not None:
+                            eng.refresh_weights_layers(prev["net"], prev["layer_lo"], prev["layer_hi"])
+                        g, off, numel = b["group"], b["offset"], b["numel"]
+                        self.sync.all_reduce_(eng.grads[g][off:off + numel])
+                        eng.adam_range(g, off, numel, first[g])
+                        first[g] = False
+                        if b["net"] >= 0:
+                            pending[b["net"]] = b
+                        elif g == 1:
+                            eng.refresh_weights(1)
                     comm.wait_event(ev_G)             # the whole step: the conv kernels are done with the old bf16 weights
-                    eng.refresh_weights(1)
-                    eng.refresh_weights(0)
+                    for prev in pending.values():
+                        eng.refresh_weights_layers(prev["net"], prev["layer_lo"], prev["layer_hi"])
+                    if any(b["net"] < 0 and b["group"] == 0 for b in self._buckets):
+                        eng.refresh_weights(0)        # (single-bucket / validation mode: the whole generator group)
                     ev_done.record(comm)
                 else:
                     comm.wait_event(ev_G)
