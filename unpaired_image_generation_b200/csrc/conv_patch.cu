@@ -41,14 +41,23 @@ constexpr int kPatchSmemMax = 232448;
 // KA = channels per patch row: 64 (128-byte rows, SWIZZLE_128B, four K = 16 MMAs per tap) or 16 (the 16-stored-
 // channel image-like tensors: 32-byte rows, SWIZZLE_32B, one MMA per tap).  Weight boxes are always 64 K-elements
 // wide (SWIZZLE_128B): with KA = 16 one box carries four consecutive taps.
-template <int BN, int MT, int KPS, int KA>
+//
+// CG = 2: CTA pairs (cta_group::2, 2-CTA clusters).  The pair computes two M tiles (one per CTA, M = 256 per MMA)
+// against ONE weight tile of which each CTA stages half the rows (BN / 2): the weight bytes streamed from L2 per
+// FLOP -- the limiter of the single-CTA kernel at 148 CTAs (measured: tensor pipe 66 % active, 60 B/clk/SM of weight
+// boxes against the ~43 B/clk/SM the L2 delivers chip-wide) -- and the B-operand shared-memory reads per SM halve.
+// Only the leader (cluster rank 0) issues MMAs; both CTAs run their own patch / weight producers (the peer's TMA
+// bytes are credited to the leader's full barriers) and their own epilogue (each CTA's TMEM holds its own 128 rows).
+template <int BN, int MT, int KPS, int KA, int CG>
 __global__ void __launch_bounds__(224, 1)
 igemm_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const IgemmArgs args, const PatchArgs pa) {
   static_assert(KA == 64 || KA == 16, "patch rows carry 64 or 16 channels");
+  static_assert(CG == 1 || (CG == 2 && BN >= 32), "CTA pairs split the N tile in two");
   constexpr int TPB = 64 / KA;   // taps per weight box
   constexpr int kKK = KA / 16;   // K = 16 MMAs per tap
-  constexpr int kBBytesTx = BN * 128;
+  constexpr int BNL = BN / CG;   // weight rows staged by this CTA
+  constexpr int kBBytesTx = BNL * 128;
   constexpr int kBBytes = (kBBytesTx + 1023) / 1024 * 1024;
   constexpr int kStageBytes = KPS * kBBytes;
   constexpr int kAcc = BN < 32 ? 32 : BN;  // TMEM columns per accumulator
@@ -77,6 +86,7 @@ igemm_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nblk = blockIdx.y;
+  const int rank = CG == 2 ? (int)cluster_ctarank() : 0;  // 0 = leader of the pair
   long long* prof = args.prof ? args.prof + 16 * (blockIdx.x + gridDim.x * blockIdx.y) : nullptr;
   if (prof && threadIdx.x == 0) prof[0] = clock64();
 
@@ -84,9 +94,14 @@ igemm_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int nbox = (T + TPB - 1) / TPB;      // weight boxes per channel chunk
   const int nbs = (nbox + KPS - 1) / KPS;    // weight stages per channel chunk
   // persistent: this CTA owns the M-direction work items blockIdx.x, blockIdx.x + gridDim.x, ...
-  // (a work item is MT stacked tiles of 16 x 8 output pixels of one image)
+  // (a work item is MT stacked tiles of 16 x 8 output pixels of one image).  CTA pairs walk UNITS of two consecutive
+  // items (item = 2 * unit + rank); the second item of the last unit may not exist: the peer then streams an
+  // out-of-range image (TMA zero fill) and skips its epilogue.
   const int items = pa.num_items;
   const int tiles_per_img = args.tiles_w * args.tiles_h;
+  const int unit0 = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int ustep = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int units = CG == 2 ? (items + 1) / 2 : items;
 
   // tables indexed by the WEIGHT tap w (taps are swept in weight order; input gradients read the patch backwards)
   for (int w = threadIdx.x; w < T; w += blockDim.x) {
@@ -106,15 +121,21 @@ igemm_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       mbar_init(&a_full[s], 1);
       mbar_init(&a_empty[s], 1);
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 128);  // every epilogue thread arrives once its TMEM reads are done
+      mbar_init(&tmem_empty_bar[s], 128 * CG);  // every epilogue thread (of both CTAs) arrives once its TMEM reads are done
     }
     fence_mbar_init();
   } else if (warp == 1) {
-    tmem_alloc(tmem_ptr, kTmemCols);
-    tmem_relinquish();
+    if constexpr (CG == 2) {
+      tmem_alloc_pair(tmem_ptr, kTmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_ptr, kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers exist before anything is signalled across the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   pdl_wait();  // everything above overlapped the previous kernel's tail; its outputs are visible from here on
@@ -126,22 +147,30 @@ igemm_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     // ===================== patch producer =====================
     uint32_t ph = 1;  // parity to wait for on a_empty: the first pass over the two buffers does not block
     int ca = 0;
-    for (int item = blockIdx.x; item < items; item += gridDim.x) {
-      const int n = item / tiles_per_img, r = item - n * tiles_per_img;
+    for (int unit = unit0; unit < units; unit += ustep) {
+      const int item = CG == 2 ? 2 * unit + rank : unit;
+      int n = item / tiles_per_img;
+      const int r = item - n * tiles_per_img;
       const int th = r / args.tiles_w, tw = r - th * args.tiles_w;
       const int wo0 = tw * 8, ho0 = th * 16 * MT;
+      if (item >= items) n = args.N;  // missing second item of the last unit: out-of-range image, zero filled
       for (int c = 0; c < pa.chunks; ++c) {
         mbar_wait(&a_empty[ca], ph);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&a_full[ca], MT * pa.nbox * pa.box_bytes);
+          if (rank == 0) mbar_arrive_expect_tx(&a_full[ca], CG * MT * pa.nbox * pa.box_bytes);
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
             uint8_t* dst = patches + (ca * MT + mt) * pa.patch_bytes;
-            for (int b = 0; b < pa.nbox; ++b)
-              tma_load_5d(dst + b * pa.box_bytes, &tmA, &a_full[ca], c * KA, wo0 + pa.ox + b, 0,
-                          ho0 + mt * 16 + pa.oy, n);
+            for (int b = 0; b < pa.nbox; ++b) {
+              if constexpr (CG == 2)
+                tma_load_5d_pair(dst + b * pa.box_bytes, &tmA, &a_full[ca], c * KA, wo0 + pa.ox + b, 0,
+                                 ho0 + mt * 16 + pa.oy, n);
+              else
+                tma_load_5d(dst + b * pa.box_bytes, &tmA, &a_full[ca], c * KA, wo0 + pa.ox + b, 0,
+                            ho0 + mt * 16 + pa.oy, n);
+            }
           }
-          if (prof && c == 0 && item == (int)blockIdx.x) prof[2] = clock64();
+          if (prof && c == 0 && unit == unit0) prof[2] = clock64();
         }
         __syncwarp();
         if (ca == 1) ph ^= 1;
@@ -153,20 +182,23 @@ igemm_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     int s = 0;
     uint32_t ph = 1;
     uint8_t* sb = smem;
-    for (int item = blockIdx.x; item < items; item += gridDim.x) {
-      if (pa.b_resident && item != (int)blockIdx.x) break;  // the whole filter stays in shared memory after the first item
+    for (int unit = unit0; unit < units; unit += ustep) {
+      if (pa.b_resident && unit != unit0) break;  // the whole filter stays in shared memory after the first item
       for (int c = 0; c < pa.chunks; ++c) {
         for (int bs = 0; bs < nbs; ++bs) {
           mbar_wait(&b_empty[s], ph);
           if (elect_one()) {
             const int nk = min(KPS, nbox - bs * KPS);
-            mbar_arrive_expect_tx(&b_full[s], nk * kBBytesTx);
+            if (rank == 0) mbar_arrive_expect_tx(&b_full[s], CG * nk * kBBytesTx);
 #pragma unroll
             for (int j = 0; j < KPS; ++j) {
               if (j < nk) {
                 const int box = bs * KPS + j;
                 const int kcoord = (KA == 64) ? s_bk[box] + c * 64 : box * 64;
-                tma_load_2d(sb + j * kBBytes, &tmB, &b_full[s], kcoord, nblk * BN);
+                if constexpr (CG == 2)
+                  tma_load_2d_pair(sb + j * kBBytes, &tmB, &b_full[s], kcoord, nblk * BN + rank * BNL);
+                else
+                  tma_load_2d(sb + j * kBBytes, &tmB, &b_full[s], kcoord, nblk * BN);
               }
             }
           }
@@ -182,18 +214,19 @@ igemm_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
     if (prof && lane == 0) prof[3] = clock64();
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc_bf16(128, BN < 16 ? 16 : BN, 0, 0);
+    // ===================== MMA issuer (the leader's when CTAs are paired) =====================
+    if (rank == 0) {
+    constexpr uint32_t idesc = make_idesc_bf16(128 * CG, BN < 16 ? 16 : BN, 0, 0);
     constexpr uint32_t desc_hi_b = smem_desc_hi(1024, 2);
     const uint32_t desc_hi_a = smem_desc_hi((uint32_t)pa.sbo, swizzle_layout_type(KA * 2));
-    const uint32_t lo_ring = smem_u32(smem) >> 4;
-    const uint32_t lo_patch = smem_u32(patches) >> 4;
+    const uint32_t lo_ring = (smem_u32(smem) & 0x3FFFFu) >> 4;
+    const uint32_t lo_patch = (smem_u32(patches) & 0x3FFFFu) >> 4;
     const uint32_t patch_units = (uint32_t)pa.patch_bytes >> 4;
     int s = 0, ca = 0, acc_i = 0;
     uint32_t ph = 0, a_ph = 0, e_ph = 1;  // e_ph: parity to wait for on tmem_empty (first use of each set: free)
     uint32_t b_lo0 = lo_ring;
-    for (int item = blockIdx.x; item < items; item += gridDim.x) {
-      mbar_wait(&tmem_empty_bar[acc_i], e_ph);  // the epilogue has drained this accumulator set
+    for (int unit = unit0; unit < units; unit += ustep) {
+      mbar_wait(&tmem_empty_bar[acc_i], e_ph);  // the epilogue (of both CTAs) has drained this accumulator set
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + acc_i * (MT * kAcc);
       uint32_t accumulate = 0;
@@ -220,18 +253,31 @@ igemm_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     const uint32_t a_lo = a_base + mt * patch_units + aoff;
 #pragma unroll
                     for (int kk = 0; kk < kKK; ++kk) {  // K = 16 channels = 32 bytes inside the swizzle atom
-                      umma_bf16(tmem_acc + mt * kAcc, smem_desc_join(a_lo + 2 * kk, desc_hi_a),
-                                smem_desc_join(b_lo + 2 * kk, desc_hi_b), idesc,
-                                (kk == 0 && j == 0 && ts == 0) ? accumulate : 1u);
+                      if constexpr (CG == 2)
+                        umma_bf16_pair(tmem_acc + mt * kAcc, smem_desc_join(a_lo + 2 * kk, desc_hi_a),
+                                       smem_desc_join(b_lo + 2 * kk, desc_hi_b), idesc,
+                                       (kk == 0 && j == 0 && ts == 0) ? accumulate : 1u);
+                      else
+                        umma_bf16(tmem_acc + mt * kAcc, smem_desc_join(a_lo + 2 * kk, desc_hi_a),
+                                  smem_desc_join(b_lo + 2 * kk, desc_hi_b), idesc,
+                                  (kk == 0 && j == 0 && ts == 0) ? accumulate : 1u);
                     }
                   }
                 }
               }
             }
-            if (!pa.b_resident) umma_commit(&b_empty[s]);  // weight slot free once these MMAs retire
-            if (bs == nbs - 1) {
-              umma_commit(&a_empty[ca]);  // ... and the patch buffer after the chunk's last tap
-              if (c == pa.chunks - 1) umma_commit(&tmem_full_bar[acc_i]);
+            if constexpr (CG == 2) {  // the same barriers of BOTH CTAs
+              if (!pa.b_resident) umma_commit_pair(&b_empty[s]);
+              if (bs == nbs - 1) {
+                umma_commit_pair(&a_empty[ca]);
+                if (c == pa.chunks - 1) umma_commit_pair(&tmem_full_bar[acc_i]);
+              }
+            } else {
+              if (!pa.b_resident) umma_commit(&b_empty[s]);  // weight slot free once these MMAs retire
+              if (bs == nbs - 1) {
+                umma_commit(&a_empty[ca]);  // ... and the patch buffer after the chunk's last tap
+                if (c == pa.chunks - 1) umma_commit(&tmem_full_bar[acc_i]);
+              }
             }
           }
           __syncwarp();
@@ -252,6 +298,7 @@ igemm_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
     }
     if (prof && lane == 0) prof[4] = clock64();
+    }  // rank == 0
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
@@ -265,23 +312,26 @@ igemm_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
     int acc_i = 0;
     uint32_t f_ph = 0;
-    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    for (int unit = unit0; unit < units; unit += ustep) {
+      const int item = CG == 2 ? 2 * unit + rank : unit;
       const int n = item / tiles_per_img, r = item - n * tiles_per_img;
       const int th = r / args.tiles_w, tw = r - th * args.tiles_w;
       const int wo0 = tw * 8, ho0 = th * 16 * MT;
       mbar_wait_relaxed(&tmem_full_bar[acc_i], f_ph);
       tc_fence_after();
-      if (item + (int)gridDim.x >= items) pdl_launch_dependents();  // last main loop done: the next kernel may launch
-      if (prof && threadIdx.x == 64 && item == (int)blockIdx.x) prof[5] = clock64();
+      if (unit + ustep >= units) pdl_launch_dependents();  // last main loop done: the next kernel may launch
+      if (prof && threadIdx.x == 64 && unit == unit0) prof[5] = clock64();
       const uint32_t tmem_acc = tmem_base + acc_i * (MT * kAcc);
 #pragma unroll 1
       for (int mt = 0; mt < MT; ++mt) {
-        if (ho0 + mt * 16 >= args.Ho) break;  // ragged CTA row: the stacked tile is entirely outside
+        if (item >= items || ho0 + mt * 16 >= args.Ho) break;  // missing item / ragged CTA row: nothing to write
         epilogue_tile<BN, (BN >= 64 ? 64 : BN)>(args, tmem_acc + mt * kAcc, stage, s_bias, n, ho0 + mt * 16 + (row >> 3),
                                                 wo0 + (row & 7), nblk, args.out_off[0], q, lane, prof);
       }
       tc_fence_before();
-      mbar_arrive(&tmem_empty_bar[acc_i]);  // this thread's TMEM reads of the set are complete
+      // this thread's TMEM reads of the set are complete (the MMA issuer that refills it lives in the leader)
+      if constexpr (CG == 2) mbar_arrive_leader(&tmem_empty_bar[acc_i]);
+      else mbar_arrive(&tmem_empty_bar[acc_i]);
       if (++acc_i == NACC) {
         acc_i = 0;
         f_ph ^= 1;
@@ -292,9 +342,12 @@ igemm_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   tc_fence_before();
   __syncthreads();
   if (prof && threadIdx.x == 0) prof[7] = clock64();
+  // neither CTA of a pair may exit (or free its TMEM) while the other can still read its shared memory / signal its barriers
+  if constexpr (CG == 2) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if constexpr (CG == 2) tmem_dealloc_pair(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -314,12 +367,13 @@ static bool patch_kps1() {
 int igemm_patch_kps(int BN, int ka) { return (ka == 16 || BN >= 256) ? 1 : BN >= 64 ? (patch_kps1() ? 1 : 3) : 7; }
 int igemm_patch_smem_budget() { return patch_smem_cap() - 1024 - kPatchMisc; }
 
-template <int BN, int MT, int KPS, int KA>
+// BN = N tile of the MMA; CG = CTAs per tile pair (1, or 2: each CTA stages BN / 2 weight rows and KPS follows that half)
+template <int BN, int MT, int KPS, int KA, int CG>
 static void launch_patch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmArgs& args, const PatchArgs& pa,
                            dim3 grid, cudaStream_t stream) {
-  constexpr int kBBytes = (BN * 128 + 1023) / 1024 * 1024;
+  constexpr int kBBytes = ((BN / CG) * 128 + 1023) / 1024 * 1024;
   static bool configured = false;
-  auto kern = igemm_patch_kernel<BN, MT, KPS, KA>;
+  auto kern = igemm_patch_kernel<BN, MT, KPS, KA, CG>;
   if (!configured) {
     CGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPatchSmemMax));
     configured = true;
@@ -330,36 +384,65 @@ static void launch_patch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const
   const int ring = pa.b_stages * KPS * kBBytes;
   const int smem = 1024 + ring + 2 * MT * pa.patch_bytes + kPatchMisc;
   CGB_CHECK(smem <= kPatchSmemMax, "patch igemm: shared memory budget exceeded");
-  launch_pdl(kern, grid, dim3(224), (size_t)smem, stream, tmA, tmB, args, pa);
+  if constexpr (CG == 1) {
+    launch_pdl(kern, grid, dim3(224), (size_t)smem, stream, tmA, tmB, args, pa);
+  } else {
+    CGB_CHECK(grid.x % 2 == 0, "patch igemm: CTA pairs need an even grid");
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(224);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    CGB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, args, pa));
+  }
 }
 
-void launch_igemm_patch(int BN, int MT, const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmArgs& args,
+void launch_igemm_patch(int BN, int MT, int CG, const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmArgs& args,
                         const PatchArgs& pa, int num_ctas_m, int n_blocks, cudaStream_t stream) {
   dim3 grid(num_ctas_m, n_blocks, 1);
+  if (CG == 2) {
+    CGB_CHECK(pa.ka == 64, "patch igemm: CTA pairs are built for 64-channel chunks");
+    switch (BN * 10 + MT) {
+      case 2561: return launch_patch_t<256, 1, 3, 64, 2>(tmA, tmB, args, pa, grid, stream);
+      case 1282: return launch_patch_t<128, 2, 3, 64, 2>(tmA, tmB, args, pa, grid, stream);
+      case 1281: return launch_patch_t<128, 1, 3, 64, 2>(tmA, tmB, args, pa, grid, stream);
+      default: break;
+    }
+    CGB_CHECK(false, "launch_igemm_patch: unsupported CTA-pair config BN=" + std::to_string(BN) + " MT=" + std::to_string(MT));
+  }
   if (pa.ka == 16) {
     switch (BN * 10 + MT) {
-      case 2561: return launch_patch_t<256, 1, 1, 16>(tmA, tmB, args, pa, grid, stream);
-      case 1282: return launch_patch_t<128, 2, 1, 16>(tmA, tmB, args, pa, grid, stream);
-      case 1281: return launch_patch_t<128, 1, 1, 16>(tmA, tmB, args, pa, grid, stream);
-      case 642: return launch_patch_t<64, 2, 1, 16>(tmA, tmB, args, pa, grid, stream);
-      case 641: return launch_patch_t<64, 1, 1, 16>(tmA, tmB, args, pa, grid, stream);
+      case 2561: return launch_patch_t<256, 1, 1, 16, 1>(tmA, tmB, args, pa, grid, stream);
+      case 1282: return launch_patch_t<128, 2, 1, 16, 1>(tmA, tmB, args, pa, grid, stream);
+      case 1281: return launch_patch_t<128, 1, 1, 16, 1>(tmA, tmB, args, pa, grid, stream);
+      case 642: return launch_patch_t<64, 2, 1, 16, 1>(tmA, tmB, args, pa, grid, stream);
+      case 641: return launch_patch_t<64, 1, 1, 16, 1>(tmA, tmB, args, pa, grid, stream);
       default: break;
     }
     CGB_CHECK(false, "launch_igemm_patch: unsupported 16-channel config BN=" + std::to_string(BN) + " MT=" + std::to_string(MT));
   }
   switch (BN * 10 + MT) {
-    case 2562: return launch_patch_t<256, 2, 1, 64>(tmA, tmB, args, pa, grid, stream);
-    case 2561: return launch_patch_t<256, 1, 1, 64>(tmA, tmB, args, pa, grid, stream);
-    case 1282: return patch_kps1() ? launch_patch_t<128, 2, 1, 64>(tmA, tmB, args, pa, grid, stream)
-                                   : launch_patch_t<128, 2, 3, 64>(tmA, tmB, args, pa, grid, stream);
-    case 1281: return patch_kps1() ? launch_patch_t<128, 1, 1, 64>(tmA, tmB, args, pa, grid, stream)
-                                   : launch_patch_t<128, 1, 3, 64>(tmA, tmB, args, pa, grid, stream);
-    case 642: return patch_kps1() ? launch_patch_t<64, 2, 1, 64>(tmA, tmB, args, pa, grid, stream)
-                                  : launch_patch_t<64, 2, 3, 64>(tmA, tmB, args, pa, grid, stream);
-    case 641: return patch_kps1() ? launch_patch_t<64, 1, 1, 64>(tmA, tmB, args, pa, grid, stream)
-                                  : launch_patch_t<64, 1, 3, 64>(tmA, tmB, args, pa, grid, stream);
-    case 162: return launch_patch_t<16, 2, 7, 64>(tmA, tmB, args, pa, grid, stream);
-    case 161: return launch_patch_t<16, 1, 7, 64>(tmA, tmB, args, pa, grid, stream);
+    case 2562: return launch_patch_t<256, 2, 1, 64, 1>(tmA, tmB, args, pa, grid, stream);
+    case 2561: return launch_patch_t<256, 1, 1, 64, 1>(tmA, tmB, args, pa, grid, stream);
+    case 1282: return patch_kps1() ? launch_patch_t<128, 2, 1, 64, 1>(tmA, tmB, args, pa, grid, stream)
+                                   : launch_patch_t<128, 2, 3, 64, 1>(tmA, tmB, args, pa, grid, stream);
+    case 1281: return patch_kps1() ? launch_patch_t<128, 1, 1, 64, 1>(tmA, tmB, args, pa, grid, stream)
+                                   : launch_patch_t<128, 1, 3, 64, 1>(tmA, tmB, args, pa, grid, stream);
+    case 642: return patch_kps1() ? launch_patch_t<64, 2, 1, 64, 1>(tmA, tmB, args, pa, grid, stream)
+                                  : launch_patch_t<64, 2, 3, 64, 1>(tmA, tmB, args, pa, grid, stream);
+    case 641: return patch_kps1() ? launch_patch_t<64, 1, 1, 64, 1>(tmA, tmB, args, pa, grid, stream)
+                                  : launch_patch_t<64, 1, 3, 64, 1>(tmA, tmB, args, pa, grid, stream);
+    case 162: return launch_patch_t<16, 2, 7, 64, 1>(tmA, tmB, args, pa, grid, stream);
+    case 161: return launch_patch_t<16, 1, 7, 64, 1>(tmA, tmB, args, pa, grid, stream);
     default: break;
   }
   CGB_CHECK(false, "launch_igemm_patch: unsupported config BN=" + std::to_string(BN) + " MT=" + std::to_string(MT));

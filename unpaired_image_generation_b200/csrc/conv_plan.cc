@@ -190,9 +190,16 @@ static bool try_patch(IgemmPlan& p, const TensorDesc& act, bool padded_view, con
   int best_bn = 0, best_mt = 0, best_stages = 0;
   const int T = k * k;
   bool resident = false;
+  // CTA pairs (cta_group::2, conv_patch.cu): two M tiles share one weight tile, each CTA stages half of its rows.
+  // CGB_PATCH_CG=0 keeps every layer on single CTAs.
+  static const int cg_mode = std::getenv("CGB_PATCH_CG") ? std::atoi(std::getenv("CGB_PATCH_CG")) : 1;
+  auto pair_ok = [&](int bn, int mt) {
+    return cg_mode != 0 && ka == 64 && ((bn == 256 && mt == 1) || bn == 128);
+  };
   auto fits = [&](int bn, int mt, int* stages) {
-    const int kps = igemm_patch_kps(bn, ka);
-    const int stage = kps * ((bn * 128 + 1023) / 1024 * 1024);
+    const bool pr = pair_ok(bn, mt);
+    const int kps = pr ? 3 : igemm_patch_kps(bn, ka);
+    const int stage = kps * (((pr ? bn / 2 : bn) * 128 + 1023) / 1024 * 1024);
     const int budget = igemm_patch_smem_budget() - 2 * mt * pa.patch_bytes;
     int st = budget / stage;
     if (st > 16) st = 16;
@@ -246,6 +253,7 @@ static bool try_patch(IgemmPlan& p, const TensorDesc& act, bool padded_view, con
   p.pargs = pa;
   p.BN = best_bn;
   p.MT = best_mt;
+  p.CG = pair_ok(best_bn, best_mt) ? 2 : 1;
   p.CM = p.CN = 1;
   p.n_blocks = (prow + p.BN - 1) / p.BN;
   p.n_classes = 1;
@@ -258,10 +266,13 @@ static bool try_patch(IgemmPlan& p, const TensorDesc& act, bool padded_view, con
   // the epilogue of one item with the main loop of the next (two TMEM accumulator sets)
   pa.num_items = act.N * tiles_w * p.args.tiles_h;
   p.pargs.num_items = pa.num_items;
-  p.num_ctas_m = std::min(pa.num_items, std::max(1, sm_count / p.n_blocks));
+  if (p.CG == 2)  // pairs walk units of two items; one pair per TPC (two SMs)
+    p.num_ctas_m = 2 * std::min((pa.num_items + 1) / 2, std::max(1, sm_count / p.n_blocks / 2));
+  else
+    p.num_ctas_m = std::min(pa.num_items, std::max(1, sm_count / p.n_blocks));
   p.num_tiles = pa.num_items;
   p.tmA = view_s1(act, padded_view, ka, box_w, pa.PH);
-  p.tmB = make_tmap_2d(w, prow, Kw, Kw, 64, p.BN, 128);
+  p.tmB = make_tmap_2d(w, prow, Kw, Kw, 64, p.BN / p.CG, 128);
   return true;
 }
 
@@ -563,7 +574,7 @@ WgradPlan plan_wgrad(const ConvSpec& s, const TensorDesc& x, const TensorDesc& d
 void run(const IgemmPlan& p, cudaStream_t stream) {
   CGB_CHECK(p.args.kiters != nullptr, "igemm plan has no device K-iteration table");
   if (p.patch) {
-    launch_igemm_patch(p.BN, p.MT, p.tmA, p.tmB, p.args, p.pargs, p.num_ctas_m, p.n_blocks, stream);
+    launch_igemm_patch(p.BN, p.MT, p.CG, p.tmA, p.tmB, p.args, p.pargs, p.num_ctas_m, p.n_blocks, stream);
     return;
   }
   for (int z = 0; z < p.n_classes; ++z) CGB_CHECK(p.args.k_count[z] <= 192, "K-iteration table exceeds the smem staging area");

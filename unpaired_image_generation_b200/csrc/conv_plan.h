@@ -65,6 +65,7 @@ struct IgemmPlan {
   bool patch = false;
   PatchArgs pargs;
   int MT = 1;                 // stacked 16 x 8 M tiles per CTA
+  int CG = 1;                 // 2: CTA pairs (cta_group::2) sharing one weight tile
   int num_ctas_m = 0;
 };
 

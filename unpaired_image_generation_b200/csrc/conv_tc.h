@@ -22,8 +22,9 @@ void launch_igemm(int BN, int BK, int CM, int CN, const CUtensorMap& tmA, const 
 
 
 // Patch-resident variant for stride-1 convs / stride-1 input gradients with 64-channel chunks (conv_patch.cu).
-// MT = M tiles (16 x 8 output pixels each, stacked along h) per CTA; KPS = filter taps per weight stage.
-void launch_igemm_patch(int BN, int MT, const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmArgs& args,
+// MT = M tiles (16 x 8 output pixels each, stacked along h) per CTA; KPS = filter taps per weight stage;
+// CG = 2: CTA pairs (cta_group::2), tmB's box then carries BN / 2 rows and num_ctas_m is even.
+void launch_igemm_patch(int BN, int MT, int CG, const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmArgs& args,
                         const PatchArgs& pa, int num_ctas_m, int n_blocks, cudaStream_t stream);
 int igemm_patch_kps(int BN, int ka);  // weight boxes carried by one stage for this N tile / patch-row width
 int igemm_patch_smem_budget(); // bytes available for the weight ring + patches
