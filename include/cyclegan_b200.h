@@ -196,6 +196,13 @@ int cgb_conv_layer_test(int n, int h, int w, int cin, int cout, int k, int strid
  * the halo writer); `out` receives its interior.  da: gradient w.r.t. out; dy_out: gradient w.r.t. y. */
 int cgb_instnorm_test(int n, int c, int h, int w, int act, const float* y, const float* residual, const float* da,
                       float* out, float* dy_out);
+/* InstanceNorm(+act) backward with the gradient sources the step uses: g1 (gradient w.r.t. the activation,
+ * [n][c][h][w], may be NULL) and g2 (gradient w.r.t. the REFLECT-PADDED activation, [n][c][h+2*fold][w+2*fold],
+ * may be NULL; its halo pixels are folded onto their mirror images).  dy_out: gradient w.r.t. y;
+ * da_out (may be NULL): the assembled, bf16-rounded gradient w.r.t. the activation (the residual skip path).
+ * force_two_pass != 0 skips the cluster-fused kernel so that the reduce + apply pair is exercised. */
+int cgb_instnorm_bwd_test(int n, int c, int h, int w, int act, int fold, int force_two_pass, const float* y,
+                          const float* g1, const float* g2, float* dy_out, float* da_out);
 /* The same two harnesses through the fp32 validation kernels (csrc/fp32_path.h). */
 int cgb_conv_layer_test_f32(int n, int h, int w, int cin, int cout, int k, int stride, int pad, int reflect,
                             int transposed, int act, const float* x, const float* weight, const float* bias,

@@ -154,6 +154,41 @@ def test_instance_norm_forward_backward(act, residual, shape):
     assert rel(dyo, y.grad) < 1e-2
 
 
+# InstanceNorm backward with the gradient sources of the real step: g1 (plain), g2 (gradient w.r.t. the reflect-padded
+# activation, folded onto the mirror pixels), both, and the stored skip-path gradient `da`; through the cluster-fused
+# kernel where it applies and through the reduce + apply pair (two_pass = 1: the path large maps / batches take).
+@pytest.mark.parametrize("act,fold,use_g1,two_pass,shape", [
+    (3, 1, False, 1, (2, 256, 64)), (0, 1, True, 1, (2, 256, 64)), (3, 3, False, 1, (1, 64, 256)),
+    (3, 1, True, 0, (1, 256, 64)), (1, 0, True, 1, (1, 512, 31)), (3, 0, True, 1, (2, 128, 128)),
+    (3, 3, True, 1, (2, 64, 40))])
+def test_instance_norm_backward_with_folded_halo_gradient(act, fold, use_g1, two_pass, shape):
+    _need_gpu()
+    lib = _lib.load()
+    gen = torch.Generator().manual_seed(11)
+    n, c, h = shape
+    y = bf(torch.randn(n, c, h, h, generator=gen) * 2 + 0.5).requires_grad_(True)
+    g1 = bf(torch.randn(n, c, h, h, generator=gen)) if use_g1 else None
+    g2 = bf(torch.randn(n, c, h + 2 * fold, h + 2 * fold, generator=gen)) if fold > 0 else None
+    out = F.instance_norm(y, eps=1e-5)
+    out = F.relu(out) if act == 3 else (F.leaky_relu(out, 0.2) if act == 1 else out)
+    out.retain_grad()
+    loss = 0.0
+    if g1 is not None:
+        loss = loss + (out * g1).sum()
+    if g2 is not None:
+        loss = loss + (F.pad(out, (fold,) * 4, mode="reflect") * g2).sum()
+    loss.backward()
+    dyo = torch.empty(n, c, h, h, device="cuda")
+    dao = torch.empty(n, c, h, h, device="cuda")
+    yd = y.detach().cuda()                       # keep the device copies alive across the call
+    g1d = g1.cuda() if g1 is not None else None
+    g2d = g2.cuda() if g2 is not None else None
+    _lib.check(lib.cgb_instnorm_bwd_test(n, c, h, h, act, fold, two_pass, _p(yd), _p(g1d), _p(g2d), _p(dyo), _p(dao)))
+    r_da, r_dy = rel(dao, out.grad), rel(dyo, y.grad)
+    assert r_da < 5e-3, r_da     # the assembled activation gradient (bf16-rounded)
+    assert r_dy < 1e-2, r_dy
+
+
 # ------------------------------------------------------------------------------------------------
 # modules and the training step
 # ------------------------------------------------------------------------------------------------

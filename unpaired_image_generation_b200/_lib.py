@@ -71,6 +71,7 @@ SIGNATURES = {
     "cgb_profile_timeline": (c_int, [_P, _P, c_char_p, c_int]),
     "cgb_conv_layer_test": (c_int, [c_int] * 11 + [_P] * 8),
     "cgb_instnorm_test": (c_int, [c_int] * 5 + [_P] * 5),
+    "cgb_instnorm_bwd_test": (c_int, [c_int] * 7 + [_P] * 5),
     "cgb_conv_layer_test_f32": (c_int, [c_int] * 11 + [_P] * 8),
     "cgb_instnorm_test_f32": (c_int, [c_int] * 5 + [_P] * 5),
 }

@@ -616,6 +616,43 @@ int cgb_instnorm_test(int n, int c, int h, int w, int act, const float* y, const
   CGB_API_END
 }
 
+int cgb_instnorm_bwd_test(int n, int c, int h, int w, int act, int fold, int force_two_pass, const float* y,
+                          const float* g1, const float* g2, float* dy_out, float* da_out) {
+  CGB_API_BEGIN
+  CGB_CHECK(y && dy_out && (g1 || g2), "y, dy_out and at least one gradient source are required");
+  CGB_CHECK(c % 8 == 0, "channels must be a multiple of 8");
+  Scratch sc;
+  TensorDesc Y = sc.tensor(n, h, w, c, 0);
+  TensorDesc DY = sc.tensor(n, h, w, c, 0);
+  float2* stats = static_cast<float2*>(sc.alloc((size_t)n * c * sizeof(float2)));
+  float2* bstats = static_cast<float2*>(sc.alloc((size_t)n * c * sizeof(float2)));
+  nchw_to_nhwc(y, c, Y, 0);
+  in_stats(Y, stats, 0);
+  TensorDesc G1, G2, DA;
+  GradSrc g;
+  if (g1) {
+    G1 = sc.tensor(n, h, w, c, 0);
+    nchw_to_nhwc(g1, c, G1, 0);
+    g.g1 = &G1;
+  }
+  if (g2) {
+    G2 = sc.tensor(n, h + 2 * fold, w + 2 * fold, c, 0);
+    nchw_to_nhwc(g2, c, G2, 0);
+    g.g2 = &G2;
+    g.fold = fold;
+  }
+  if (da_out) DA = sc.tensor(n, h, w, c, 0);
+  if (force_two_pass || !in_bwd_fused(Y, stats, g, act, da_out ? &DA : nullptr, DY, 0)) {
+    CGB_CUDA(cudaMemsetAsync(bstats, 0, (size_t)n * c * sizeof(float2), 0));
+    in_bwd_reduce(Y, stats, g, act, da_out ? &DA : nullptr, bstats, 0);
+    in_bwd_apply(Y, stats, bstats, g, act, DY, 0);
+  }
+  nhwc_to_nchw(DY, c, dy_out, 0);
+  if (da_out) nhwc_to_nchw(DA, c, da_out, 0);
+  CGB_CUDA(cudaDeviceSynchronize());
+  CGB_API_END
+}
+
 int cgb_conv_layer_test_f32(int n, int h, int w, int cin, int cout, int k, int stride, int pad, int reflect,
                             int transposed, int act, const float* x, const float* weight, const float* bias,
                             const float* dy, float* y, float* dx, float* dw, float* db) {

@@ -995,6 +995,299 @@ in_bwd_fused_kernel(DevTensor y, const float2* __restrict__ stats, DevGrad g, in
   ptx::cluster_sync_all();  // no CTA may exit while a peer can still read its partial sums
 }
 
+// ------------------------------------------------------------------------------------------ row-streaming variants
+// The kernels above walk a flat pixel range with 64-bit (n, h, w) addressing, runtime activation / gradient-source
+// switches and per-pixel border tests: ncu (profiles/r02_o_ncu_pointwise_b8.txt) shows them ISSUE-bound, not memory-
+// bound -- 55-62 % issue-slot utilisation at 25 % occupancy (117-120 registers), 1.6-3 TB/s, ~500 SASS instructions per
+// 16-byte vector.  Here a block owns whole image rows: an interior row of any tensor is contiguous (W * C elements),
+// thread t handles the vectors t, t + 256, ... of the row, so its channel vector is fixed (C divides 2048), the
+// addresses inside a row are one 32-bit multiply-add, and activation / gradient sources / residual are template
+// parameters.  The reflect-halo writer (apply) and the halo fold (backward) touch the few border pixels in a
+// separate, rarely taken branch.
+template <int ACT>
+__device__ __forceinline__ float act_fwd_t(float x) {
+  if (ACT == kActRelu) return fmaxf(x, 0.f);
+  if (ACT == kActLeaky) return x > 0.f ? x : 0.2f * x;
+  return x;
+}
+template <int ACT>
+__device__ __forceinline__ float act_grad_t(float x) {
+  if (ACT == kActRelu) return x > 0.f ? 1.f : 0.f;
+  if (ACT == kActLeaky) return x > 0.f ? 1.f : 0.2f;
+  return 1.f;
+}
+// mirror partner of interior index i inside a reflect halo of width p (interior extent n): -1 when i has none
+__device__ __forceinline__ bool mirror_of(int i, int n, int p, int* m) {
+  if (i >= 1 && i <= p) {
+    *m = -i;
+    return true;
+  }
+  if (i >= n - 1 - p && i <= n - 2) {
+    *m = 2 * (n - 1) - i;
+    return true;
+  }
+  return false;
+}
+
+struct RowSpan {  // rows [h0, h1) of image n and the item range [j0, j1) of this block inside every row
+  int h0, h1, j0, j1;
+};
+// grid.x = ceil(H / rpb) * jsplit: a block takes rpb rows (jsplit == 1) or a 1 / jsplit slice of one row
+__device__ __forceinline__ RowSpan row_span(int H, int vpr, int rpb, int jsplit) {
+  RowSpan r;
+  const int u = blockIdx.x / jsplit, js = blockIdx.x - u * jsplit;
+  r.h0 = u * rpb;
+  r.h1 = min(H, r.h0 + rpb);
+  const int J = (vpr + 255) >> 8;
+  const int jper = (J + jsplit - 1) / jsplit;
+  r.j0 = js * jper;
+  r.j1 = min(J, r.j0 + jper);
+  return r;
+}
+
+template <int ACT, bool RES, int PPT>
+__global__ void __launch_bounds__(256, 3)
+in_apply_rows_kernel(DevTensor y, const float2* __restrict__ stats, DevTensor res, DevTensor out, int vpr, int rpb,
+                     int jsplit) {
+  ptx::pdl_wait();
+  if (kPwTrigger) ptx::pdl_launch_dependents();
+  const int t = threadIdx.x, n = blockIdx.y;
+  const int C = out.C, H = out.H, W = out.W, p = out.halo;
+  const int lanes = C >> 3, rows = 256 / lanes, prow = t / lanes;
+  const int c0 = (t - prow * lanes) * 8;
+  const RowSpan sp = row_span(H, vpr, rpb, jsplit);
+  float a[8], b[8];
+  load_norm8(stats, (long long)n * C + c0, 1.f / (float)(H * W), a, b);
+  for (int h = sp.h0; h < sp.h1; ++h) {
+    const bf16* yrow = y.p + n * y.sN + h * y.sH;
+    const bf16* rrow = RES ? res.p + n * res.sN + h * res.sH : nullptr;
+    bf16* orow = out.p + n * out.sN + h * out.sH;
+    int hm = 0;
+    const bool hb = p > 0 && mirror_of(h, H, p, &hm);
+    bf16* mrow = out.p + n * out.sN + (long long)hm * out.sH;
+#pragma unroll 1
+    for (int j = sp.j0; j < sp.j1; j += PPT) {
+      uint4 raw[PPT], rr[PPT];
+      bool ok[PPT];
+#pragma unroll
+      for (int k = 0; k < PPT; ++k) {
+        const int v = t + ((j + k) << 8);
+        ok[k] = (j + k < sp.j1) && v < vpr;
+        if (ok[k]) {
+          raw[k] = *reinterpret_cast<const uint4*>(yrow + v * 8);
+          if (RES) rr[k] = *reinterpret_cast<const uint4*>(rrow + v * 8);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < PPT; ++k) {
+        if (!ok[k]) continue;
+        float v[8];
+        unpack8(raw[k], v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = act_fwd_t<ACT>(fmaf(v[i], a[i], b[i]));
+        if (RES) {
+          float rv[8];
+          unpack8(rr[k], rv);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] += rv[i];
+        }
+        const int w = prow + (j + k) * rows;
+        const int eo = (t + ((j + k) << 8)) * 8;  // == w * C + c0
+        store8(orow + eo, v);
+        if (p > 0) {  // this pixel is the mirror image of up to three halo pixels
+          int wm = 0;
+          const bool wb = mirror_of(w, W, p, &wm);
+          if (wb) store8(orow + wm * C + c0, v);
+          if (hb) {
+            store8(mrow + eo, v);
+            if (wb) store8(mrow + wm * C + c0, v);
+          }
+        }
+      }
+    }
+  }
+}
+
+// gradient w.r.t. the activation of one item: g1 + g2 (+ the mirrored halo pixels of the padded-domain source g2)
+template <bool G1, bool G2>
+__device__ __forceinline__ void rows_grad(const uint4& g1raw, const uint4& g2raw, const bf16* g2img, long long g2sH, int C,
+                                          int c0, int h, int w, int H, int W, int p, bool hb, int hm, float (&gr)[8]) {
+  if (G1) {
+    unpack8(g1raw, gr);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) gr[i] = 0.f;
+  }
+  if (G2) {
+    float v[8];
+    unpack8(g2raw, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) gr[i] += v[i];
+    const bool wb = (w >= 1 && w <= p) || (w >= W - 1 - p && w <= W - 2);
+    if (hb || wb) {
+      const int wm = (w >= 1 && w <= p) ? p - w : 2 * (W - 1) - w + p;  // padded-domain column of the mirror
+      if (hb) {
+        load8(g2img + hm * g2sH + (w + p) * C + c0, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) gr[i] += v[i];
+      }
+      if (wb) {
+        load8(g2img + (h + p) * g2sH + wm * C + c0, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) gr[i] += v[i];
+      }
+      if (hb && wb) {
+        load8(g2img + hm * g2sH + wm * C + c0, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) gr[i] += v[i];
+      }
+    }
+  }
+}
+
+template <int ACT, bool G1, bool G2, bool DA, int PPT>
+__global__ void __launch_bounds__(256, 3)
+in_bwd_reduce_rows_kernel(DevTensor y, const float2* __restrict__ stats, DevGrad g, DevTensor da,
+                          float* __restrict__ bstats, int vpr, int rpb) {
+  ptx::pdl_wait();
+  if (kPwTrigger) ptx::pdl_launch_dependents();
+  __shared__ float red[256 * 16];
+  const int t = threadIdx.x, n = blockIdx.y;
+  const int C = y.C, H = y.H, W = y.W, p = g.fold;
+  const int lanes = C >> 3, rows = 256 / lanes, prow = t / lanes, cl = t - prow * lanes;
+  const int c0 = cl * 8;
+  const RowSpan sp = row_span(H, vpr, rpb, 1);
+  float a[8], b[8], s1[8], s2[8];
+  load_norm8(stats, (long long)n * C + c0, 1.f / (float)(H * W), a, b);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
+  const bf16* g2img = G2 ? g.g2.p + n * g.g2.sN : nullptr;
+  for (int h = sp.h0; h < sp.h1; ++h) {
+    const bf16* yrow = y.p + n * y.sN + h * y.sH;
+    const bf16* g1row = G1 ? g.g1.p + n * g.g1.sN + h * g.g1.sH : nullptr;
+    const bf16* g2row = G2 ? g2img + (h + p) * g.g2.sH + p * C : nullptr;
+    bf16* darow = DA ? da.p + n * da.sN + h * da.sH : nullptr;
+    const bool hb = G2 && ((h >= 1 && h <= p) || (h >= H - 1 - p && h <= H - 2));
+    const int hm = (h >= 1 && h <= p) ? p - h : 2 * (H - 1) - h + p;  // padded-domain row of the mirror
+#pragma unroll 1
+    for (int j = sp.j0; j < sp.j1; j += PPT) {
+      uint4 yraw[PPT], g1raw[PPT], g2raw[PPT];
+      bool ok[PPT];
+#pragma unroll
+      for (int k = 0; k < PPT; ++k) {
+        const int v = t + ((j + k) << 8);
+        ok[k] = (j + k < sp.j1) && v < vpr;
+        if (ok[k]) {
+          yraw[k] = *reinterpret_cast<const uint4*>(yrow + v * 8);
+          if (G1) g1raw[k] = *reinterpret_cast<const uint4*>(g1row + v * 8);
+          if (G2) g2raw[k] = *reinterpret_cast<const uint4*>(g2row + v * 8);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < PPT; ++k) {
+        if (!ok[k]) continue;
+        float v[8], gr[8];
+        rows_grad<G1, G2>(g1raw[k], g2raw[k], g2img, g.g2.sH, C, c0, h, prow + (j + k) * rows, H, W, p, hb, hm, gr);
+        if (DA) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) gr[i] = round_bf16(gr[i]);
+          store8(darow + (t + ((j + k) << 8)) * 8, gr);
+        }
+        unpack8(yraw[k], v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xh = fmaf(v[i], a[i], b[i]);
+          const float dz = gr[i] * act_grad_t<ACT>(xh);
+          s1[i] += dz;
+          s2[i] = fmaf(dz, xh, s2[i]);
+        }
+      }
+    }
+  }
+  // the block's pixel slots that share a channel vector -> shared memory -> one vector atomic per channel pair
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    red[t * 16 + i] = s1[i];
+    red[t * 16 + 8 + i] = s2[i];
+  }
+  __syncthreads();
+  if (prow == 0) {
+    for (int r = 1; r < rows; ++r) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s1[i] += red[(r * lanes + cl) * 16 + i];
+        s2[i] += red[(r * lanes + cl) * 16 + 8 + i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i += 2)
+      red_add_v4(bstats + ((long long)n * C + c0 + i) * 2, s1[i], s2[i], s1[i + 1], s2[i + 1]);
+  }
+}
+
+template <int ACT, bool G1, bool G2, int PPT>
+__global__ void __launch_bounds__(256, 3)
+in_bwd_apply_rows_kernel(DevTensor y, const float2* __restrict__ stats, const float2* __restrict__ bstats, DevGrad g,
+                         DevTensor dy, int vpr, int rpb, int jsplit) {
+  ptx::pdl_wait();
+  if (kPwTrigger) ptx::pdl_launch_dependents();
+  const int t = threadIdx.x, n = blockIdx.y;
+  const int C = y.C, H = y.H, W = y.W, p = g.fold;
+  const int lanes = C >> 3, rows = 256 / lanes, prow = t / lanes;
+  const int c0 = (t - prow * lanes) * 8;
+  const RowSpan sp = row_span(H, vpr, rpb, jsplit);
+  // dy = rstd * (dz - mean(dz) - xhat * mean(dz * xhat)) = a * dz - c - d * xhat
+  float a[8], b[8], c[8], d[8];
+  const float inv = 1.f / (float)(H * W);
+  load_norm8(stats, (long long)n * C + c0, inv, a, b);
+#pragma unroll
+  for (int i = 0; i < 8; i += 2) {
+    const float4 bs = __ldg(reinterpret_cast<const float4*>(bstats + (long long)n * C + c0 + i));
+    c[i] = a[i] * bs.x * inv;
+    d[i] = a[i] * bs.y * inv;
+    c[i + 1] = a[i + 1] * bs.z * inv;
+    d[i + 1] = a[i + 1] * bs.w * inv;
+  }
+  const bf16* g2img = G2 ? g.g2.p + n * g.g2.sN : nullptr;
+  for (int h = sp.h0; h < sp.h1; ++h) {
+    const bf16* yrow = y.p + n * y.sN + h * y.sH;
+    const bf16* g1row = G1 ? g.g1.p + n * g.g1.sN + h * g.g1.sH : nullptr;
+    const bf16* g2row = G2 ? g2img + (h + p) * g.g2.sH + p * C : nullptr;
+    bf16* dyrow = dy.p + n * dy.sN + h * dy.sH;
+    const bool hb = G2 && ((h >= 1 && h <= p) || (h >= H - 1 - p && h <= H - 2));
+    const int hm = (h >= 1 && h <= p) ? p - h : 2 * (H - 1) - h + p;
+#pragma unroll 1
+    for (int j = sp.j0; j < sp.j1; j += PPT) {
+      uint4 yraw[PPT], g1raw[PPT], g2raw[PPT];
+      bool ok[PPT];
+#pragma unroll
+      for (int k = 0; k < PPT; ++k) {
+        const int v = t + ((j + k) << 8);
+        ok[k] = (j + k < sp.j1) && v < vpr;
+        if (ok[k]) {
+          yraw[k] = *reinterpret_cast<const uint4*>(yrow + v * 8);
+          if (G1) g1raw[k] = *reinterpret_cast<const uint4*>(g1row + v * 8);
+          if (G2) g2raw[k] = *reinterpret_cast<const uint4*>(g2row + v * 8);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < PPT; ++k) {
+        if (!ok[k]) continue;
+        float v[8], gr[8];
+        rows_grad<G1, G2>(g1raw[k], g2raw[k], g2img, g.g2.sH, C, c0, h, prow + (j + k) * rows, H, W, p, hb, hm, gr);
+        unpack8(yraw[k], v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xh = fmaf(v[i], a[i], b[i]);
+          const float dz = gr[i] * act_grad_t<ACT>(xh);
+          v[i] = fmaf(a[i], dz, -c[i]) - d[i] * xh;
+        }
+        store8(dyrow + (t + ((j + k) << 8)) * 8, v);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ head / losses
 __device__ __forceinline__ float block_sum(float v) {
   __shared__ float sh[32];
@@ -1362,9 +1655,57 @@ static int stream_ppb(long long pixels, int rows, int ppt, int images) {
   return (int)std::max<long long>(ppb, unit);
 }
 
+// Row-streaming kernels (CGB_PW_ROWS=0 falls back to the flat-range kernels): channel counts that divide 2048
+// (8 .. 2048, powers of two) with a halo / fold narrower than the map.
+static bool rows_enabled() {
+  static const bool on = !(std::getenv("CGB_PW_ROWS") && std::atoi(std::getenv("CGB_PW_ROWS")) == 0);
+  return on;
+}
+static bool rows_ok(const TensorDesc& y, int border) {
+  return rows_enabled() && y.esz == 2 && y.C >= 8 && y.C <= 2048 && (y.C & (y.C - 1)) == 0 && 2 * border + 2 <= y.H &&
+         2 * border + 2 <= y.W;
+}
+// rows per block (and, when the whole batch has fewer rows than the machine holds blocks, slices per row) for a
+// launch that should fill 148 SMs x 3 resident blocks about `waves` times; max_bpi caps the blocks per image
+static void rows_grid(int H, int N, int vpr, int max_bpi, int* rpb, int* jsplit) {
+  const long long R = (long long)H * N;
+  const int want = 148 * 3 * 2;
+  int r = (int)std::max<long long>(1, R / want);
+  if (max_bpi > 0) r = std::max(r, (H + max_bpi - 1) / max_bpi);
+  int js = 1;
+  if (max_bpi == 0 && r == 1) {
+    const int J = (vpr + 255) / 256;
+    while (js * 2 <= J && R * js * 2 <= 148 * 3) js *= 2;
+  }
+  *rpb = r;
+  *jsplit = js;
+}
+#define CGB_ACT_SWITCH(act, CALL)                              \
+  switch (act) {                                               \
+    case kActNone: { constexpr int ACT = kActNone; CALL; } break;   \
+    case kActLeaky: { constexpr int ACT = kActLeaky; CALL; } break; \
+    case kActRelu: { constexpr int ACT = kActRelu; CALL; } break;   \
+    default: CGB_CHECK(false, "InstanceNorm kernels: unsupported activation");  \
+  }
+
 void in_apply(const TensorDesc& y, const float2* stats, int act, const TensorDesc* residual, const TensorDesc& out,
               cudaStream_t st) {
   CGB_CHECK(y.C == out.C && y.H == out.H && y.W == out.W && y.N == out.N, "in_apply: shape mismatch");
+  if (rows_ok(out, out.halo) && (act == kActNone || act == kActLeaky || act == kActRelu)) {
+    const int vpr = out.W * out.C / 8;
+    int rpb, jsplit;
+    rows_grid(out.H, out.N, vpr, 0, &rpb, &jsplit);
+    dim3 grid((out.H + rpb - 1) / rpb * jsplit, out.N);
+    const DevTensor r = residual ? dev(*residual) : dev_null();
+    if (residual) {
+      CGB_ACT_SWITCH(act, (launch_pdl(in_apply_rows_kernel<ACT, true, 4>, grid, dim3(256), 0, st, dev(y), stats, r, dev(out),
+                                      vpr, rpb, jsplit)));
+    } else {
+      CGB_ACT_SWITCH(act, (launch_pdl(in_apply_rows_kernel<ACT, false, 4>, grid, dim3(256), 0, st, dev(y), stats, r, dev(out),
+                                      vpr, rpb, jsplit)));
+    }
+    return;
+  }
   const int total = (out.H + 2 * out.halo) * (out.W + 2 * out.halo);
   const int lanes = std::min(256, out.C / 8), rows = 256 / lanes;
   int appb;
@@ -1468,6 +1809,28 @@ bool in_bwd_fused(const TensorDesc& y, const float2* stats, const GradSrc& g, in
 void in_bwd_reduce(const TensorDesc& y, const float2* stats, const GradSrc& g, int act, const TensorDesc* da_out,
                    float2* bstats, cudaStream_t st) {
   check_grad(y, g);
+  if (rows_ok(y, g.g2 ? g.fold : 0) && (act == kActNone || act == kActLeaky || act == kActRelu)) {
+    const int vpr = y.W * y.C / 8;
+    int rpb, jsplit;
+    rows_grid(y.H, y.N, vpr, 64, &rpb, &jsplit);  // <= 64 blocks per image end in atomics on the same statistics
+    dim3 grid((y.H + rpb - 1) / rpb, y.N);
+    const DevTensor dat = da_out ? dev(*da_out) : dev_null();
+    float* bs = reinterpret_cast<float*>(bstats);
+#define CGB_RED_LAUNCH(G1, G2, DA) \
+  CGB_ACT_SWITCH(act, (launch_pdl(in_bwd_reduce_rows_kernel<ACT, G1, G2, DA, 2>, grid, dim3(256), 0, st, dev(y), stats, dev(g), dat, bs, vpr, rpb)))
+    const int key = (g.g1 ? 4 : 0) | (g.g2 ? 2 : 0) | (da_out ? 1 : 0);
+    switch (key) {
+      case 4: CGB_RED_LAUNCH(true, false, false); break;
+      case 5: CGB_RED_LAUNCH(true, false, true); break;
+      case 2: CGB_RED_LAUNCH(false, true, false); break;
+      case 3: CGB_RED_LAUNCH(false, true, true); break;
+      case 6: CGB_RED_LAUNCH(true, true, false); break;
+      case 7: CGB_RED_LAUNCH(true, true, true); break;
+      default: CGB_CHECK(false, "in_bwd_reduce: no gradient source");
+    }
+#undef CGB_RED_LAUNCH
+    return;
+  }
   const int HW = y.H * y.W;
   const int lanes = std::min(256, y.C / 8), rows = 256 / lanes;
   // every block ends with one atomic per channel on the image's (sum dz, sum dz*xhat) pair: at most 64 blocks
@@ -1495,6 +1858,23 @@ void in_bwd_reduce(const TensorDesc& y, const float2* stats, const GradSrc& g, i
 void in_bwd_apply(const TensorDesc& y, const float2* stats, const float2* bstats, const GradSrc& g, int act,
                   const TensorDesc& dy, cudaStream_t st) {
   check_grad(y, g);
+  if (rows_ok(y, g.g2 ? g.fold : 0) && (act == kActNone || act == kActLeaky || act == kActRelu)) {
+    const int vpr = y.W * y.C / 8;
+    int rpb, jsplit;
+    rows_grid(y.H, y.N, vpr, 0, &rpb, &jsplit);
+    dim3 grid((y.H + rpb - 1) / rpb * jsplit, y.N);
+#define CGB_APP_LAUNCH(G1, G2) \
+  CGB_ACT_SWITCH(act, (launch_pdl(in_bwd_apply_rows_kernel<ACT, G1, G2, 2>, grid, dim3(256), 0, st, dev(y), stats, bstats, dev(g), dev(dy), vpr, rpb, jsplit)))
+    if (g.g1 && g.g2) {
+      CGB_APP_LAUNCH(true, true);
+    } else if (g.g1) {
+      CGB_APP_LAUNCH(true, false);
+    } else {
+      CGB_APP_LAUNCH(false, true);
+    }
+#undef CGB_APP_LAUNCH
+    return;
+  }
   const int total = y.H * y.W;
   const int lanes = std::min(256, y.C / 8), rows = 256 / lanes;
   int appb;
