@@ -15,6 +15,7 @@ Tolerance protocol (DESIGN.md "parity protocol"):
 import ctypes
 import json
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -187,6 +188,23 @@ def test_instance_norm_backward_with_folded_halo_gradient(act, fold, use_g1, two
     r_da, r_dy = rel(dao, out.grad), rel(dyo, y.grad)
     assert r_da < 5e-3, r_da     # the assembled activation gradient (bf16-rounded)
     assert r_dy < 1e-2, r_dy
+
+
+# The library picks one of three implementations per launch (bulk-copy kernels for large launches, register
+# row-streaming kernels for small ones, the flat-range kernels for odd channel counts).  The switches are read once per
+# process, so the InstanceNorm tests above are re-run in child processes that force each family onto every shape.
+@pytest.mark.parametrize("env", [{"CGB_PW_BULK_MIN": "1"}, {"CGB_PW_BULK": "0"}, {"CGB_PW_BULK": "0", "CGB_PW_ROWS": "0"}],
+                         ids=["bulk-everywhere", "rows-everywhere", "flat-range"])
+def test_instance_norm_kernel_families(env):
+    _need_gpu()
+    if os.environ.get("CGB_IN_CHILD"):
+        pytest.skip("child process")
+    import subprocess
+    e = dict(os.environ, CGB_IN_CHILD="1", **env)
+    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-m", "gpu", "-k",
+                        "test_instance_norm_forward_backward or test_instance_norm_backward_with"],
+                       env=e, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
 # ------------------------------------------------------------------------------------------------

@@ -6,6 +6,7 @@
 #include "ptx.cuh"
 
 #include <cstdlib>
+#include <set>
 
 #ifndef CGB_PW_TRIGGER
 #define CGB_PW_TRIGGER 0
@@ -1288,6 +1289,236 @@ in_bwd_apply_rows_kernel(DevTensor y, const float2* __restrict__ stats, const fl
   }
 }
 
+// ------------------------------------------------------------------------------------------ bulk-copy variants
+// Same decomposition as the row-streaming kernels, but the inputs of a segment (one image row, or a slice of `segv`
+// <= kBulkVec vectors of it) arrive by ONE cp.async.bulk per tensor issued by one thread: all of the block's reads are
+// in flight from its first instruction (the register kernels above issue them in 2-4 dependent batches per thread,
+// so a short-lived block spends most of its life ramping up), nothing is held in registers while in flight, and three
+// blocks per SM keep up to 3 x 32-96 KB outstanding.  Threads then read their vectors from shared memory.
+constexpr int kBulkVec = 2048;  // at most this many 16-byte vectors per segment and tensor (32 KB); multiples of 256
+
+struct Seg {  // segment s of this block -> (row, first vector, vector count)
+  int h, v0, nv;
+};
+__device__ __forceinline__ Seg seg_of(int s, int nslice, int vpr, int segv) {
+  Seg g;
+  g.h = s / nslice;
+  g.v0 = (s - g.h * nslice) * segv;
+  g.nv = min(segv, vpr - g.v0);
+  return g;
+}
+
+template <int ACT, bool RES>
+__global__ void __launch_bounds__(256, 3)
+in_apply_bulk_kernel(DevTensor y, const float2* __restrict__ stats, DevTensor res, DevTensor out, int vpr, int nslice, int segv) {
+  extern __shared__ __align__(128) uint8_t bulk_smem[];
+  __shared__ uint64_t bar;
+  uint4* sy = reinterpret_cast<uint4*>(bulk_smem);
+  uint4* sr = sy + segv;
+  const int t = threadIdx.x, n = blockIdx.y;
+  const int C = out.C, H = out.H, W = out.W, p = out.halo;
+  const int lanes = C >> 3, lsh = 31 - __clz(lanes);
+  const int c0 = (t & (lanes - 1)) * 8;
+  const Seg sg = seg_of(blockIdx.x, nslice, vpr, segv);
+  const int h = sg.h;
+  if (t == 0) {
+    ptx::mbar_init(&bar, 1);
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+  ptx::pdl_wait();
+  if (kPwTrigger) ptx::pdl_launch_dependents();
+  if (t == 0) {
+    ptx::mbar_arrive_expect_tx(&bar, (uint32_t)sg.nv * 16u * (RES ? 2u : 1u));
+    ptx::bulk_load(sy, y.p + n * y.sN + h * y.sH + (long long)sg.v0 * 8, (uint32_t)sg.nv * 16u, &bar);
+    if (RES) ptx::bulk_load(sr, res.p + n * res.sN + h * res.sH + (long long)sg.v0 * 8, (uint32_t)sg.nv * 16u, &bar);
+  }
+  float a[8], b[8];
+  load_norm8(stats, (long long)n * C + c0, 1.f / (float)(H * W), a, b);
+  bf16* orow = out.p + n * out.sN + h * out.sH;
+  int hm = 0;
+  const bool hb = p > 0 && mirror_of(h, H, p, &hm);
+  bf16* mrow = out.p + n * out.sN + (long long)hm * out.sH;
+  ptx::mbar_wait(&bar, 0);
+#pragma unroll 2
+  for (int vi = t; vi < sg.nv; vi += 256) {
+    float v[8];
+    unpack8(sy[vi], v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = act_fwd_t<ACT>(fmaf(v[i], a[i], b[i]));
+    if (RES) {
+      float rv[8];
+      unpack8(sr[vi], rv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += rv[i];
+    }
+    const int gv = sg.v0 + vi;   // vector index inside the row
+    const int w = gv >> lsh;
+    store8(orow + gv * 8, v);
+    if (p > 0) {  // this pixel is the mirror image of up to three halo pixels
+      int wm = 0;
+      const bool wb = mirror_of(w, W, p, &wm);
+      if (wb) store8(orow + wm * C + c0, v);
+      if (hb) {
+        store8(mrow + gv * 8, v);
+        if (wb) store8(mrow + wm * C + c0, v);
+      }
+    }
+  }
+}
+
+// issue the bulk copies of one backward segment (y, g1, g2 rows) -- one thread
+template <bool G1, bool G2>
+__device__ __forceinline__ void bwd_bulk_issue(const DevTensor& y, const DevGrad& g, int n, const Seg& sg, uint4* sy,
+                                               uint4* sg1, uint4* sg2, uint64_t* bar) {
+  const uint32_t bytes = (uint32_t)sg.nv * 16u;
+  ptx::mbar_arrive_expect_tx(bar, bytes * (1u + (G1 ? 1u : 0u) + (G2 ? 1u : 0u)));
+  ptx::bulk_load(sy, y.p + n * y.sN + sg.h * y.sH + (long long)sg.v0 * 8, bytes, bar);
+  if (G1) ptx::bulk_load(sg1, g.g1.p + n * g.g1.sN + sg.h * g.g1.sH + (long long)sg.v0 * 8, bytes, bar);
+  if (G2)
+    ptx::bulk_load(sg2, g.g2.p + n * g.g2.sN + (sg.h + g.fold) * g.g2.sH + (long long)g.fold * y.C + (long long)sg.v0 * 8,
+                   bytes, bar);
+}
+
+template <int ACT, bool G1, bool G2, bool DA>
+__global__ void __launch_bounds__(256, 3)
+in_bwd_reduce_bulk_kernel(DevTensor y, const float2* __restrict__ stats, DevGrad g, DevTensor da,
+                          float* __restrict__ bstats, int vpr, int nslice, int segv, int spb) {
+  extern __shared__ __align__(128) uint8_t bulk_smem[];
+  __shared__ uint64_t bar;
+  uint4* sy = reinterpret_cast<uint4*>(bulk_smem);
+  uint4* sg1 = sy + segv;
+  uint4* sg2 = sg1 + (G1 ? segv : 0);
+  const int t = threadIdx.x, n = blockIdx.y;
+  const int C = y.C, H = y.H, W = y.W, p = g.fold;
+  const int lanes = C >> 3, lsh = 31 - __clz(lanes), rows = 256 >> lsh, prow = t >> lsh, cl = t & (lanes - 1);
+  const int c0 = cl * 8;
+  const int s0 = blockIdx.x * spb, s1e = min(H * nslice, s0 + spb);  // this block's segments
+  if (t == 0) {
+    ptx::mbar_init(&bar, 1);
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+  ptx::pdl_wait();
+  if (kPwTrigger) ptx::pdl_launch_dependents();
+  if (t == 0 && s0 < s1e) bwd_bulk_issue<G1, G2>(y, g, n, seg_of(s0, nslice, vpr, segv), sy, sg1, sg2, &bar);
+  float a[8], b[8], s1[8], s2[8];
+  load_norm8(stats, (long long)n * C + c0, 1.f / (float)(H * W), a, b);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
+  const bf16* g2img = G2 ? g.g2.p + n * g.g2.sN : nullptr;
+  uint32_t phase = 0;
+  for (int s = s0; s < s1e; ++s) {
+    const Seg sg = seg_of(s, nslice, vpr, segv);
+    const int h = sg.h;
+    bf16* darow = DA ? da.p + n * da.sN + h * da.sH : nullptr;
+    const bool hb = G2 && ((h >= 1 && h <= p) || (h >= H - 1 - p && h <= H - 2));
+    const int hm = (h >= 1 && h <= p) ? p - h : 2 * (H - 1) - h + p;  // padded-domain row of the mirror
+    ptx::mbar_wait(&bar, phase);
+    phase ^= 1;
+#pragma unroll 2
+    for (int vi = t; vi < sg.nv; vi += 256) {
+      const int gv = sg.v0 + vi;
+      float v[8], gr[8];
+      rows_grad<G1, G2>(G1 ? sg1[vi] : sy[vi], G2 ? sg2[vi] : sy[vi], g2img, g.g2.sH, C, c0, h, gv >> lsh, H, W, p, hb, hm, gr);
+      if (DA) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) gr[i] = round_bf16(gr[i]);
+        store8(darow + gv * 8, gr);
+      }
+      unpack8(sy[vi], v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float xh = fmaf(v[i], a[i], b[i]);
+        const float dz = gr[i] * act_grad_t<ACT>(xh);
+        s1[i] += dz;
+        s2[i] = fmaf(dz, xh, s2[i]);
+      }
+    }
+    if (s + 1 < s1e) {
+      __syncthreads();  // every thread is done reading the segment: its buffers may be refilled
+      if (t == 0) bwd_bulk_issue<G1, G2>(y, g, n, seg_of(s + 1, nslice, vpr, segv), sy, sg1, sg2, &bar);
+    }
+  }
+  // the block's pixel slots that share a channel vector -> shared memory -> one vector atomic per channel pair
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(bulk_smem);  // 256 * 16 floats: the segment buffers are idle now
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    red[t * 16 + i] = s1[i];
+    red[t * 16 + 8 + i] = s2[i];
+  }
+  __syncthreads();
+  if (prow == 0) {
+    for (int r = 1; r < rows; ++r) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s1[i] += red[(r * lanes + cl) * 16 + i];
+        s2[i] += red[(r * lanes + cl) * 16 + 8 + i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i += 2)
+      red_add_v4(bstats + ((long long)n * C + c0 + i) * 2, s1[i], s2[i], s1[i + 1], s2[i + 1]);
+  }
+}
+
+template <int ACT, bool G1, bool G2>
+__global__ void __launch_bounds__(256, 3)
+in_bwd_apply_bulk_kernel(DevTensor y, const float2* __restrict__ stats, const float2* __restrict__ bstats, DevGrad g,
+                         DevTensor dy, int vpr, int nslice, int segv) {
+  extern __shared__ __align__(128) uint8_t bulk_smem[];
+  __shared__ uint64_t bar;
+  uint4* sy = reinterpret_cast<uint4*>(bulk_smem);
+  uint4* sg1 = sy + segv;
+  uint4* sg2 = sg1 + (G1 ? segv : 0);
+  const int t = threadIdx.x, n = blockIdx.y;
+  const int C = y.C, H = y.H, W = y.W, p = g.fold;
+  const int lanes = C >> 3, lsh = 31 - __clz(lanes);
+  const int c0 = (t & (lanes - 1)) * 8;
+  const Seg sg = seg_of(blockIdx.x, nslice, vpr, segv);
+  const int h = sg.h;
+  if (t == 0) {
+    ptx::mbar_init(&bar, 1);
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+  ptx::pdl_wait();
+  if (kPwTrigger) ptx::pdl_launch_dependents();
+  if (t == 0) bwd_bulk_issue<G1, G2>(y, g, n, sg, sy, sg1, sg2, &bar);
+  // dy = rstd * (dz - mean(dz) - xhat * mean(dz * xhat)) = a * dz - c - d * xhat
+  float a[8], b[8], c[8], d[8];
+  const float inv = 1.f / (float)(H * W);
+  load_norm8(stats, (long long)n * C + c0, inv, a, b);
+#pragma unroll
+  for (int i = 0; i < 8; i += 2) {
+    const float4 bs = __ldg(reinterpret_cast<const float4*>(bstats + (long long)n * C + c0 + i));
+    c[i] = a[i] * bs.x * inv;
+    d[i] = a[i] * bs.y * inv;
+    c[i + 1] = a[i + 1] * bs.z * inv;
+    d[i + 1] = a[i + 1] * bs.w * inv;
+  }
+  const bf16* g2img = G2 ? g.g2.p + n * g.g2.sN : nullptr;
+  bf16* dyrow = dy.p + n * dy.sN + h * dy.sH;
+  const bool hb = G2 && ((h >= 1 && h <= p) || (h >= H - 1 - p && h <= H - 2));
+  const int hm = (h >= 1 && h <= p) ? p - h : 2 * (H - 1) - h + p;
+  ptx::mbar_wait(&bar, 0);
+#pragma unroll 2
+  for (int vi = t; vi < sg.nv; vi += 256) {
+    const int gv = sg.v0 + vi;
+    float v[8], gr[8];
+    rows_grad<G1, G2>(G1 ? sg1[vi] : sy[vi], G2 ? sg2[vi] : sy[vi], g2img, g.g2.sH, C, c0, h, gv >> lsh, H, W, p, hb, hm, gr);
+    unpack8(sy[vi], v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float xh = fmaf(v[i], a[i], b[i]);
+      const float dz = gr[i] * act_grad_t<ACT>(xh);
+      v[i] = fmaf(a[i], dz, -c[i]) - d[i] * xh;
+    }
+    store8(dyrow + gv * 8, v);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ head / losses
 __device__ __forceinline__ float block_sum(float v) {
   __shared__ float sh[32];
@@ -1688,9 +1919,51 @@ static void rows_grid(int H, int N, int vpr, int max_bpi, int* rpb, int* jsplit)
     default: CGB_CHECK(false, "InstanceNorm kernels: unsupported activation");  \
   }
 
+// Bulk-copy kernels (CGB_PW_BULK=0 falls back to the register row-streaming kernels): same shape conditions.
+static bool bulk_enabled() {
+  static const bool on = !(std::getenv("CGB_PW_BULK") && std::atoi(std::getenv("CGB_PW_BULK")) == 0);
+  return on;
+}
+// Segments are whole rows, or kBulkVec-vector slices of longer rows.  Small launches (fewer than two blocks per SM:
+// batch 1 on the 64 x 64 maps) stay on the register kernels: they are latency-bound and the barrier set-up plus the
+// single-thread issue cost more than they save (measured at batch 1: 4.35 ms/step with the register kernels, 4.41 with
+// bulk copies everywhere; at batch 8: 24.1 vs 23.6).
+static bool bulk_plan(int H, int N, int vpr, int* segv, int* nslice) {
+  const int sv = std::min(kBulkVec, (vpr + 255) / 256 * 256);
+  *segv = sv;
+  *nslice = (vpr + sv - 1) / sv;
+  static const int min_blocks = std::getenv("CGB_PW_BULK_MIN") ? std::atoi(std::getenv("CGB_PW_BULK_MIN")) : 2 * 148;
+  return bulk_enabled() && (long long)H * N * *nslice >= min_blocks;
+}
+template <typename... KArgs, typename... Args>
+static void launch_bulk(void (*kern)(KArgs...), dim3 grid, size_t smem, cudaStream_t st, Args&&... args) {
+  static std::set<const void*> configured;  // kernels whose dynamic shared-memory limit has been raised
+  const void* key = reinterpret_cast<const void*>(kern);
+  if (!configured.count(key)) {
+    CGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * kBulkVec * 16));
+    configured.insert(key);
+  }
+  launch_pdl(kern, grid, dim3(256), smem, st, std::forward<Args>(args)...);
+}
+
 void in_apply(const TensorDesc& y, const float2* stats, int act, const TensorDesc* residual, const TensorDesc& out,
               cudaStream_t st) {
   CGB_CHECK(y.C == out.C && y.H == out.H && y.W == out.W && y.N == out.N, "in_apply: shape mismatch");
+  int segv = 0, nslice = 0;
+  if (rows_ok(out, out.halo) && (act == kActNone || act == kActLeaky || act == kActRelu) &&
+      bulk_plan(out.H, out.N, out.W * out.C / 8, &segv, &nslice)) {
+    const int vpr = out.W * out.C / 8;
+    dim3 grid(out.H * nslice, out.N);
+    const DevTensor r = residual ? dev(*residual) : dev_null();
+    if (residual) {
+      CGB_ACT_SWITCH(act, (launch_bulk(in_apply_bulk_kernel<ACT, true>, grid, (size_t)segv * 32, st, dev(y), stats, r, dev(out),
+                                       vpr, nslice, segv)));
+    } else {
+      CGB_ACT_SWITCH(act, (launch_bulk(in_apply_bulk_kernel<ACT, false>, grid, (size_t)segv * 16, st, dev(y), stats, r, dev(out),
+                                       vpr, nslice, segv)));
+    }
+    return;
+  }
   if (rows_ok(out, out.halo) && (act == kActNone || act == kActLeaky || act == kActRelu)) {
     const int vpr = out.W * out.C / 8;
     int rpb, jsplit;
@@ -1809,6 +2082,32 @@ bool in_bwd_fused(const TensorDesc& y, const float2* stats, const GradSrc& g, in
 void in_bwd_reduce(const TensorDesc& y, const float2* stats, const GradSrc& g, int act, const TensorDesc* da_out,
                    float2* bstats, cudaStream_t st) {
   check_grad(y, g);
+  int segv = 0, nslice = 0;
+  if (rows_ok(y, g.g2 ? g.fold : 0) && (act == kActNone || act == kActLeaky || act == kActRelu) &&
+      bulk_plan(y.H, y.N, y.W * y.C / 8, &segv, &nslice)) {
+    const int vpr = y.W * y.C / 8;
+    const int segs = y.H * nslice;
+    const int spb = (segs + 63) / 64;  // <= 64 blocks per image end in atomics on the same statistics
+    dim3 grid((segs + spb - 1) / spb, y.N);
+    const DevTensor dat = da_out ? dev(*da_out) : dev_null();
+    float* bs = reinterpret_cast<float*>(bstats);
+    // (the final cross-slot reduction reuses the buffers: 256 x 16 floats)
+    const size_t smem = std::max<size_t>(256 * 16 * sizeof(float), (size_t)segv * 16 * (1 + (g.g1 ? 1 : 0) + (g.g2 ? 1 : 0)));
+#define CGB_RED_LAUNCH(G1, G2, DA) \
+  CGB_ACT_SWITCH(act, (launch_bulk(in_bwd_reduce_bulk_kernel<ACT, G1, G2, DA>, grid, smem, st, dev(y), stats, dev(g), dat, bs, vpr, nslice, segv, spb)))
+    const int key = (g.g1 ? 4 : 0) | (g.g2 ? 2 : 0) | (da_out ? 1 : 0);
+    switch (key) {
+      case 4: CGB_RED_LAUNCH(true, false, false); break;
+      case 5: CGB_RED_LAUNCH(true, false, true); break;
+      case 2: CGB_RED_LAUNCH(false, true, false); break;
+      case 3: CGB_RED_LAUNCH(false, true, true); break;
+      case 6: CGB_RED_LAUNCH(true, true, false); break;
+      case 7: CGB_RED_LAUNCH(true, true, true); break;
+      default: CGB_CHECK(false, "in_bwd_reduce: no gradient source");
+    }
+#undef CGB_RED_LAUNCH
+    return;
+  }
   if (rows_ok(y, g.g2 ? g.fold : 0) && (act == kActNone || act == kActLeaky || act == kActRelu)) {
     const int vpr = y.W * y.C / 8;
     int rpb, jsplit;
@@ -1858,6 +2157,24 @@ void in_bwd_reduce(const TensorDesc& y, const float2* stats, const GradSrc& g, i
 void in_bwd_apply(const TensorDesc& y, const float2* stats, const float2* bstats, const GradSrc& g, int act,
                   const TensorDesc& dy, cudaStream_t st) {
   check_grad(y, g);
+  int segv = 0, nslice = 0;
+  if (rows_ok(y, g.g2 ? g.fold : 0) && (act == kActNone || act == kActLeaky || act == kActRelu) &&
+      bulk_plan(y.H, y.N, y.W * y.C / 8, &segv, &nslice)) {
+    const int vpr = y.W * y.C / 8;
+    dim3 grid(y.H * nslice, y.N);
+    const size_t smem = (size_t)segv * 16 * (1 + (g.g1 ? 1 : 0) + (g.g2 ? 1 : 0));
+#define CGB_APPB_LAUNCH(G1, G2) \
+  CGB_ACT_SWITCH(act, (launch_bulk(in_bwd_apply_bulk_kernel<ACT, G1, G2>, grid, smem, st, dev(y), stats, bstats, dev(g), dev(dy), vpr, nslice, segv)))
+    if (g.g1 && g.g2) {
+      CGB_APPB_LAUNCH(true, true);
+    } else if (g.g1) {
+      CGB_APPB_LAUNCH(true, false);
+    } else {
+      CGB_APPB_LAUNCH(false, true);
+    }
+#undef CGB_APPB_LAUNCH
+    return;
+  }
   if (rows_ok(y, g.g2 ? g.fold : 0) && (act == kActNone || act == kActLeaky || act == kActRelu)) {
     const int vpr = y.W * y.C / 8;
     int rpb, jsplit;

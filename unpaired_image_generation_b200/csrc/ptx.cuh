@@ -126,6 +126,14 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// plain bulk copy (no tensor map): `bytes` contiguous bytes, global -> shared; 16-byte aligned addresses and size
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // multicast variants: the box lands at the same smem offset (and signals the mbarrier at the same offset)
 // in every CTA of the cluster whose bit is set in cta_mask
 __device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
