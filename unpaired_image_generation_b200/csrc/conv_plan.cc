@@ -108,6 +108,16 @@ static void finalize(IgemmPlan& p, ViewKind vk, const TensorDesc& act, const bf1
   if (vk == kViewS2) p.tmA = view_s2(act, p.BK, SW, SH);
   else p.tmA = view_s1(act, vk == kViewS1Padded, p.BK, SW, SH);
   p.tmB = make_tmap_2d(w, padded_rows(rows), Kw, Kw, p.BK, p.BN / p.CM, p.BK * 2);
+  // many short CTAs (the stride-2 / transposed layers on large maps: 2-9 K iterations each, several waves): trade the
+  // deep ring for 2-3 co-resident CTAs per SM.  CGB_IGEMM_LITE=0 disables, =N sets the minimum number of waves (-1: always),
+  // CGB_IGEMM_LITE_MAXK the longest K loop (iterations of 64 channels) that still qualifies.
+  static const int lite_waves = std::getenv("CGB_IGEMM_LITE") ? std::atoi(std::getenv("CGB_IGEMM_LITE")) : 2;
+  static const int lite_maxk = std::getenv("CGB_IGEMM_LITE_MAXK") ? std::atoi(std::getenv("CGB_IGEMM_LITE_MAXK")) : 16;
+  int max_k = 0;
+  for (int z = 0; z < p.n_classes; ++z) max_k = std::max(max_k, p.args.k_count[z]);
+  const long long ctas = (long long)p.num_tiles * p.n_blocks * p.n_classes;
+  p.lite = lite_waves != 0 && p.BK == 64 && p.BN >= 64 && p.CM * p.CN == 1 &&
+           (lite_waves < 0 || (max_k <= lite_maxk && ctas >= (long long)lite_waves * sm_count));
 }
 
 static void set_tiles(IgemmPlan& p, int N, int Ho, int Wo) {
@@ -578,7 +588,7 @@ void run(const IgemmPlan& p, cudaStream_t stream) {
     return;
   }
   for (int z = 0; z < p.n_classes; ++z) CGB_CHECK(p.args.k_count[z] <= 192, "K-iteration table exceeds the smem staging area");
-  launch_igemm(p.BN, p.BK, p.CM, p.CN, p.tmA, p.tmB, p.args, p.num_tiles, p.n_blocks, p.n_classes, stream);
+  launch_igemm(p.BN, p.BK, p.CM, p.CN, p.lite, p.tmA, p.tmB, p.args, p.num_tiles, p.n_blocks, p.n_classes, stream);
 }
 
 void run(const WgradPlan& p, cudaStream_t stream) {

@@ -59,6 +59,7 @@ struct IgemmPlan {
   IgemmArgs args;
   int BN = 0, BK = 0, num_tiles = 0, n_blocks = 0, n_classes = 1;
   int CM = 1, CN = 1;         // thread-block cluster (M tiles x N blocks) sharing operands by TMA multicast
+  bool lite = false;          // tap-table kernel: low-shared-memory instantiation, several CTAs per SM
   std::vector<KIter> kiters;  // host copy; args.kiters must point at a device copy
   double flops = 0;           // algorithmic 2*MACs (for roofline accounting)
   // patch-resident variant (conv_patch.cu): stride-1 convs / input gradients with 64-channel chunks

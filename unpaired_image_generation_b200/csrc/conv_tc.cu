@@ -43,8 +43,11 @@ struct IgemmCfg {
 // CM x CN thread-block cluster: the CN CTAs that share an M tile (same blockIdx.x, consecutive N blocks) each
 // fetch 1/CN of the activation box and multicast it to the others; the CM CTAs that share an N block
 // (consecutive M tiles) do the same with the weight tile.  L2 -> SM operand traffic drops by CN (A) and CM (B).
-template <int BN, int BK, int STAGES, int KPS, int CM, int CN>
-__global__ void __launch_bounds__(192, 1)
+// MINB = CTAs per SM the register allocation must allow: the "lite" instantiations (2-stage rings, one K iteration per
+// stage, 54-102 KB of shared memory) put 2-3 CTAs on an SM for launches of many short CTAs (the stride-2 / transposed
+// layers on large maps: 2-9 K iterations per CTA), so one CTA's prologue and epilogue overlap another's loads and MMAs.
+template <int BN, int BK, int STAGES, int KPS, int CM, int CN, int MINB = 1>
+__global__ void __launch_bounds__(192, MINB)
 igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const IgemmArgs args) {
   using Cfg = IgemmCfg<BN, BK, STAGES, KPS>;
@@ -410,12 +413,12 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
 // ------------------------------------------------------------------------------------------
 // Host launchers
 // ------------------------------------------------------------------------------------------
-template <int BN, int BK, int STAGES, int KPS, int CM, int CN>
+template <int BN, int BK, int STAGES, int KPS, int CM, int CN, int MINB = 1>
 static void launch_igemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmArgs& args, dim3 grid,
                            cudaStream_t stream) {
   using Cfg = IgemmCfg<BN, BK, STAGES, KPS>;
   static bool configured = false;
-  auto kern = igemm_conv_kernel<BN, BK, STAGES, KPS, CM, CN>;
+  auto kern = igemm_conv_kernel<BN, BK, STAGES, KPS, CM, CN, MINB>;
   if (!configured) {
     CGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
@@ -442,9 +445,17 @@ static void launch_igemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const
   CGB_CUDA(cudaGetLastError());
 }
 
-void launch_igemm(int BN, int BK, int CM, int CN, const CUtensorMap& tmA, const CUtensorMap& tmB,
+void launch_igemm(int BN, int BK, int CM, int CN, bool lite, const CUtensorMap& tmA, const CUtensorMap& tmB,
                   const IgemmArgs& args, int num_tiles, int n_blocks, int n_classes, cudaStream_t stream) {
   dim3 grid(num_tiles, n_blocks, n_classes);
+  if (lite && BK == 64 && CM * CN == 1) {
+    switch (BN) {
+      case 256: return launch_igemm_t<256, 64, 2, 1, 1, 1, 2>(tmA, tmB, args, grid, stream);
+      case 128: return launch_igemm_t<128, 64, 2, 1, 1, 1, 3>(tmA, tmB, args, grid, stream);
+      case 64: return launch_igemm_t<64, 64, 2, 1, 1, 1, 3>(tmA, tmB, args, grid, stream);
+      default: break;
+    }
+  }
   const int key = BN * 1000000 + BK * 10000 + CM * 100 + CN;
   switch (key) {
     // single-CTA (BN, BK, stages, K iterations per stage)

@@ -17,7 +17,8 @@ CUtensorMap make_tmap_2d(const bf16* base, long long rows, long long cols, long 
                          int box_rows, int swizzle_bytes);
 
 // CM x CN: thread-block cluster (M tiles x N blocks) sharing operands through TMA multicast; 1 x 1 = none.
-void launch_igemm(int BN, int BK, int CM, int CN, const CUtensorMap& tmA, const CUtensorMap& tmB,
+// lite: 2-stage low-shared-memory instantiation (2-3 CTAs per SM) for launches of many short CTAs.
+void launch_igemm(int BN, int BK, int CM, int CN, bool lite, const CUtensorMap& tmA, const CUtensorMap& tmB,
                   const IgemmArgs& args, int num_tiles, int n_blocks, int n_classes, cudaStream_t stream);
 
 
