@@ -8,7 +8,8 @@ OUT=gpurun_out/${TAG}_sweep_b${BATCH:-1}.txt
 : > $OUT
 IFS=';' read -ra SETTINGS <<< "${SWEEP:-CGB_PDL=1}"
 for s in "${SETTINGS[@]}"; do
-  line=$(env $s timeout 300 python bench.py --batch ${BATCH:-1} --size ${SIZE:-256} --steps ${STEPS:-20} --no-cpu-baseline --no-extra-configs 2>/dev/null)
+  line=$(env $s timeout 300 python bench.py --batch ${BATCH:-1} --size ${SIZE:-256} --steps ${STEPS:-20} --no-cpu-baseline --no-extra-configs 2>/tmp/sweep_err.txt)
+  [ -z "$line" ] && { echo "---- $s: no output; stderr tail:" >> $OUT; tail -n 15 /tmp/sweep_err.txt >> $OUT; }
   python - "$s" "$line" >> $OUT <<'PY'
 import json, sys
 try:

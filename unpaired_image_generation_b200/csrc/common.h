@@ -118,6 +118,18 @@ struct WgradArgs {
   int b_virtual;           // the same for the X side (atoms of the GEMM's N extent)
 };
 
+// Weight gradient of a stride-1 conv on CTA pairs (wgrad_pair.cu): a pair owns one filter row, 256 output channels and
+// 128 input channels; K (8 x 8 pixel chunks) is split over pairs.
+struct WgradPairArgs {
+  int kh, kw, T;                 // filter extent, taps per filter (= kh * kw)
+  int Cout, Cin;                 // extents of g[Cout][T][Cin] (Cout % 256 == 0, Cin % 128 == 0)
+  int tiles_w, tiles_h, N;       // 8 x 8 pixel chunks per image, images
+  int split_k;                   // K splits
+  int n_units, cin_blocks;       // units = kh x cin_blocks x (Cout / 256); pair q works on unit q % n_units, split q / n_units
+  int x_ox, x_oy;                // origin of the X patch of tap (0, 0) relative to the dY chunk origin, in the X view's coordinates
+  float* g;                      // fp32, accumulated with atomics (must be zeroed)
+};
+
 // Launch with the programmatic-dependent-launch attribute (see ptx.cuh: pdl_wait / pdl_launch_dependents).
 // Every kernel launched through this helper MUST call pdl_wait() before touching global memory.
 bool pdl_enabled();  // CGB_PDL=0 disables (conv_plan.cc)

@@ -565,6 +565,45 @@ WgradPlan plan_wgrad(const ConvSpec& s, const TensorDesc& x, const TensorDesc& d
       }
   }
   p.args.num_taps = (int)p.taps.size();
+  p.flops = 2.0 * x.N * (double)PH * PW * s.Cout * s.Cin * T;
+  // stride-1 layers with wide channels: CTA pairs, one filter row per pair (wgrad_pair.cu).  CGB_WGRAD_PAIR=0 disables.
+  static const bool pair_on = !(std::getenv("CGB_WGRAD_PAIR") && std::atoi(std::getenv("CGB_WGRAD_PAIR")) == 0);
+  // (short reductions stay on the tap-per-CTA kernel: the discriminator's 31 x 31 layer at batch 1 has 16 chunks; measured
+  // 15.0 us there against 22.0 us for pairs)
+  static const long long pair_min_total = std::getenv("CGB_WGRADP_MIN_TOTAL") ? std::atoll(std::getenv("CGB_WGRADP_MIN_TOTAL")) : 32;
+  if (pair_on && !s.transposed && s.stride == 1 && s.k <= 4 && s.Cout == s.CoutS && s.Cin == s.CinS && s.Cout % 256 == 0 &&
+      s.Cin % 128 == 0 && (long long)x.N * ((PW + 7) / 8) * ((PH + 7) / 8) >= pair_min_total) {
+    WgradPairArgs& a = p.pargs;
+    std::memset(&a, 0, sizeof(a));
+    a.kh = a.kw = k;
+    a.T = T;
+    a.Cout = s.Cout;
+    a.Cin = s.Cin;
+    a.tiles_w = (PW + 7) / 8;
+    a.tiles_h = (PH + 7) / 8;
+    a.N = x.N;
+    a.cin_blocks = s.Cin / 128;
+    a.n_units = k * a.cin_blocks * (s.Cout / 256);
+    a.x_ox = a.x_oy = s.reflect ? 0 : -s.pad;
+    a.g = g;
+    // K split: about `frac` of the machine's TPCs in pairs, but at least `min_chunks` chunks per pair (the fp32
+    // reduction of a pair's 256 x (kw * 128) tile costs about as much as a dozen chunks of MMAs).  The weight gradients
+    // run on side lanes next to the backward chain, so the FASTEST launch is not the best one: measured at batch 8
+    // (profiles/r02_y_sweep_wgrad_pairs_b8.txt) frac 1.0 / 0.7 / 0.5 / 0.35 / 0.25: residual wgrad 1164 / 885 / 782 / 574 /
+    // 456 TFLOP/s but step 22.26 / 21.93 / 21.89 / 21.76 / 21.85 ms; at batch 1 min_chunks 8 / 16 / 32 / 64: 4.75 /
+    // 4.34 / 4.19 / 4.23 ms (the tap-per-CTA kernel: 4.28).
+    static const double pfrac = std::getenv("CGB_WGRADP_FRAC") ? std::atof(std::getenv("CGB_WGRADP_FRAC")) : 0.4;
+    static const long long pmin = std::getenv("CGB_WGRADP_MIN_CHUNKS") ? std::atoll(std::getenv("CGB_WGRADP_MIN_CHUNKS")) : 32;
+    const long long chunks = (long long)a.N * a.tiles_w * a.tiles_h;
+    long long split = (long long)(sm_count / 2 * pfrac) / a.n_units;
+    split = std::max(1LL, std::min(split, std::max(1LL, chunks / pmin)));
+    a.split_k = (int)split;
+    p.tmDY = view_s1(dy, false, 64, 8, 8);
+    p.tmX = view_s1(x, s.reflect, 64, 8 + k - 1, 8);
+    p.pair = true;
+    p.args.split_k = a.split_k;
+    return p;
+  }
   const long long total_chunks = (long long)p.args.N * p.args.tiles_w * p.args.tiles_h;
   const long long base_ctas = (long long)p.m_blocks * ((s.CinS + p.BNW - 1) / p.BNW) * T;
   // split-K so that the launch has about `frac` of a wave of CTAs: long K per CTA amortises the prologue and
@@ -592,6 +631,10 @@ void run(const IgemmPlan& p, cudaStream_t stream) {
 }
 
 void run(const WgradPlan& p, cudaStream_t stream) {
+  if (p.pair) {
+    launch_wgrad_pair(p.tmDY, p.tmX, p.pargs, stream);
+    return;
+  }
   CGB_CHECK(p.args.taps != nullptr, "wgrad plan has no device tap table");
   launch_wgrad(p.BNW, p.tmDY, p.tmX, p.args, p.m_blocks, stream);
 }

@@ -76,6 +76,8 @@ struct WgradPlan {
   int BNW = 0, m_blocks = 0;
   std::vector<WTap> taps;
   double flops = 0;
+  bool pair = false;     // stride-1 layers with Cout % 256 == 0, Cin % 128 == 0: CTA-pair kernel (wgrad_pair.cu)
+  WgradPairArgs pargs;
 };
 
 // Forward of Conv2d (stride 1 or 2) or ConvTranspose2d.  x: input (with halo when reflect),

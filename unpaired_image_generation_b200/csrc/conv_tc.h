@@ -33,4 +33,8 @@ int igemm_patch_smem_budget(); // bytes available for the weight ring + patches
 void launch_wgrad(int BNW, const CUtensorMap& tmDY, const CUtensorMap& tmX, const WgradArgs& args, int m_blocks,
                   cudaStream_t stream);
 
+// CTA-pair weight gradient of stride-1 convs (wgrad_pair.cu).  tmDY: box (64 channels, 8, 1, 8, 1) of the dY view;
+// tmX: box (64 channels, 8 + kw - 1, 1, 8, 1) of the (padded, for reflect convs) X view.
+void launch_wgrad_pair(const CUtensorMap& tmDY, const CUtensorMap& tmX, const WgradPairArgs& args, cudaStream_t stream);
+
 }  // namespace cgb

@@ -351,8 +351,8 @@ static int run_case(const std::string& name, ConvSpec s, int N, int H, int W, in
     CGB_CUDA(cudaMemset(d_g, 0, ref.size() * sizeof(float)));
     WgradPlan p = plan_wgrad(s, x, dy, d_g, sm_count);
     p.args.taps = dev_upload(p.taps);
-    printf("  wgrad: BNW=%d m_blocks=%d taps=%d split_k=%d chunks=%dx%dx%d\n", p.BNW, p.m_blocks, p.args.num_taps,
-           p.args.split_k, p.args.N, p.args.tiles_h, p.args.tiles_w);
+    printf("  wgrad: BNW=%d m_blocks=%d taps=%d split_k=%d chunks=%dx%dx%d pair=%d units=%d\n", p.BNW, p.m_blocks,
+           p.args.num_taps, p.args.split_k, p.args.N, p.args.tiles_h, p.args.tiles_w, (int)p.pair, p.pair ? p.pargs.n_units : 0);
     run(p, 0);
     CGB_CUDA(cudaDeviceSynchronize());
     std::vector<float> got(ref.size());

@@ -95,7 +95,10 @@ class CycleGANTrainer:
         eng.set_grad_scale(self.sync.grad_scale)
         self.engine = eng
         self.stream = torch.cuda.Stream(device=eng.device)
-        self.comm_stream = torch.cuda.Stream(device=eng.device)
+        # the communication stream runs at high priority: a collective only progresses once EVERY rank's NCCL CTAs are
+        # resident, so its blocks should not queue behind the step's pending conv CTAs (CGB_DP_COMM_PRIO=0: default priority)
+        prio = int(os.environ.get("CGB_DP_COMM_PRIO", "-1"))
+        self.comm_stream = torch.cuda.Stream(device=eng.device, priority=prio)
         self._buckets = eng.grad_bucket_plan()
         if self.pool_size > 0:
             self._dec_ring = [(torch.empty(2, batch, 2, dtype=torch.int32).pin_memory(), None)
