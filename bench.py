@@ -416,7 +416,7 @@ def measure_extra(cgb, torch, dist, world, rank, batch, size, steps, peaks):
     ms = float(t.item()) / steps
     out = {"workload": f"CycleGAN {size}x{size}, batch {batch} per GPU, bf16, full train step, dp{world}",
            "batch_per_gpu": batch, "size": size, "n_gpus": world, "value": world * batch / (ms * 1e-3), "unit": UNIT,
-           "ms_per_step": ms, "steps": steps, "schedule": "paired" if batch >= 4 else "unpaired",
+           "ms_per_step": ms, "steps": steps, "schedule": "paired" if batch >= 2 else "unpaired",
            "step_conv_tflops_per_gpu": eng.conv_flops_per_step / (ms * 1e-3) / 1e12,
            "step_conv_frac_of_peak": eng.conv_flops_per_step / (ms * 1e-3) / 1e12 / peaks["tf_sustained"]}
     if rank == 0 and world == 1:

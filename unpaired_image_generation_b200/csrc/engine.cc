@@ -122,8 +122,8 @@ void cgb_engine::layout(Arena& A) {
   auto images = [](const TensorDesc& t, int first, int n) { return t.images(first, n); };
   // The paired schedule does 20 % less kernel work but puts the identity passes on the critical chain.  Measured
   // on B200 with the final kernels: batch 1: 4.74 ms paired vs 4.65 ms unpaired; batch 8: 25.7 ms paired vs 27.2 ms
-  // unpaired.  Default: paired from 4 image pairs per GPU up; CGB_PAIR=0 / 1 overrides.
-  pair = std::getenv("CGB_PAIR") ? std::atoi(std::getenv("CGB_PAIR")) != 0 : cfg.batch >= 4;
+  // unpaired.  Default: paired from 2 image pairs per GPU up; CGB_PAIR=0 / 1 overrides.
+  pair = std::getenv("CGB_PAIR") ? std::atoi(std::getenv("CGB_PAIR")) != 0 : cfg.batch >= 2;  // measured (profiles/r02_aa_sweep_sched_b*.txt): batch 1 4.21 vs 4.22 ms, batch 2 7.27 vs 6.58, batch 8 22.3 vs 21.5
   if (fp32) pair = false;  // validation mode: one pass per image set, one gradient buffer per pass kind
   if (fp32 && !infer_only) {
     for (int k = 0; k < 3; ++k) gslot[0][k] = static_cast<float*>(A.alloc((size_t)group_numel[0] * sizeof(float)));
@@ -1049,10 +1049,30 @@ void cgb_engine::record_programs() {
     const bool dp = !with_adam_d;
     int ev_rec_done[2] = {-1, -1};  // [g]: the rec pass through generator g (G_AB: rec_B, G_BA: rec_A) is complete
     int ev_idt_done[2] = {-1, -1};  // [g]: the identity pass through generator g is complete
+    int ev_gstep = -1;              // in-step optimiser: the generators' step counter has been advanced (lane 2)
+    bool gstep_waited = false;
+    int pend_lo[2] = {-1, -1}, pend_hi[2] = {-1, -1};  // bucket of each generator whose bf16 packs are not refreshed yet
+    auto add_pack_layers = [&](Program& p, int gnet, int lo, int hi) {
+      if (lo < 0 || hi <= lo) return;
+      const int nl = (int)layers[gnet].size();
+      const PackEntry* tb = pack_table[CGB_GROUP_G] + gnet * nl + lo;
+      const int cnt = hi - lo, mx = pack_max[CGB_GROUP_G];
+      float* pm = P[CGB_GROUP_G];
+      bf16* arena = pack[CGB_GROUP_G];
+      p.add([pm, tb, cnt, mx, arena](cudaStream_t st) { pack_weights(pm, tb, cnt, mx, arena, st); });
+    };
     static const int n_dp_buckets = std::getenv("CGB_DP_BUCKETS") ? std::max(1, std::atoi(std::getenv("CGB_DP_BUCKETS"))) : 4;
+    // Single-GPU program: the same bucket boundaries drive the generators' optimiser INSIDE the step.  Once a bucket is
+    // final, Adam on that range runs on lane 2 (G_AB) / 3 (G_BA) -- idle after the D phase -- while the backward chains
+    // continue; the bf16 packs of a bucket are refreshed when the NEXT bucket of the same generator is final (the chain
+    // has left those layers, nothing else reads them), the last bucket's after the join.  Only that last, smallest
+    // bucket remains exposed instead of the whole 0.25 ms Adam + refresh.  CGB_ADAM_OVERLAP=0: optimiser after the step.
+    static const bool adam_overlap_on = !(std::getenv("CGB_ADAM_OVERLAP") && std::atoi(std::getenv("CGB_ADAM_OVERLAP")) == 0);
+    const bool adam_overlap = !dp && !fp32 && n_dp_buckets > 1 && adam_overlap_on;
+    if (!dp) step_has_adam_g = adam_overlap;
     auto bucket_hook = [&](int gnet) {
       return std::function<void(Program&, int, int)>([&, gnet](Program& p, int layer, int other_wlane) {
-        if (!dp || fp32 || n_dp_buckets <= 1) return;  // (validation mode: gradients are final after the slot sum)
+        if (!(dp || adam_overlap) || fp32 || n_dp_buckets <= 1) return;  // (validation mode: gradients are final after the slot sum)
         const std::vector<LayerParam>& L = layers[gnet];
         // bucket j covers layers [lo_j, lo_{j-1}); lo_0 = end, residual blocks split evenly, the last bucket ends at the stem
         int lo = -1, hi = (int)L.size();
@@ -1070,6 +1090,28 @@ void cgb_engine::record_programs() {
         if (ev_idt_done[gnet] >= 0) p.wait(p.cur_lane, ev_idt_done[gnet]);
         const long long net_end = gnet == 0 ? layers[1][0].w_off : group_numel[CGB_GROUP_G];
         const long long off = L[lo].w_off, end = hi < (int)L.size() ? L[hi].w_off : net_end;
+        if (adam_overlap) {
+          const int ev_final = p.record(p.cur_lane);
+          const int back = p.cur_lane, al = 2 + gnet;
+          p.cur_lane = al;
+          p.wait(al, ev_final);
+          if (al == 3 && !gstep_waited) {  // the step counter / bias corrections were advanced on lane 2
+            p.wait(3, ev_gstep);
+            gstep_waited = true;
+          }
+          float *pp = P[CGB_GROUP_G] + off, *gg = G[CGB_GROUP_G] + off, *mm = M[CGB_GROUP_G] + off, *vv = V[CGB_GROUP_G] + off;
+          const long long n = end - off;
+          int* stp = adam_step[CGB_GROUP_G];
+          float* hyp = adam_hyper[CGB_GROUP_G];
+          p.add([E, pp, gg, mm, vv, n, stp, hyp](cudaStream_t st) {
+            cgb::adam_range(pp, gg, mm, vv, n, E->cfg.beta1, E->cfg.beta2, E->cfg.eps, stp, hyp, E->grad_scale, false, st);
+          });
+          add_pack_layers(p, gnet, pend_lo[gnet], pend_hi[gnet]);  // the previous bucket of this generator
+          pend_lo[gnet] = lo;
+          pend_hi[gnet] = hi;
+          p.cur_lane = back;
+          return;
+        }
         int nth = 0;  // how many buckets of this generator came before
         for (const GradBucket& b : grad_buckets) nth += b.net == gnet;
         GradBucket gb{CGB_GROUP_G, off, end - off};
@@ -1139,12 +1181,12 @@ void cgb_engine::record_programs() {
     pr.cur_lane = 0;
     emit_gen_forward(pr, &sink, gen[1], CGB_NET_G_BA, fake_B, img[CGB_IMG_REC_A], false, &xcol[2], nullptr);
     emit_gen_backward(pr, &sink, gen[1], gs[0], &real_A, cfg.lambda_A / numel_img, CGB_LOSS_CYCLE_A, GradSrc(), &dxp_img[0]);
-    if (dp) ev_rec_done[CGB_NET_G_BA] = pr.record(0);
+    if (dp || adam_overlap) ev_rec_done[CGB_NET_G_BA] = pr.record(0);
     pr.mark("rec_A fwd+bwd done");
     pr.cur_lane = 1;
     emit_gen_forward(pr, &sink, gen[3], CGB_NET_G_AB, fake_A, img[CGB_IMG_REC_B], false, &xcol[3], nullptr);
     emit_gen_backward(pr, &sink, gen[3], gs[1], &real_B, cfg.lambda_B / numel_img, CGB_LOSS_CYCLE_B, GradSrc(), &dxp_img[1]);
-    if (dp) ev_rec_done[CGB_NET_G_AB] = pr.record(1);
+    if (dp || adam_overlap) ev_rec_done[CGB_NET_G_AB] = pr.record(1);
     pr.mark("rec_B fwd+bwd done");
     // Lanes 2 / 3: the identity pass of one generator, the adversarial term on the fake (D frozen: input gradient
     // only, needed by the fake's backward on lane 0 / 1) and the whole D phase of one discriminator.
@@ -1166,7 +1208,7 @@ void cgb_engine::record_programs() {
       auto idt_bwd = [&]() {
         if (!pair) {
           emit_gen_backward(pr, &sink, GP, GS, &real_in, idt_scale, idt_slot, GradSrc(), nullptr);
-          if (dp) ev_idt_done[gnet] = pr.record(lane);
+          if (dp || adam_overlap) ev_idt_done[gnet] = pr.record(lane);
           pr.mark(side == 0 ? "idt_A fwd+bwd done" : "idt_B fwd+bwd done");
         }
       };
@@ -1214,6 +1256,14 @@ void cgb_engine::record_programs() {
         pr.add(prog_adam[CGB_GROUP_D].ops[i], 0, prog_adam[CGB_GROUP_D].kinds[i]);
       pr.launches = before + prog_adam[CGB_GROUP_D].launches;
     }
+    if (adam_overlap) {  // advance the generators' step counter / bias corrections once, before any bucket's Adam
+      int* stp = adam_step[CGB_GROUP_G];
+      float* hyp = adam_hyper[CGB_GROUP_G];
+      pr.add([E, stp, hyp](cudaStream_t st) {
+        cgb::adam_range(nullptr, nullptr, nullptr, nullptr, 0, E->cfg.beta1, E->cfg.beta2, E->cfg.eps, stp, hyp, E->grad_scale, true, st);
+      });
+      ev_gstep = pr.record(2);
+    }
     pr.mark("Adam(D) done");
     // the passes that produced the fakes
     GradSrc g;
@@ -1241,6 +1291,10 @@ void cgb_engine::record_programs() {
     pr.mark("bwd fake_A done");
     pr.join();
     pr.cur_lane = 0;
+    if (adam_overlap) {  // the chains are done with the lowest layers: refresh the last bucket of each generator
+      add_pack_layers(pr, CGB_NET_G_AB, pend_lo[0], pend_hi[0]);
+      add_pack_layers(pr, CGB_NET_G_BA, pend_lo[1], pend_hi[1]);
+    }
     add_sum_slots(pr, CGB_GROUP_G);
     if (dp && (fp32 || n_dp_buckets <= 1)) {  // one bucket: the whole generator group, at the end
       GradBucket gb{CGB_GROUP_G, 0, group_numel[CGB_GROUP_G]};
@@ -1268,7 +1322,8 @@ void cgb_engine::record_programs() {
     pr.cur_lane = 0;
   }
   const bool lite = std::getenv("CGB_STEM_GEMM") == nullptr && std::getenv("CGB_XCOL_ON_CHAIN") == nullptr;
-  segments[CGB_SEG_STEP].seq = {lite ? &prog_set_inputs_lite : &prog_set_inputs, &prog_step, &prog_adam[CGB_GROUP_G]};
+  segments[CGB_SEG_STEP].seq = {lite ? &prog_set_inputs_lite : &prog_set_inputs, &prog_step};
+  if (!step_has_adam_g) segments[CGB_SEG_STEP].seq.push_back(&prog_adam[CGB_GROUP_G]);
   segments[CGB_SEG_G].seq = {&prog_set_inputs, &prog_cycle, &prog_G};
   segments[CGB_SEG_D].seq = {&prog_D};
   segments[CGB_SEG_ADAM_G].seq = {&prog_adam[0]};

@@ -298,6 +298,7 @@ struct cgb_engine {
   cgb::Program prog_set_inputs_lite;  // staging -> images only (the merged step builds the im2col4 matrices on side lanes)
   cgb::Program prog_set_inputs, prog_cycle, prog_G, prog_D, prog_adam[2], prog_refresh[2];
   cgb::Program prog_step;   // forward + G phase + D phase as ONE schedule (no joins between the phases)
+  bool step_has_adam_g = false;  // prog_step runs the generators' Adam + bf16 refresh itself, bucket by bucket
   cgb::Program prog_step_dp;  // the same without Adam(D): data-parallel callers all-reduce the gradients first
   cgb::Program prog_adams;  // both optimisers side by side
   cgb::Program prog_mod_gen[2], prog_mod_dis[2];
