@@ -116,6 +116,7 @@ struct WgradArgs {
   int a_virtual;           // 1: the dY-side tensor map is a virtual im2col over a row-expanded tensor: dims (64 channels, w,
                            //    row pair, h, n); 64-channel atom a of the GEMM's M extent = row pair a (rows h + 2a, h + 2a + 1)
   int b_virtual;           // the same for the X side (atoms of the GEMM's N extent)
+  int trigger;             // 1: let the next kernel of the lane start launching once the main loop is done (PDL)
 };
 
 // Weight gradient of a stride-1 conv on CTA pairs (wgrad_pair.cu): a pair owns one filter row, 256 output channels and
@@ -127,6 +128,7 @@ struct WgradPairArgs {
   int split_k;                   // K splits
   int n_units, cin_blocks;       // units = kh x cin_blocks x (Cout / 256); pair q works on unit q % n_units, split q / n_units
   int x_ox, x_oy;                // origin of the X patch of tap (0, 0) relative to the dY chunk origin, in the X view's coordinates
+  int trigger;                   // 1: let the next kernel of the lane start launching once the main loop is done (PDL)
   float* g;                      // fp32, accumulated with atomics (must be zeroed)
 };
 

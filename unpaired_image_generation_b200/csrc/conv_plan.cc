@@ -566,6 +566,11 @@ WgradPlan plan_wgrad(const ConvSpec& s, const TensorDesc& x, const TensorDesc& d
   }
   p.args.num_taps = (int)p.taps.size();
   p.flops = 2.0 * x.N * (double)PH * PW * s.Cout * s.Cin * T;
+  // Weight gradients run back to back on side lanes.  An early-launched successor (programmatic dependent launch)
+  // would sit in griddepcontrol.wait holding an SM's worth of shared memory and TMEM that the backward chain's
+  // kernels need: no early trigger by default (CGB_WGRAD_TRIGGER=1 restores it).
+  static const int wtrigger = std::getenv("CGB_WGRAD_TRIGGER") ? std::atoi(std::getenv("CGB_WGRAD_TRIGGER")) : 0;
+  p.args.trigger = wtrigger;
   // stride-1 layers with wide channels: CTA pairs, one filter row per pair (wgrad_pair.cu).  CGB_WGRAD_PAIR=0 disables.
   static const bool pair_on = !(std::getenv("CGB_WGRAD_PAIR") && std::atoi(std::getenv("CGB_WGRAD_PAIR")) == 0);
   // (short reductions stay on the tap-per-CTA kernel: the discriminator's 31 x 31 layer at batch 1 has 16 chunks; measured
@@ -586,6 +591,7 @@ WgradPlan plan_wgrad(const ConvSpec& s, const TensorDesc& x, const TensorDesc& d
     a.n_units = k * a.cin_blocks * (s.Cout / 256);
     a.x_ox = a.x_oy = s.reflect ? 0 : -s.pad;
     a.g = g;
+    a.trigger = wtrigger;
     // K split: about `frac` of the machine's TPCs in pairs, but at least `min_chunks` chunks per pair (the fp32
     // reduction of a pair's 256 x (kw * 128) tile costs about as much as a dozen chunks of MMAs).  The weight gradients
     // run on side lanes next to the backward chain, so the FASTEST launch is not the best one: measured at batch 8

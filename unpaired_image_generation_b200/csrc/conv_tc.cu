@@ -359,7 +359,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
     const bool vec_ok = (args.Cin & 3) == 0 && args.col_map == nullptr;
     mbar_wait_relaxed(tmem_full_bar, 0);
     tc_fence_after();
-    pdl_launch_dependents();
+    if (args.trigger) pdl_launch_dependents();
     // Coalesced reductions: a thread owns one gradient ROW (cout), so a direct red.v4 per thread touches 32
     // different rows per warp instruction (32 L2 transactions of 16 bytes).  The 32 x 32 fp32 block of each
     // chunk is transposed through shared memory (the pipeline buffers are idle now) so that every warp

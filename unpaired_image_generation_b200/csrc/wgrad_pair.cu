@@ -147,7 +147,7 @@ wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     const bool valid = co < a.Cout;
     mbar_wait_relaxed(tmem_full_bar, 0);
     tc_fence_after();
-    pdl_launch_dependents();
+    if (a.trigger) pdl_launch_dependents();
     // a thread owns one gradient row (cout): the 32 x 32 fp32 block of each column chunk is transposed through shared
     // memory (the pipeline buffers are idle now) so that a warp instruction covers 4 rows x 128 contiguous bytes
     float* tstage = reinterpret_cast<float*>(smem) + qw * (32 * 33);
