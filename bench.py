@@ -305,7 +305,7 @@ def run_b200(args):
             pass
         roofline = {
             "bound": "tensor",
-            "kernel": "igemm_patch_kernel<BN,MT,KPS> (persistent tcgen05 patch-resident implicit GEMM), residual-block conv "
+            "kernel": "igemm_patch_kernel<BN,MT,KPS,KA,CG=2> (persistent tcgen05 patch-resident implicit GEMM on CTA pairs), residual-block conv "
                       "256->256 3x3 reflect, fprop + dgrad",
             "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"],
             "traffic": ncu_traffic, "traffic_source": traffic_source,
@@ -316,7 +316,7 @@ def run_b200(args):
             "all_igemm_launches": {"achieved": agg, "frac": agg / peaks["tf_sustained"], "launches_per_step": n_ig,
                                    "ms_per_step_serial": ms_ig, "flops_per_step": fl_ig},
             "other_kernels": {
-                "wgrad_kernel(tcgen05)": {"ms_per_step": ms_wg, "launches": n_wg,
+                "wgrad (wgrad_pair_kernel on the stride-1 layers, wgrad_kernel on the rest; tcgen05)": {"ms_per_step": ms_wg, "launches": n_wg,
                                           "tflops": fl_wg / (ms_wg * 1e-3) / 1e12 if ms_wg > 0 else None},
                 "wgrad_small(im2col4 + tcgen05 GEMM, 3-/1-channel layers)": {"ms_per_step": ms_wd, "launches": n_wd,
                                                    "tflops": fl_wd / (ms_wd * 1e-3) / 1e12 if ms_wd > 0 else None},
