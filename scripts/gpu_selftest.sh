@@ -1,6 +1,6 @@
 #!/bin/bash
 # Stand-alone conv self-test (CPU loop nests as the reference) over a list of settings.
-#   TAG=r02_m CASES="res_small:1 res:1 res:8" SETTINGS="CGB_PATCH_CG=0;CGB_PATCH_CG=1" bash scripts/gpu_selftest.sh
+#   TAG=r02_m CASES="res_small:1 res:1 res:8 head:1:256" SETTINGS="CGB_PATCH_CG=0;CGB_PATCH_CG=1" bash scripts/gpu_selftest.sh
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 TAG=${TAG:-r02}
@@ -10,9 +10,9 @@ BIN=unpaired_image_generation_b200/csrc/build/selftest_conv
 IFS=';' read -ra SETS <<< "${SETTINGS:-CGB_PDL=1}"
 for s in "${SETS[@]}"; do
   for c in ${CASES:-res_small:1 res:1}; do
-    name=${c%%:*}; n=${c##*:}
-    echo "=== $s $name N=$n" >> $OUT
-    env $s timeout ${CASE_TIMEOUT:-120} $BIN $name $n >> $OUT 2>&1
+    IFS=':' read -r name n h <<< "$c"   # name:batch[:spatial extent]
+    echo "=== $s $name N=$n H=${h:-default}" >> $OUT
+    env $s timeout ${CASE_TIMEOUT:-120} $BIN $name $n 0 ${h:-0} >> $OUT 2>&1
     echo "exit $?" >> $OUT
   done
 done

@@ -1,4 +1,5 @@
 // extern "C" surface of libcyclegan_b200.so (declared in include/cyclegan_b200.h).
+#include <cstdio>
 #include <cstring>
 #include <vector>
 
@@ -413,7 +414,15 @@ int cgb_profile_timeline(cgb_engine_t* e, void* stream, char* buf, int buf_cap) 
   CGB_API_BEGIN
   CGB_CHECK(e && e->bound && buf && buf_cap > 0, "bad argument / engine not bound");
   CGB_CHECK(!e->infer_only, "inference-only engine: training entry points are unavailable");
-  const std::string t = buf_cap < 0 ? std::string() : (std::getenv("CGB_PROFILE_OPS") ? e->profile_ops(S(stream), 5) : e->timeline(S(stream)));
+  std::string t;
+  if (const char* hp = std::getenv("CGB_HANG_PROBE")) {  // "steps,stall_ms,fine": development hang hunt (engine.cc hang_probe)
+    int steps = 1000, stall_ms = 5000, fine = 0;
+    std::sscanf(hp, "%d,%d,%d", &steps, &stall_ms, &fine);
+    t = e->hang_probe(S(stream), steps, stall_ms, fine);
+    if (t.empty()) t = "no hang in " + std::to_string(steps) + " replays\n";
+  } else {
+    t = std::getenv("CGB_PROFILE_OPS") ? e->profile_ops(S(stream), 5) : e->timeline(S(stream));
+  }
   std::strncpy(buf, t.c_str(), buf_cap - 1);
   buf[buf_cap - 1] = 0;
   CGB_API_END

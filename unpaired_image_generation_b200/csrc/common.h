@@ -132,9 +132,29 @@ struct WgradPairArgs {
   float* g;                      // fp32, accumulated with atomics (must be zeroed)
 };
 
+// "Taps in N" kernel (conv_tapn.cu): stride-1 k x k conv from 64 channels to <= 4 (generator head; stem input gradient).
+struct TapNArgs {
+  int k;                  // filter taps per side (<= 8)
+  int flip;               // 1: input gradient (filter rows walked backwards, taps gathered backwards)
+  int ox, oy;             // patch origin relative to the tile's output origin, in the activation view's coordinates
+  int tiles_w, tiles_h;   // 8-wide, 16-high output tiles per image
+  int N, num_items;       // images, tiles in total (persistent CTAs loop over blockIdx.x + i * gridDim.x)
+  int Ho, Wo;             // valid output extent
+  int cout;               // real output channels (<= 4); the tensor stores 16
+  long long sN, sH, sW;   // output element strides
+  bf16* out;
+  const float* bias;      // nullptr = none
+  int bias_n;
+  int act;                // Act enum: none or tanh
+};
+
 // Launch with the programmatic-dependent-launch attribute (see ptx.cuh: pdl_wait / pdl_launch_dependents).
 // Every kernel launched through this helper MUST call pdl_wait() before touching global memory.
 bool pdl_enabled();  // CGB_PDL=0 disables (conv_plan.cc)
+bool pair_pdl_enabled();  // programmatic dependent launch for the CTA-pair (cluster) kernels: CGB_PAIR_PDL (conv_plan.cc)
+// Dynamic shared memory a TMEM-hungry kernel requests so that no other TMEM-using CTA fits beside it on the SM
+// (the smallest such CTA, a lite tap-table instantiation, needs 54 KB): 0 when CGB_EXCL_SMEM=0 (conv_plan.cc)
+int tmem_exclusive_smem();
 template <typename... KArgs, typename... Args>
 inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};

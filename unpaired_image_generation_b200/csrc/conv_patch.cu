@@ -399,7 +399,7 @@ static void launch_patch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    attr[1].val.programmaticStreamSerializationAllowed = pair_pdl_enabled() ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 2;
     CGB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, args, pa));

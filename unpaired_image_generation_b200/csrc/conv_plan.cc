@@ -12,6 +12,22 @@ bool pdl_enabled() {
   return on;
 }
 
+// The CTA-pair (2-CTA cluster) kernels are launched as ORDINARY graph nodes, without the programmatic-dependent-launch
+// attribute.  With it the training step hung about once per 20 000 replays at batch 1 (scripts/gpu_stress.py: stalls at
+// replays 3 949, 14 849, 15 999, 30 699 and 38 849 of five runs; 70 000 replays without a stall once the attribute was
+// dropped, 80 000 on the commit before the pair kernels existed).  No bounded mbarrier wait tripped, so the stall is in
+// the launch machinery (cluster kernel as primary / dependent of a programmatic edge), not in the kernels' protocols;
+// the root cause was not isolated.  CGB_PAIR_PDL=1 restores the attribute for experiments.
+bool pair_pdl_enabled() {
+  static const bool on = std::getenv("CGB_PAIR_PDL") ? std::atoi(std::getenv("CGB_PAIR_PDL")) != 0 : false;
+  return on && pdl_enabled();
+}
+
+int tmem_exclusive_smem() {
+  static const bool on = !(std::getenv("CGB_EXCL_SMEM") && std::atoi(std::getenv("CGB_EXCL_SMEM")) == 0);
+  return on ? 184 * 1024 : 0;  // 184 KB + 54 KB (+ 1 KB reserved per CTA) > 227 KB
+}
+
 int padded_rows(int c) { return c <= 16 ? 16 : (c + 63) / 64 * 64; }
 long long packed_wf_elems(const ConvSpec& s) { return (long long)padded_rows(s.CoutS) * s.taps() * s.CinS; }
 long long packed_wt_elems(const ConvSpec& s) { return (long long)padded_rows(s.CinS) * s.taps() * s.CoutS; }
@@ -286,6 +302,47 @@ static bool try_patch(IgemmPlan& p, const TensorDesc& act, bool padded_view, con
   return true;
 }
 
+// Taps-in-N kernel (conv_tapn.cu) for a stride-1 k x k conv-like pass from 64 stored channels to <= 4 real ones
+// (16 stored): the 7 x 7 generator head and the input gradient of the 7 x 7 stem.  CGB_TAPN=0 disables.
+static bool try_tapn(IgemmPlan& p, const TensorDesc& act, bool padded_view, const bf16* w, long long Kw, int k, int cout,
+                     const TensorDesc& out, int Ho, int Wo, int ox, int oy, bool flip, const float* bias, int bias_n,
+                     int actfn, int sm_count) {
+  static const bool on = !(std::getenv("CGB_TAPN") && std::atoi(std::getenv("CGB_TAPN")) == 0);
+  if (!on || k < 5 || k > 8 || act.C != 64 || out.C != 16 || cout > 4 || (actfn != kActNone && actfn != kActTanh)) return false;
+  TapNArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.k = k;
+  a.flip = flip ? 1 : 0;
+  a.ox = ox;
+  a.oy = oy;
+  a.tiles_w = (Wo + 7) / 8;
+  a.tiles_h = (Ho + 15) / 16;
+  a.N = act.N;
+  a.num_items = a.N * a.tiles_w * a.tiles_h;
+  a.Ho = Ho;
+  a.Wo = Wo;
+  a.cout = cout;
+  a.sN = out.sN();
+  a.sH = out.sH();
+  a.sW = out.sW();
+  a.out = out.interior();
+  a.bias = bias;
+  a.bias_n = bias_n;
+  a.act = actfn;
+  p.tapn = true;
+  p.targs = a;
+  p.patch = false;
+  p.BN = 32;
+  p.MT = 1;
+  p.n_blocks = 1;
+  p.n_classes = 1;
+  p.num_tiles = a.num_items;
+  p.num_ctas_m = std::min(a.num_items, sm_count);
+  p.tmA = view_s1(act, padded_view, 64, 16, 16 + k - 1);
+  p.tmB = make_tmap_tapn_weights(w, k, Kw);
+  return true;
+}
+
 IgemmPlan plan_fprop(const ConvSpec& s, const TensorDesc& x, const bf16* wf, const TensorDesc& y, const float* bias,
                      int act, int sm_count) {
   CGB_CHECK(tc_supports_fprop(s), "fprop: channel counts not supported by the tensor-core path");
@@ -381,6 +438,9 @@ IgemmPlan plan_fprop(const ConvSpec& s, const TensorDesc& x, const bf16* wf, con
   }
   bool patched = false;
   if (!s.transposed && s.stride == 1)
+    patched = try_tapn(p, x, s.reflect, wf, Kw, k, s.Cout, y, Ho, Wo, s.reflect ? 0 : -s.pad, s.reflect ? 0 : -s.pad, false,
+                       bias, bias ? s.Cout : 0, act, sm_count);
+  if (!patched && !s.transposed && s.stride == 1)
     patched = try_patch(p, x, s.reflect, wf, s.CoutS, Kw, k, s.CinS, Ho, Wo, s.reflect ? 0 : -s.pad,
                         s.reflect ? 0 : -s.pad, false, sm_count);
   if (!patched) finalize(p, vk, x, wf, s.CoutS, Kw, sm_count);
@@ -489,8 +549,11 @@ IgemmPlan plan_dgrad(const ConvSpec& s, const TensorDesc& dy, const bf16* wt, co
   if (!s.transposed && s.stride == 1) {
     // dx[h] = sum_r dy[h + off - r] w[r]: the patch starts at off - (k - 1) and the filter is walked backwards
     const int off = s.reflect ? 0 : s.pad;
-    patched = try_patch(p, dy, false, wt, s.CinS, Kw, k, s.CoutS, dx.H, dx.W, off - (k - 1), off - (k - 1), true,
-                        sm_count);
+    patched = try_tapn(p, dy, false, wt, Kw, k, s.Cin, dx, dx.H, dx.W, off - (k - 1), off - (k - 1), true, nullptr, 0,
+                       kActNone, sm_count);
+    if (!patched)
+      patched = try_patch(p, dy, false, wt, s.CinS, Kw, k, s.CoutS, dx.H, dx.W, off - (k - 1), off - (k - 1), true,
+                          sm_count);
   }
   if (!patched) finalize(p, vk, dy, wt, s.CinS, Kw, sm_count);
   const double out_px = s.transposed ? (double)dx.H * dx.W : (double)dy.H * dy.W;
@@ -627,6 +690,10 @@ WgradPlan plan_wgrad(const ConvSpec& s, const TensorDesc& x, const TensorDesc& d
 }
 
 void run(const IgemmPlan& p, cudaStream_t stream) {
+  if (p.tapn) {
+    launch_conv_tapn(p.tmA, p.tmB, p.targs, p.num_ctas_m, stream);
+    return;
+  }
   CGB_CHECK(p.args.kiters != nullptr, "igemm plan has no device K-iteration table");
   if (p.patch) {
     launch_igemm_patch(p.BN, p.MT, p.CG, p.tmA, p.tmB, p.args, p.pargs, p.num_ctas_m, p.n_blocks, stream);

@@ -67,6 +67,8 @@ struct IgemmPlan {
   PatchArgs pargs;
   int MT = 1;                 // stacked 16 x 8 M tiles per CTA
   int CG = 1;                 // 2: CTA pairs (cta_group::2) sharing one weight tile
+  bool tapn = false;          // taps-in-N kernel (conv_tapn.cu): k x k, 64 -> <= 4 channels, stride 1
+  TapNArgs targs;
   int num_ctas_m = 0;
 };
 

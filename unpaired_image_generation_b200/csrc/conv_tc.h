@@ -33,6 +33,12 @@ int igemm_patch_smem_budget(); // bytes available for the weight ring + patches
 void launch_wgrad(int BNW, const CUtensorMap& tmDY, const CUtensorMap& tmX, const WgradArgs& args, int m_blocks,
                   cudaStream_t stream);
 
+// 4-D view of a packed weight matrix W[rows >= 5][k * k * 64] for the taps-in-N kernel: dims (64 channels, 4 rows,
+// 8 taps, k filter rows), one box = the whole filter (k x 4 KB: rows tx * 4 + row of filter row ty at ty * 4096).
+CUtensorMap make_tmap_tapn_weights(const bf16* base, int k, long long pitch_elems);
+// Taps-in-N conv (conv_tapn.cu).  tmA: box (64 channels, 16, 1, 16 + k - 1, 1) of the activation view.
+void launch_conv_tapn(const CUtensorMap& tmA, const CUtensorMap& tmB, const TapNArgs& args, int num_ctas, cudaStream_t stream);
+
 // CTA-pair weight gradient of stride-1 convs (wgrad_pair.cu).  tmDY: box (64 channels, 8, 1, 8, 1) of the dY view;
 // tmX: box (64 channels, 8 + kw - 1, 1, 8, 1) of the (padded, for reflect convs) X view.
 void launch_wgrad_pair(const CUtensorMap& tmDY, const CUtensorMap& tmX, const WgradPairArgs& args, cudaStream_t stream);

@@ -2,6 +2,8 @@
 // conv_plan.h (tcgen05 convolutions) and pointwise.h (HBM-bound kernels).
 #include "engine.h"
 
+#include <chrono>
+
 #include <cstdlib>
 #include <cstring>
 
@@ -354,6 +356,62 @@ std::string cgb_engine::timeline(cudaStream_t st) {
   for (cudaEvent_t ev : evs) cudaEventDestroy(ev);
   cudaGraphExecDestroy(exec);
   cudaGraphDestroy(g);
+  return out;
+}
+
+// Hang hunt (development): replays the training step from a graph that carries an external event after every phase
+// marker (fine == 0) or after every op (fine != 0) until a replay does not finish within stall_ms; then reports, per
+// lane, the last marker that completed and the first that did not.  Returns "" when all `steps` replays finished.
+std::string cgb_engine::hang_probe(cudaStream_t st, int steps, int stall_ms, int fine) {
+  CGB_CHECK(st != nullptr, "hang probe needs a non-default stream");
+  lane_streams[0] = st;
+  for (int l = 1; l < kLanes; ++l)
+    if (!lane_streams[l]) CGB_CUDA(cudaStreamCreateWithFlags(&lane_streams[l], cudaStreamNonBlocking));
+  for (const Program* p : segments[CGB_SEG_STEP].seq) p->run(st);  // eager warm-up
+  CGB_CUDA(cudaStreamSynchronize(st));
+  std::vector<Program::Mark> marks;
+  std::vector<cudaEvent_t> evs;
+  size_t next_event = 0;
+  cudaGraph_t g = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  CGB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+  for (const Program* p : segments[CGB_SEG_STEP].seq) p->run_lanes(lane_streams, evs, &next_event, &marks, fine != 0);
+  CGB_CUDA(cudaStreamEndCapture(st, &g));
+  CGB_CUDA(cudaGraphInstantiate(&exec, g, 0));
+  cudaEvent_t done;
+  CGB_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+  std::string out;
+  for (int i = 0; i < steps && out.empty(); ++i) {
+    CGB_CUDA(cudaGraphLaunch(exec, st));
+    if (i % 16 != 15 && i != steps - 1) continue;  // keep a few replays in flight, like a training loop
+    CGB_CUDA(cudaEventRecord(done, st));
+    const auto t0 = std::chrono::steady_clock::now();
+    while (cudaEventQuery(done) == cudaErrorNotReady) {
+      if (std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count() > stall_ms) {
+        out = "HANG near replay " + std::to_string(i) + " (" + std::to_string(marks.size()) + " markers)\n";
+        int last_done[kLanes], first_open[kLanes];
+        for (int l = 0; l < kLanes; ++l) last_done[l] = first_open[l] = -1;
+        for (int m = 0; m < (int)marks.size(); ++m) {
+          const bool ok = cudaEventQuery(marks[m].ev) == cudaSuccess;
+          if (ok) last_done[marks[m].lane] = m;
+          else if (first_open[marks[m].lane] < 0) first_open[marks[m].lane] = m;
+        }
+        for (int l = 0; l < kLanes; ++l) {
+          out += "lane " + std::to_string(l) + ": last finished [" + (last_done[l] >= 0 ? marks[last_done[l]].label : std::string("-")) +
+                 "]  first unfinished [" + (first_open[l] >= 0 ? marks[first_open[l]].label : std::string("-")) + "]\n";
+        }
+        break;
+      }
+    }
+  }
+  if (out.empty()) {
+    CGB_CUDA(cudaStreamSynchronize(st));
+    for (const Program::Mark& m : marks) cudaEventDestroy(m.ev);
+    for (cudaEvent_t ev : evs) cudaEventDestroy(ev);
+    cudaEventDestroy(done);
+    cudaGraphExecDestroy(exec);
+    cudaGraphDestroy(g);
+  }  // (after a hang nothing can be released: the caller exits the process)
   return out;
 }
 

@@ -122,7 +122,7 @@ struct Program {
     cudaEvent_t ev;
   };
   void run_lanes(cudaStream_t* lane_streams, std::vector<cudaEvent_t>& events, size_t* next_event,
-                 std::vector<Mark>* timeline = nullptr) const {
+                 std::vector<Mark>* timeline = nullptr, bool mark_ops = false) const {
     std::vector<cudaEvent_t> rec(n_records, nullptr);
     for (size_t i = 0; i < ops.size(); ++i) {
       if (kinds[i] == kOpRecord || kinds[i] == kOpWait) {
@@ -160,6 +160,14 @@ struct Program {
         CGB_CUDA(cudaStreamWaitEvent(lane_streams[lanes[i]], ev, 0));
       } else {
         ops[i](lane_streams[lanes[i]]);
+        if (timeline && mark_ops) {  // hang probe: an external event after every op tells which op never finished
+          Mark m;
+          m.label = "#" + std::to_string(i) + " " + names[i];
+          m.lane = lanes[i];
+          CGB_CUDA(cudaEventCreateWithFlags(&m.ev, cudaEventDisableTiming));
+          CGB_CUDA(cudaEventRecordWithFlags(m.ev, lane_streams[lanes[i]], cudaEventRecordExternal));
+          timeline->push_back(m);
+        }
       }
     }
   }
@@ -327,6 +335,7 @@ struct cgb_engine {
   void run_segment(int seg, cudaStream_t st);
   void drop_graphs();
   std::string timeline(cudaStream_t st);
+  std::string hang_probe(cudaStream_t st, int steps, int stall_ms, int fine);
   std::string profile_ops(cudaStream_t st, int reps);
 
   ~cgb_engine();

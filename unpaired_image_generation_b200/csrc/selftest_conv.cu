@@ -250,9 +250,9 @@ static int run_case(const std::string& name, ConvSpec s, int N, int H, int W, in
     IgemmPlan p = plan_fprop(s, x, d_wf, y, d_bias, act, sm_count);
     (void)force_bn;
     p.args.kiters = dev_upload(p.kiters);
-    printf("  fprop: BN=%d BK=%d cluster %dx%d tiles=%d nblk=%d classes=%d kiters=%zu patch=%d MT=%d CG=%d ctas_m=%d bstages=%d lite=%d\n", p.BN,
+    printf("  fprop: BN=%d BK=%d cluster %dx%d tiles=%d nblk=%d classes=%d kiters=%zu patch=%d MT=%d CG=%d ctas_m=%d bstages=%d lite=%d tapn=%d\n", p.BN,
            p.BK, p.CM, p.CN, p.num_tiles, p.n_blocks, p.n_classes, p.kiters.size(), (int)p.patch, p.MT, p.CG, p.num_ctas_m,
-           p.patch ? p.pargs.b_stages : 0, (int)p.lite);
+           p.patch ? p.pargs.b_stages : 0, (int)p.lite, (int)p.tapn);
     run(p, 0);
     CGB_CUDA(cudaDeviceSynchronize());
     std::vector<bf16> yb((size_t)y.elems());
@@ -321,9 +321,9 @@ static int run_case(const std::string& name, ConvSpec s, int N, int H, int W, in
     CGB_CUDA(cudaMemset(dx.ptr, 0xFF, dx.elems() * sizeof(bf16)));
     IgemmPlan p = plan_dgrad(s, dy, d_wt, dx, sm_count);
     p.args.kiters = dev_upload(p.kiters);
-    printf("  dgrad: BN=%d BK=%d cluster %dx%d tiles=%d nblk=%d classes=%d kiters=%zu out %dx%d patch=%d MT=%d CG=%d ctas_m=%d bstages=%d lite=%d\n",
+    printf("  dgrad: BN=%d BK=%d cluster %dx%d tiles=%d nblk=%d classes=%d kiters=%zu out %dx%d patch=%d MT=%d CG=%d ctas_m=%d bstages=%d lite=%d tapn=%d\n",
            p.BN, p.BK, p.CM, p.CN, p.num_tiles, p.n_blocks, p.n_classes, p.kiters.size(), DH, DW, (int)p.patch, p.MT, p.CG,
-           p.num_ctas_m, p.patch ? p.pargs.b_stages : 0, (int)p.lite);
+           p.num_ctas_m, p.patch ? p.pargs.b_stages : 0, (int)p.lite, (int)p.tapn);
     run(p, 0);
     CGB_CUDA(cudaDeviceSynchronize());
     std::vector<bf16> db((size_t)dx.elems());

@@ -76,4 +76,22 @@ CUtensorMap make_tmap_2d(const bf16* base, long long rows, long long cols, long 
   return m;
 }
 
+CUtensorMap make_tmap_tapn_weights(const bf16* base, int k, long long pitch_elems) {
+  CGB_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "matrix base must be 16-byte aligned");
+  CGB_CHECK(k >= 2 && k <= 8, "taps-in-N weights: 2 <= k <= 8");
+  CUtensorMap m;
+  // element (ci, row, tx, ty) = W[row][(ty * k + tx) * 64 + ci]; tx runs to 8: for k < 8 the extra taps read the next
+  // filter row's first taps (in bounds: the matrix has >= 5 rows); their output columns are never gathered
+  cuuint64_t gdim[4] = {64, 4, 8, (cuuint64_t)k};
+  cuuint64_t gstr[3] = {(cuuint64_t)pitch_elems * 2, 128, (cuuint64_t)k * 128};
+  cuuint32_t box[4] = {64, 4, 8, (cuuint32_t)k};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CGB_CHECK(gstr[0] % 16 == 0, "matrix pitch must be a multiple of 16 bytes");
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(base), gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CGB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(4d) failed with code " + std::to_string((int)r));
+  return m;
+}
+
 }  // namespace cgb

@@ -197,8 +197,11 @@ void launch_wgrad_pair(const CUtensorMap& tmDY, const CUtensorMap& tmX, const Wg
   CGB_CHECK(a.kw >= 1 && a.kw <= 4, "wgrad pairs: at most 4 taps per filter row (4 x 128 TMEM columns)");
   CGB_CHECK(a.Cout % 256 == 0 && a.Cin % 128 == 0, "wgrad pairs: Cout % 256 == 0 and Cin % 128 == 0 required");
   const int stage = kDyBytes + (8 + a.kw - 1) * 8 * 128;
-  const int smem = 1024 + kWpStages * stage + 256;
+  int smem = 1024 + kWpStages * stage + 256;
   CGB_CHECK(smem <= kWpSmemMax, "wgrad pairs: shared memory budget exceeded");
+  // This kernel allocates all 512 TMEM columns: no other TMEM-using CTA may share its SM (a co-resident CTA of the
+  // low-shared-memory tap-table instantiations would make tcgen05.alloc block).  Request enough shared memory to own the SM.
+  if (tmem_exclusive_smem() > smem) smem = tmem_exclusive_smem();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2u * (unsigned)(a.n_units * a.split_k));
   cfg.blockDim = dim3(192);
@@ -210,7 +213,7 @@ void launch_wgrad_pair(const CUtensorMap& tmDY, const CUtensorMap& tmX, const Wg
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  attr[1].val.programmaticStreamSerializationAllowed = pair_pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
   CGB_CUDA(cudaLaunchKernelEx(&cfg, wgrad_pair_kernel, tmDY, tmX, a));
