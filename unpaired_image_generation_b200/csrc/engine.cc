@@ -1119,7 +1119,13 @@ void cgb_engine::record_programs() {
       bf16* arena = pack[CGB_GROUP_G];
       p.add([pm, tb, cnt, mx, arena](cudaStream_t st) { pack_weights(pm, tb, cnt, mx, arena, st); });
     };
-    static const int n_dp_buckets = std::getenv("CGB_DP_BUCKETS") ? std::max(1, std::atoi(std::getenv("CGB_DP_BUCKETS"))) : 4;
+    // Buckets per generator.  Data parallel: 2 -- every bucket is one more collective on the communication stream and at
+    // 8 GPUs their latencies, not their bytes, are what is left exposed (measured on 8 x B200, batch 1 per GPU,
+    // profiles/r02_oo_dp8_sweep.txt: 4 buckets 4.683 ms/step, 2 buckets 4.588, one bucket after the step 5.07).
+    // Single GPU (in-step Adam): 4.  CGB_DP_BUCKETS / CGB_ADAM_BUCKETS override.
+    static const int dp_buckets = std::getenv("CGB_DP_BUCKETS") ? std::max(1, std::atoi(std::getenv("CGB_DP_BUCKETS"))) : 2;
+    static const int adam_buckets = std::getenv("CGB_ADAM_BUCKETS") ? std::max(1, std::atoi(std::getenv("CGB_ADAM_BUCKETS"))) : 4;
+    const int n_dp_buckets = dp ? dp_buckets : adam_buckets;
     // Single-GPU program: the same bucket boundaries drive the generators' optimiser INSIDE the step.  Once a bucket is
     // final, Adam on that range runs on lane 2 (G_AB) / 3 (G_BA) -- idle after the D phase -- while the backward chains
     // continue; the bf16 packs of a bucket are refreshed when the NEXT bucket of the same generator is final (the chain
