@@ -272,3 +272,17 @@ def test_image_pool_on_device_matches_standin():
     assert used_history
     with pytest.raises(RuntimeError, match="image pool is not enabled"):
         _trainer()[0]._ensure_engine(torch.empty(1, 3, 64, 64, device="meta")).get_image("pool_fake_B")
+
+
+def test_step_replays_do_not_stall():
+    """1 500 back-to-back replays of the batch-1 step in a child process with a progress watchdog
+    (scripts/gpu_stress.py).  Round 2 found a stall of the launch machinery about once per 20 000 replays when the
+    CTA-pair kernels carried the programmatic-dependent-launch attribute; the long runs that
+    established the fix (70 000 replays) are in profiles/r02_ll_stress_pairpdl0.txt -- this is the quick guard."""
+    _need_gpu()
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "gpu_stress.py"), "long", "1500", "1"],
+                       capture_output=True, text=True, timeout=300, env=dict(os.environ, STRESS_STALL_S="20"))
+    assert r.returncode == 0 and "ok 1500 steps" in r.stdout, r.stdout[-1000:] + r.stderr[-1000:]
