@@ -15,6 +15,7 @@ import json
 import os
 import statistics
 import subprocess
+import threading
 import sys
 import tempfile
 import time
@@ -150,6 +151,28 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------
 # B200 arm
 # ----------------------------------------------------------------------------------------------
+class StallWatchdog:
+    """A device-side stall must not hold the caller until its own time limit: if no phase of the bench completes for
+    `limit_s` seconds, say so on stdout / stderr and leave the process (the step graph is replayed asynchronously, so
+    a stalled kernel would otherwise block the next synchronisation forever)."""
+
+    def __init__(self, limit_s: float):
+        self.limit_s, self.t, self.what = limit_s, time.time(), "start"
+        threading.Thread(target=self._run, daemon=True).start()
+
+    def beat(self, what: str):
+        self.t, self.what = time.time(), what
+
+    def _run(self):
+        while True:
+            time.sleep(5.0)
+            if time.time() - self.t > self.limit_s:
+                msg = f"bench.py: no progress for {self.limit_s:.0f} s after phase '{self.what}' (device stall?)"
+                print(json.dumps({"error": msg}), flush=True)
+                print(msg, file=sys.stderr, flush=True)
+                os._exit(3)
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -180,6 +203,7 @@ def run_b200(args):
             os.close(saved_stdout)
     peaks = load_peaks()
     batch, size = args.batch, args.size
+    dog = StallWatchdog(float(os.environ.get("CGB_BENCH_STALL_S", "300")))
 
     G_AB, G_BA = cgb.Generator(seed=1), cgb.Generator(seed=2)
     D_A, D_B = cgb.Discriminator(seed=3), cgb.Discriminator(seed=4)
@@ -207,9 +231,11 @@ def run_b200(args):
     # ---- value: whole-job throughput, device-resident inputs.  The timed region is EXACTLY --steps steps, bracketed by
     # barrier + synchronize; it is repeated back to back until at least ~1 s of device time has been measured (20 steps
     # are only 0.1 s) and the value is the mean over all repetitions, each reduced with MAX over the ranks.
+    dog.beat("engine created")
     for _ in range(max(args.warmup, 3)):
         device_step()
     barrier()
+    dog.beat("warm-up")
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -227,6 +253,7 @@ def run_b200(args):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         rep_ms.append(float(t.item()))
+        dog.beat(f"timed repetition {len(rep_ms)}")
         if len(rep_ms) == 1:
             reps = int(min(50, max(1, -(-1000.0 // rep_ms[0]))))  # same on every rank: derived from the reduced time
     clocks = sampler.stop() if rank == 0 else None
@@ -241,6 +268,7 @@ def run_b200(args):
     e2e_steps = args.steps
     for _ in range(e2e_steps):
         losses = tr.train_step(host_A, host_B)
+        dog.beat("e2e step")
     barrier()
     e2e_sec = (time.perf_counter() - t0) / e2e_steps
     te = torch.tensor([e2e_sec], dtype=torch.float64, device="cuda")
@@ -328,8 +356,10 @@ def run_b200(args):
         }
         # ---- cpu_baseline: the stand-in on this box's host cores, bounded sample
         cpu = None
+        dog.beat("roofline profiling")
         if not args.no_cpu_baseline and world == 1:  # rank 0 at N = 1 only (the other ranks would idle in the barrier)
             times, cores = time_standin(1, size, 2, 1)
+            dog.beat("cpu baseline")
             sec = min(times)
             cpu = {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"best of 2 full train steps after 1 warm-up of oracle/cyclegan_standin.py (fp32 torch CPU, "
@@ -362,6 +392,7 @@ def run_b200(args):
         for key, (xb, xs) in (("configs2_256_b8", (8, 256)), ("configs3_512_b4", (4, 512))):
             if (xb, xs) == (batch, size):
                 continue
+            dog.beat("before " + key)
             try:
                 extras[key] = measure_extra(cgb, torch, dist, world, rank, xb, xs, max(3, args.steps // 2), peaks)
             except Exception as ex:  # never lose the headline line

@@ -1,6 +1,7 @@
 """CPU-only tests: the C-ABI library loads and exports what include/cyclegan_b200.h declares, the
 host-side inventory / layout logic matches the stand-in, and the product fails loudly without a GPU."""
 import ctypes
+import json
 import os
 import re
 
@@ -163,3 +164,13 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_bench_stall_watchdog_leaves_the_process():
+    """bench.py must not sit on a stalled device until the caller's time limit: the watchdog reports the phase and exits"""
+    import subprocess
+    import sys
+    code = "import time, bench\nd = bench.StallWatchdog(1.0)\nd.beat('unit test')\ntime.sleep(30)\n"
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, timeout=60)
+    assert r.returncode == 3
+    assert "no progress" in json.loads(r.stdout.strip().splitlines()[-1])["error"]
